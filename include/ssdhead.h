@@ -1,0 +1,151 @@
+/*
+ * ssdhead.h - C ABI of libssdhead.so: the SSD multibox head path on B200 (sm_100a).
+ *
+ * The reference (nitishsaDire/objectDetection_ssd) is pure Python and has no FFI; the
+ * boundary it offers for this path is the call surface of Losses.py / Util.py.  Every
+ * entry point below names the reference function (file:line under /root/reference) it
+ * replaces; objectdetection_ssd_b200/{Losses,Util}.py bind them with ctypes under the
+ * reference's own names.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types; all tensors dense row-major fp32
+ *     unless stated; "dev" pointers are CUDA device pointers, "host" pointers host memory.
+ *   - return 0 = ok, <0 = SSDHEAD_E_* (bad argument / unsupported shape), >0 = cudaError_t.
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     allocate nothing, keep no global state and are re-entrant across streams when each
+ *     call has its own workspace.  The caller owns every buffer.
+ *   - there is no CPU fallback anywhere in this library.
+ *   - gt layout: boxes packed [sumG,4] fractional xyxy, classes [sumG] fp32 (Dataset.py:26),
+ *     offsets int32 [B+1] (the cumsum of Losses.py:130).  Background class id = C-1
+ *     (Losses.py:171).  Prior tables [P,4]: `pri_xyxy` and `pri_cxcywh` (Losses.py:6-7).
+ *   - tie rules T1-T8 of SURVEY.md section 8.1 (repeated in DESIGN.md) are implemented exactly.
+ */
+#ifndef SSDHEAD_H_
+#define SSDHEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDHEAD_ABI_VERSION 1
+
+#define SSDHEAD_E_BADARG      (-1)  /* null pointer / negative size */
+#define SSDHEAD_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for */
+#define SSDHEAD_E_WORKSPACE   (-3)  /* workspace too small */
+#define SSDHEAD_E_ALIGN       (-4)  /* pointer not 16-byte aligned */
+#define SSDHEAD_E_STATE       (-5)  /* host context misuse */
+
+/* which workspace ssdhead_workspace_bytes() sizes */
+#define SSDHEAD_WS_MATCH  0
+#define SSDHEAD_WS_LOSS   1
+#define SSDHEAD_WS_DETECT 2
+#define SSDHEAD_WS_NMS    3
+
+int         ssdhead_abi_version(void);
+const char* ssdhead_error_string(int code);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t    ssdhead_launch_count(void);
+
+/* Bytes of device workspace an entry point needs.  `n` = total gt count (MATCH),
+ * max candidates per (image,class) the caller wants to allow (DETECT/NMS; 0 = P). */
+size_t ssdhead_workspace_bytes(int which, int B, int P, int C, int n);
+
+/* ---- box format / offsets: Util.py:93-96, 57-63, 98-102, 86-91 ------------------- */
+int ssdhead_cxcywh_to_xyxy(const float* in_dev, float* out_dev, int n, void* stream);   /* xywh_to_xyxy      */
+int ssdhead_xyxy_to_cxcywh(const float* in_dev, float* out_dev, int n, void* stream);   /* xyxy_to_xywh      */
+int ssdhead_encode(const float* cxcywh_dev, const float* pri_cxcywh_dev, float* out_dev, int n, void* stream); /* get_offsets_coords */
+int ssdhead_decode(const float* gcxgcy_dev, const float* pri_cxcywh_dev, float* out_dev, int n, void* stream); /* gcxgcy_to_cxcy     */
+
+/* ---- dense IoU: find_intersection + get_jaccard_tensor1, Util.py:252-265, 288-301 -- */
+int ssdhead_iou_matrix(const float* a_xyxy_dev, int n1, const float* b_xyxy_dev, int n2,
+                       float* out_dev /*[n1,n2]*/, void* stream);
+
+/* ---- matching: Losses.py:150-171 (batched) / map_prior_to_bb Util.py:333-352 --------
+ * Outputs: best_prior int32 [sumG] (argmax over priors per gt, T2);
+ *          npos int32 [B+1]: positives per image, npos[B] = batch total;
+ *          obj_idx int32 [B,P] GLOBAL gt index after the forced override (nullable);
+ *          cls     int32 [B,P] class per prior, C-1 = background (nullable).           */
+int ssdhead_match(const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                  const float* pri_xyxy_dev, int B, int P, int C, int sumG, float pos_iou,
+                  int32_t* best_prior_dev, int32_t* npos_dev, int32_t* obj_idx_dev, int32_t* cls_dev,
+                  void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- multibox loss fwd(+bwd): ssd / ssd1_, Losses.py:119-199 ------------------------
+ * One pass: conf rows are staged once into the shared memory of a thread-block cluster
+ * per image, CE + hard-negative mining (descending CE, ties -> lower prior index, T4)
+ * and, when grad_* are non-null, the gradients for unit upstream gradients are written
+ * from that same staging.  `npos_dev` is ssdhead_match's output; `npos_norm_dev` points
+ * to the int32 positive count the losses/gradients are normalised by (npos_dev+B on one
+ * GPU; the all-reduced total when the batch is sharded by image).
+ * Outputs: sums double[2] = { sum |loc-enc| over positives, sum CE over positives+mined };
+ *          losses float[2] = { sums[0]/(4N), sums[1]/N }  (loc_loss, conf_loss of ssd());
+ *          grad_loc [B,P,4], grad_conf [B,P,C] dense (nullable as a pair);
+ *          mined_mask uint32 [B, ceil(P/32)] bit p = mined negative (nullable; debug tap);
+ *          ce [B,P] per-prior cross entropy (nullable; debug tap).                     */
+int ssdhead_multibox_loss(const float* loc_dev, const float* conf_dev,
+                          const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                          const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                          const int32_t* best_prior_dev, const int32_t* npos_dev, const int32_t* npos_norm_dev,
+                          int B, int P, int C, int neg_ratio, float pos_iou,
+                          double* sums_dev, float* losses_dev,
+                          float* grad_loc_dev, float* grad_conf_dev,
+                          uint32_t* mined_mask_dev, float* ce_dev,
+                          void* ws_dev, size_t ws_bytes, void* stream);
+
+/* losses[0..1] = { sums[0]/(4N), sums[1]/N } with N read from npos_norm_dev: used after the
+ * loss sums of a sharded batch have been all-reduced. */
+int ssdhead_finish_loss(const double* sums_dev, const int32_t* npos_norm_dev, float* losses_dev, void* stream);
+
+/* grad_loc *= gout[0], grad_conf *= gout[1] (autograd upstream gradients of the two scalars,
+ * read on the device; the kernel returns without touching memory when both are 1). */
+int ssdhead_scale_grads(float* grad_loc_dev, size_t n_loc, float* grad_conf_dev, size_t n_conf,
+                        const float* gout_dev /*[2]*/, void* stream);
+
+/* ---- detection: inference(), Losses.py:11-98 ----------------------------------------
+ * Per image: decode, softmax, per foreground class (0..C-2) keep prob >= min_score, sort by
+ * descending prob (ties -> lower prior, T5), greedy NMS (suppress iou >= iou_thr), concatenate
+ * class-major, and if more than top_k survive take the global top_k by descending prob
+ * (ties -> earlier class-major position, T7).  Boxes are fractional xyxy, not clamped.
+ * Outputs: out_boxes [B,top_k,4], out_prob [B,top_k], out_cls int32 [B,top_k],
+ *          out_prior int32 [B,top_k] (prior id of each detection), out_cnt int32 [B].      */
+int ssdhead_detect(const float* loc_dev, const float* conf_dev, const float* pri_cxcywh_dev,
+                   int B, int P, int C, float min_score, float iou_thr, int top_k,
+                   float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
+                   int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Stage-isolated twin of ssdhead_detect taking decoded boxes [B,P,4] (cxcywh) and class
+ * probabilities [B,P,C] as given (the oracle's), so keep lists can be compared bit-exactly. */
+int ssdhead_detect_from_scores(const float* boxes_cxcywh_dev, const float* probs_dev,
+                               int B, int P, int C, float min_score, float iou_thr, int top_k,
+                               float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
+                               int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- host-buffer front end (pinned staging + streams owned by the context) -----------
+ * The same path for callers whose tensors live in host memory (what the reference's CPU
+ * path sees).  Copies are pipelined against the kernels in image chunks. */
+typedef struct ssdhead_ctx ssdhead_ctx;
+int  ssdhead_ctx_create(ssdhead_ctx** out, int device, int maxB, int P, int C, int max_sumG, int top_k,
+                        const float* pri_cxcywh_host);
+void ssdhead_ctx_destroy(ssdhead_ctx* ctx);
+/* page-locked host allocation helpers (so callers can hand in pinned buffers) */
+void* ssdhead_host_alloc(size_t bytes);
+void  ssdhead_host_free(void* p);
+
+/* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair. */
+int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host,
+                                   const float* gt_xyxy_host, const float* gt_cls_host, const int32_t* gt_off_host,
+                                   int B, int neg_ratio, float pos_iou,
+                                   float* losses_host, float* grad_loc_host, float* grad_conf_host);
+/* inference() over a batch with host buffers; outputs as ssdhead_detect. */
+int ssdhead_ctx_detect_host(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host, int B,
+                            float min_score, float iou_thr,
+                            float* out_boxes_host, float* out_prob_host, int32_t* out_cls_host,
+                            int32_t* out_prior_host, int32_t* out_cnt_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDHEAD_H_ */

@@ -1,0 +1,197 @@
+"""Host-side operator layer over libssdhead.so: device buffers, streams and autograd plumbing.
+
+PyTorch is used here only for device memory, the current CUDA stream, autograd wiring and
+(optionally) ``torch.distributed``; all arithmetic of the path runs in the CUDA kernels of
+``csrc/`` reached through the C ABI (``include/ssdhead.h``).  There is no CPU fallback: every
+entry point raises if the tensors cannot be placed on a CUDA device or the library is missing.
+
+Reference call sites this layer serves: ``ssd`` (Losses.py:119-134), ``ssd1_`` (Losses.py:136-199),
+``map_prior_to_bb`` (Util.py:333-352), ``inference`` (Losses.py:11-98).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .priors import cxcywh_to_xyxy_host
+
+POS_IOU = 0.5      # Losses.py:171
+NEG_RATIO = 3      # Losses.py:189
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def require_cuda(dev) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("objectdetection_ssd_b200: no CUDA device - the SSD head path has no CPU fallback")
+    dev = torch.device(dev)
+    if dev.type != "cuda":
+        raise RuntimeError(f"objectdetection_ssd_b200: expected a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class PackedGT:
+    """Ragged gt lists packed once: boxes [sumG,4] f32, classes [sumG] f32, offsets int32 [B+1]
+    (host-side equivalent of Losses.py:129-130; no per-image synchronisation)."""
+
+    def __init__(self, boxes: Sequence[torch.Tensor], classes: Sequence[torch.Tensor], dev: torch.device):
+        counts = [int(b.shape[0]) if b.dim() > 0 else 0 for b in boxes]
+        for i, n in enumerate(counts):
+            if n == 0:
+                # the reference fails the same way on an image without objects (Losses.py:153, max over an empty dim)
+                raise IndexError(f"image {i} has no ground-truth box: max() over an empty dimension")
+        self.B = len(counts)
+        self.sumG = sum(counts)
+        self.maxG = max(counts) if counts else 0
+        off = [0]
+        for n in counts:
+            off.append(off[-1] + n)
+        self.off_host = off
+        self.boxes = torch.cat([b.reshape(-1, 4) for b in boxes]).to(device=dev, dtype=torch.float32).contiguous()
+        self.classes = torch.cat([c.reshape(-1) for c in classes]).to(device=dev, dtype=torch.float32).contiguous()
+        self.off = torch.tensor(off, dtype=torch.int32).pin_memory().to(dev, non_blocking=True) \
+            if torch.cuda.is_available() else torch.tensor(off, dtype=torch.int32)
+
+
+class MultiboxHead:
+    """Prior tables and workspaces of one CUDA device."""
+
+    def __init__(self, priors_cxcywh: torch.Tensor, device=None, num_classes: int = 21):
+        self.dev = require_cuda(device if device is not None else "cuda")
+        self.lib = _lib.load()
+        pc = priors_cxcywh.detach().to("cpu", torch.float32).contiguous()
+        self.P = int(pc.shape[0])
+        self.C = int(num_classes)
+        self.pri_cxcywh = pc.to(self.dev)
+        self.pri_xyxy = cxcywh_to_xyxy_host(pc).to(self.dev)     # same fp32 ops as Util.py:93-96
+        self._ws = {}
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, which: int, B: int, n: int) -> torch.Tensor:
+        need = int(self.lib.ssdhead_workspace_bytes(which, B, self.P, self.C, n))
+        if need == 0:
+            raise RuntimeError("ssdhead: unsupported shape for this entry point "
+                               f"(B={B}, P={self.P}, C={self.C})")
+        cur = self._ws.get(which)
+        if cur is None or cur.numel() < need:
+            cur = torch.zeros(need + 4096, dtype=torch.uint8, device=self.dev)
+            self._ws[which] = cur
+        return cur
+
+    # ------------------------------------------------------------------ match
+    def match(self, gt: PackedGT, want_maps: bool = False, pos_iou: float = POS_IOU):
+        """Losses.py:150-171.  Returns dict(best_prior, npos[B+1], obj[B,P]|None, cls[B,P]|None)."""
+        B = gt.B
+        best_prior = torch.empty(max(gt.sumG, 1), dtype=torch.int32, device=self.dev)
+        npos = torch.empty(B + 1, dtype=torch.int32, device=self.dev)
+        obj = cls = None
+        if want_maps:
+            obj = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
+            cls = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
+        ws = self._workspace(_lib.WS_MATCH, B, gt.sumG)
+        _lib.check(self.lib.ssdhead_match(
+            _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off), _ptr(self.pri_xyxy),
+            B, self.P, self.C, gt.sumG, pos_iou,
+            _ptr(best_prior), _ptr(npos), _ptr(obj), _ptr(cls),
+            _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_match")
+        return dict(best_prior=best_prior, npos=npos, obj=obj, cls=cls)
+
+    # ------------------------------------------------------------------ loss
+    def loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedGT, with_grads: bool,
+             neg_ratio: int = NEG_RATIO, pos_iou: float = POS_IOU, taps: bool = False,
+             group=None, match=None):
+        """Losses.py:119-199 on device.  Returns dict(losses[2], sums[2], npos, grad_loc, grad_conf, ...).
+
+        ``group``: a torch.distributed process group over which the batch is sharded by image;
+        the positive count is all-reduced before the loss kernel (it scales the gradients) and
+        the loss sums after it."""
+        B, P, C = int(loc.shape[0]), self.P, self.C
+        if tuple(loc.shape) != (B, P, 4) or tuple(conf.shape) != (B, P, C) or gt.B != B:
+            raise ValueError(f"expected loc [B,{P},4] and conf [B,{P},{C}] with B gt lists, got "
+                             f"{tuple(loc.shape)}, {tuple(conf.shape)}, {gt.B}")
+        loc = loc.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        conf = conf.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        m = match if match is not None else self.match(gt, pos_iou=pos_iou)
+        npos = m["npos"]
+        npos_norm = npos[B:B + 1]
+        if group is not None:
+            import torch.distributed as dist
+            npos_norm = npos_norm.clone()
+            dist.all_reduce(npos_norm, op=dist.ReduceOp.SUM, group=group)
+        sums = torch.empty(2, dtype=torch.float64, device=self.dev)
+        losses = torch.empty(2, dtype=torch.float32, device=self.dev)
+        grad_loc = grad_conf = mined = ce = None
+        if with_grads:
+            grad_loc = torch.empty_like(loc)
+            grad_conf = torch.empty_like(conf)
+        if taps:
+            mined = torch.empty(B, (P + 31) // 32, dtype=torch.int32, device=self.dev)
+            ce = torch.empty(B, P, dtype=torch.float32, device=self.dev)
+        ws = self._workspace(_lib.WS_LOSS, B, 0)
+        _lib.check(self.lib.ssdhead_multibox_loss(
+            _ptr(loc), _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off),
+            _ptr(self.pri_xyxy), _ptr(self.pri_cxcywh),
+            _ptr(m["best_prior"]), _ptr(npos), _ptr(npos_norm),
+            B, P, C, int(neg_ratio), float(pos_iou),
+            _ptr(sums), _ptr(losses), _ptr(grad_loc), _ptr(grad_conf), _ptr(mined), _ptr(ce),
+            _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_multibox_loss")
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            _lib.check(self.lib.ssdhead_finish_loss(_ptr(sums), _ptr(npos_norm), _ptr(losses),
+                                                    _stream(self.dev)), "ssdhead_finish_loss")
+        return dict(losses=losses, sums=sums, npos=npos, npos_norm=npos_norm, grad_loc=grad_loc,
+                    grad_conf=grad_conf, mined_mask=mined, ce=ce, best_prior=m["best_prior"])
+
+    def scale_grads(self, grad_loc: torch.Tensor, grad_conf: torch.Tensor, gout: torch.Tensor):
+        _lib.check(self.lib.ssdhead_scale_grads(_ptr(grad_loc), grad_loc.numel(), _ptr(grad_conf),
+                                                grad_conf.numel(), _ptr(gout), _stream(self.dev)),
+                   "ssdhead_scale_grads")
+
+
+class _MultiboxLossFn(torch.autograd.Function):
+    """Autograd node for ``ssd()``: the forward kernel already wrote the gradients for unit upstream
+    gradients; backward rescales them on the device only if the upstream gradients are not 1."""
+
+    @staticmethod
+    def forward(ctx, loc, conf, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, group):
+        need = loc.requires_grad or conf.requires_grad
+        out = head.loss(loc, conf, gt, with_grads=need, neg_ratio=neg_ratio, pos_iou=pos_iou, group=group)
+        ctx.head = head
+        ctx.src = (loc.device, conf.device, loc.dtype, conf.dtype)
+        ctx.grads = (out["grad_loc"], out["grad_conf"])
+        losses = out["losses"]
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loc_loss, g_conf_loss):
+        if ctx.grads is None or ctx.grads[0] is None:
+            raise RuntimeError("ssd(): backward called twice (or without grad-requiring inputs); the fused "
+                               "kernel frees its gradient buffers after the first backward, as autograd does")
+        gl, gc = ctx.grads
+        ctx.grads = None
+        head = ctx.head
+        z = torch.zeros((), dtype=torch.float32, device=head.dev)
+        gout = torch.stack([(g_loc_loss if g_loc_loss is not None else z).to(head.dev, torch.float32).reshape(()),
+                            (g_conf_loss if g_conf_loss is not None else z).to(head.dev, torch.float32).reshape(())])
+        head.scale_grads(gl, gc, gout)
+        ld, cd, lt, ct = ctx.src
+        return gl.to(device=ld, dtype=lt), gc.to(device=cd, dtype=ct), None, None, None, None, None
+
+
+def multibox_loss(head: MultiboxHead, loc: torch.Tensor, conf: torch.Tensor,
+                  gt_boxes: List[torch.Tensor], gt_classes: List[torch.Tensor],
+                  neg_ratio: int = NEG_RATIO, pos_iou: float = POS_IOU, group=None):
+    """(loc_loss, conf_loss) as 0-dim tensors with grad_fn - the return of ``ssd()`` (Losses.py:134)."""
+    gt = PackedGT(gt_boxes, gt_classes, head.dev)
+    return _MultiboxLossFn.apply(loc, conf, head, gt, neg_ratio, pos_iou, group)

@@ -1,0 +1,37 @@
+"""Developer timing loop (not the contract bench): device-resident inputs, CUDA events."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from objectdetection_ssd_b200 import synth, priors as PR
+from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+
+def run(B, steps=20, warm=5, grads=True):
+    pri = PR.make_priors()
+    P = pri.shape[0]
+    head = MultiboxHead(pri, "cuda")
+    gb, gc = synth.make_gt(1, B)
+    loc, conf = synth.make_head(1, B, P)
+    gt = PackedGT([torch.from_numpy(b) for b in gb], [torch.from_numpy(c) for c in gc], head.dev)
+    nset = max(1, int(400e6 // (B * P * 25 * 4)) + 1)
+    sets = [(torch.from_numpy(loc).cuda() + i, torch.from_numpy(conf).cuda() + 0.01 * i) for i in range(nset)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for i in range(warm):
+        head.loss(*sets[i % nset], gt, with_grads=grads)
+    torch.cuda.synchronize()
+    tm = tl = 0.0
+    for i in range(steps):
+        l, c = sets[i % nset]
+        ev[0].record(); m = head.match(gt); ev[1].record()
+        head.loss(l, c, gt, with_grads=grads, match=m); ev[2].record()
+        torch.cuda.synchronize()
+        tm += ev[0].elapsed_time(ev[1]); tl += ev[1].elapsed_time(ev[2])
+    tm /= steps; tl /= steps
+    bytes_img = 1746400 if grads else 873200
+    print(json.dumps(dict(B=B, grads=grads, match_us=round(tm * 1e3, 1), loss_us=round(tl * 1e3, 1),
+                          img_per_s=round(B / ((tm + tl) * 1e-3)), loss_GBps=round(B * bytes_img / (tl * 1e-3) / 1e9, 1),
+                          frac_of_6538=round(B * bytes_img / ((tm + tl) * 1e-3) / 1e9 / 6538.6, 3))))
+
+if __name__ == "__main__":
+    for B in (32, 64, 256):
+        run(B, grads=True)
+    run(256, grads=False)
