@@ -66,29 +66,38 @@ int ssdhead_iou_matrix(const float* a_xyxy_dev, int n1, const float* b_xyxy_dev,
 /* ---- matching: Losses.py:150-171 (batched) / map_prior_to_bb Util.py:333-352 --------
  * Outputs: best_prior int32 [sumG] (argmax over priors per gt, T2);
  *          npos int32 [B+1]: positives per image, npos[B] = batch total;
- *          obj_idx int32 [B,P] GLOBAL gt index after the forced override (nullable);
- *          cls     int32 [B,P] class per prior, C-1 = background (nullable).           */
+ *          cls_u8 uint8 [B,P] class per prior after the forced override, C-1 = background
+ *                 (what Losses.obj_forEach_prior___ holds; consumed by ssdhead_multibox_loss);
+ *          obj_idx int32 [B,P] GLOBAL gt index after the forced override (nullable; debug tap);
+ *          cls     int32 [B,P] the class map widened to int32 (nullable; debug tap).
+ * The workspace must be zero-filled before its FIRST use; every call leaves it zeroed.      */
 int ssdhead_match(const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                   const float* pri_xyxy_dev, int B, int P, int C, int sumG, float pos_iou,
-                  int32_t* best_prior_dev, int32_t* npos_dev, int32_t* obj_idx_dev, int32_t* cls_dev,
+                  int32_t* best_prior_dev, int32_t* npos_dev, uint8_t* cls_u8_dev,
+                  int32_t* obj_idx_dev, int32_t* cls_dev,
                   void* ws_dev, size_t ws_bytes, void* stream);
 
 /* ---- multibox loss fwd(+bwd): ssd / ssd1_, Losses.py:119-199 ------------------------
- * One pass: conf rows are staged once into the shared memory of a thread-block cluster
- * per image, CE + hard-negative mining (descending CE, ties -> lower prior index, T4)
- * and, when grad_* are non-null, the gradients for unit upstream gradients are written
- * from that same staging.  `npos_dev` is ssdhead_match's output; `npos_norm_dev` points
- * to the int32 positive count the losses/gradients are normalised by (npos_dev+B on one
- * GPU; the all-reduced total when the batch is sharded by image).
+ * Two kernels.  (1) A persistent streaming kernel reads conf exactly once through a 4-stage
+ * TMA/mbarrier shared-memory ring, writes one cross-entropy value per prior and bulk-stores
+ * the zero background of the gradients.  (2) One CTA per image selects the k = neg_ratio*npos
+ * largest background CE exactly (radix select; descending CE, ties -> lower prior index, T4;
+ * positives rank with value 0, Losses.py:190) and writes the gradient rows of positives and
+ * mined negatives only, for unit upstream gradients.
+ * `npos_dev`, `best_prior_dev`, `cls_u8_dev` are ssdhead_match's outputs; `npos_norm_dev`
+ * points to the int32 positive count the losses/gradients are normalised by (npos_dev+B on
+ * one GPU; the all-reduced total when the batch is sharded by image).
  * Outputs: sums double[2] = { sum |loc-enc| over positives, sum CE over positives+mined };
  *          losses float[2] = { sums[0]/(4N), sums[1]/N }  (loc_loss, conf_loss of ssd());
  *          grad_loc [B,P,4], grad_conf [B,P,C] dense (nullable as a pair);
  *          mined_mask uint32 [B, ceil(P/32)] bit p = mined negative (nullable; debug tap);
- *          ce [B,P] per-prior cross entropy (nullable; debug tap).                     */
+ *          ce [B,P] per-prior cross entropy (nullable: then it lives in the workspace).
+ * The workspace must be zero-filled before its FIRST use; every call leaves its counter zeroed. */
 int ssdhead_multibox_loss(const float* loc_dev, const float* conf_dev,
                           const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                           const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
                           const int32_t* best_prior_dev, const int32_t* npos_dev, const int32_t* npos_norm_dev,
+                          const uint8_t* cls_u8_dev,
                           int B, int P, int C, int neg_ratio, float pos_iou,
                           double* sums_dev, float* losses_dev,
                           float* grad_loc_dev, float* grad_conf_dev,

@@ -28,8 +28,8 @@ SIGNATURES = {
     "ssdhead_encode": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ssdhead_decode": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ssdhead_iou_matrix": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
-    "ssdhead_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "ssdhead_multibox_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "ssdhead_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_multibox_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_finish_loss": (_i, [_vp, _vp, _vp, _vp]),
     "ssdhead_scale_grads": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),

@@ -20,7 +20,7 @@ const char* ssdhead_error_string(int code)
     switch (code) {
         case 0: return "ok";
         case SSDHEAD_E_BADARG: return "ssdhead: bad argument (null pointer or negative size)";
-        case SSDHEAD_E_UNSUPPORTED: return "ssdhead: unsupported shape (C must be 21; P must fit a 16-CTA cluster)";
+        case SSDHEAD_E_UNSUPPORTED: return "ssdhead: unsupported shape (C must be 21; P limited by shared memory)";
         case SSDHEAD_E_WORKSPACE: return "ssdhead: workspace too small";
         case SSDHEAD_E_ALIGN: return "ssdhead: pointer not 16-byte aligned";
         case SSDHEAD_E_STATE: return "ssdhead: host context misuse";
@@ -35,7 +35,7 @@ size_t ssdhead_workspace_bytes(int which, int B, int P, int C, int n)
     if (B < 0 || P < 0 || C < 0 || n < 0) return 0;
     switch (which) {
         case SSDHEAD_WS_MATCH:
-            return round_up((size_t)n * 8, 16) + round_up((size_t)B * 4, 16) + 16;
+            return round_up((size_t)n * 8, 16) + 2 * round_up((size_t)B * 4, 16) + 16;
         case SSDHEAD_WS_LOSS:
             return loss_workspace_bytes(B, P, C);
         case SSDHEAD_WS_DETECT:

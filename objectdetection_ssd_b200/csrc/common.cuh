@@ -40,6 +40,18 @@ __device__ __forceinline__ float iou_xyxy(const float4 a, const float area_a, co
     return __fdiv_rn(inter, uni);
 }
 
+// IoU with the division skipped for disjoint boxes: inter == +0 -> 0/union == +0 for any union > 0
+// (priors have positive area, so union > 0 whenever the gt area is not negative).
+__device__ __forceinline__ float iou_sparse(const float4 a, const float area_a, const float4 b, const float area_b) {
+    const float lx = fmaxf(a.x, b.x), ly = fmaxf(a.y, b.y);
+    const float hx = fminf(a.z, b.z), hy = fminf(a.w, b.w);
+    const float dx = fmaxf(__fsub_rn(hx, lx), 0.0f);
+    const float dy = fmaxf(__fsub_rn(hy, ly), 0.0f);
+    const float inter = __fmul_rn(dx, dy);
+    if (inter == 0.0f && area_a >= 0.0f) return 0.0f;
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
 // Util.py:93-96
 __device__ __forceinline__ float4 cxcywh_to_xyxy(const float4 b) {
     const float hw = __fdiv_rn(b.z, 2.0f), hh = __fdiv_rn(b.w, 2.0f);

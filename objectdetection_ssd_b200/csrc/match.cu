@@ -2,28 +2,32 @@
 // offset elementwise ops.  Reference: Losses.py:150-171, Util.py:57-63, 86-102, 252-265,
 // 288-301, 333-352.
 //
-// match_kernel: grid (tiles, B), 256 threads, 4 priors per thread (coalesced float4 reads of
-// the L2-resident prior table).  The gt boxes of the image are staged in shared memory; each
-// thread keeps the best gt of its priors (T1: first maximal gt), and per gt a warp-level
-// redux.max + ballot gives the best prior of the tile (T2: lowest prior index), merged across
-// warps and tiles with 64-bit atomicMax on (iou_key << 32 | ~prior).  The last tile of an image
-// to finish applies the forced-match override (T3: highest gt index wins) and publishes
-// best_prior / npos.  HBM traffic is negligible (gt + priors); the kernel exists so the loss
-// kernel can know the batch-global positive count before it writes gradients.
+// match_kernel: grid (tiles, B), 256 threads, each thread owns 4 CONSECUTIVE priors (64 B of the
+// L2-resident prior table).  The gt boxes of the image are staged in shared memory; each thread keeps
+// the best gt of its priors (T1: first maximal gt) and, per gt, its own best prior (lowest index on
+// ties); one redux.max + ballot per gt then gives the warp's best prior (T2), merged across warps and
+// tiles with 64-bit atomicMax on (iou_key << 32 | ~prior).  Pairs that do not intersect skip the IEEE
+// division (0/union == +0 exactly).  The last tile of an image to finish applies the forced-match
+// override (T3: highest gt index wins) and publishes best_prior / npos[b]; the last image to finish
+// publishes the batch total npos[B].  The workspace is left zeroed (self-cleaning): no memsets.
+// HBM traffic is negligible (gt + priors in, one class byte per prior out); the kernel exists so the
+// loss kernels know the class of every prior and the batch-global positive count.
 #include "common.cuh"
 
 namespace ssdhead {
 
 constexpr int MT = 256;          // threads per CTA
-constexpr int MPPT = 4;          // priors per thread
+constexpr int MPPT = 4;          // consecutive priors per thread
 constexpr int MTILE = MT * MPPT; // priors per CTA
 constexpr int MGC = 64;          // gt boxes staged per chunk
 
 __global__ void __launch_bounds__(MT)
 match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cls, const int* __restrict__ gt_off,
              const float4* __restrict__ pri_xyxy, int B, int P, int bg_class, float pos_iou,
-             int* __restrict__ best_prior, int* __restrict__ npos, int* __restrict__ obj_idx, int* __restrict__ cls_out,
-             unsigned long long* __restrict__ best_key, unsigned int* __restrict__ tile_counter)
+             int* __restrict__ best_prior, int* __restrict__ npos, uint8_t* __restrict__ cls_u8,
+             int* __restrict__ obj_idx, int* __restrict__ cls_out,
+             unsigned long long* __restrict__ best_key, unsigned int* __restrict__ tile_counter,
+             int* __restrict__ npos_acc, unsigned int* __restrict__ image_counter)
 {
     __shared__ float4 s_box[MGC];
     __shared__ float s_area[MGC];
@@ -34,20 +38,19 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
     const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int off0 = gt_off[b];
     const int G = gt_off[b + 1] - off0;
+    const int p0 = tile * MTILE + t * MPPT;          // first prior of this thread
 
     float4 pb[MPPT];
     float pa[MPPT], best[MPPT];
     int bestg[MPPT];
-    bool valid[MPPT];
 #pragma unroll
     for (int i = 0; i < MPPT; ++i) {
-        const int p = tile * MTILE + i * MT + t;
-        valid[i] = p < P;
-        pb[i] = valid[i] ? pri_xyxy[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[i] = (p0 + i < P) ? pri_xyxy[p0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         pa[i] = box_area(pb[i]);
         best[i] = -INFINITY;
         bestg[i] = 0;
     }
+    const bool first_warp = (tile == 0 && warp == 0);   // owns prior 0: the argmax of an all-zero IoU row (T2)
 
     for (int g0 = 0; g0 < G; g0 += MGC) {
         const int gc = min(MGC, G - g0);
@@ -62,37 +65,53 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         for (int g = 0; g < gc; ++g) {
             const float4 gb = s_box[g];
             const float ga = s_area[g];
-            uint32_t wbest = 0u, wprior = 0u;
+            uint32_t tk = 0u;          // this thread's best key for gt g, lowest prior on ties
+            int ti = 0;
 #pragma unroll
             for (int i = 0; i < MPPT; ++i) {
-                const float v = iou_xyxy(gb, ga, pb[i], pa[i]);
-                if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }          // T1: strict > keeps the first
-                const uint32_t k = valid[i] ? float_order_key(v) : 0u;
-                const uint32_t m = __reduce_max_sync(FULL, k);
-                if (m > wbest) {                                                // warp-uniform; strict > keeps lower i
-                    const unsigned ball = __ballot_sync(FULL, k == m);
-                    wbest = m;
-                    wprior = (uint32_t)(tile * MTILE + i * MT + warp * 32 + (__ffs(ball) - 1));   // T2: lowest lane
+                const float v = iou_sparse(gb, ga, pb[i], pa[i]);
+                if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }          // T1: strict > keeps the first gt
+                const uint32_t k = (p0 + i < P) ? float_order_key(v) : 0u;
+                if (k > tk) { tk = k; ti = i; }                               // strict > keeps the lower prior
+            }
+            const uint32_t m = __reduce_max_sync(FULL, tk);
+            if (m > 0x80000000u || (first_warp && m != 0u)) {                 // some IoU > 0, or the warp owning prior 0
+                const unsigned ball = __ballot_sync(FULL, tk == m);
+                const int src = __ffs(ball) - 1;                              // T2: lowest lane = lowest prior
+                const int wi = __shfl_sync(FULL, ti, src);
+                if (lane == 0) {
+                    const uint32_t wprior = (uint32_t)(tile * MTILE + (warp * 32 + src) * MPPT + wi);
+                    atomicMax(&s_key[g], ((unsigned long long)m << 32) | (unsigned long long)(0xffffffffu - wprior));
                 }
             }
-            if (lane == 0 && wbest != 0u)
-                atomicMax(&s_key[g], ((unsigned long long)wbest << 32) | (unsigned long long)(0xffffffffu - wprior));
         }
         __syncthreads();
         if (t < gc && s_key[t] != 0ull) atomicMax(&best_key[off0 + g0 + t], s_key[t]);
     }
 
-    // natural (pre-override) match of this tile
+    // natural (pre-override) match of this tile: one class byte per prior
     int cnt = 0;
+    uint32_t packed = 0u;
 #pragma unroll
     for (int i = 0; i < MPPT; ++i) {
-        const int p = tile * MTILE + i * MT + t;
-        if (!valid[i]) continue;
+        const int p = p0 + i;
         const bool hit = (G > 0) && !(best[i] < pos_iou);                       // T6: matched <=> not (iou < thr)
-        const int c = hit ? (int)gt_cls[off0 + bestg[i]] : bg_class;
-        cnt += (c != bg_class) ? 1 : 0;                                         // positive <=> class != bg (Losses.py:179)
-        if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + bestg[i];
-        if (cls_out) cls_out[(size_t)b * P + p] = c;
+        const int c = (hit && p < P) ? (int)gt_cls[off0 + bestg[i]] : bg_class;
+        packed |= (uint32_t)(c & 0xff) << (8 * i);
+        if (p < P) {
+            cnt += (c != bg_class) ? 1 : 0;                                     // positive <=> class != bg (Losses.py:179)
+            if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + bestg[i];
+            if (cls_out) cls_out[(size_t)b * P + p] = c;
+        }
+    }
+    {
+        uint8_t* dst = cls_u8 + (size_t)b * P + p0;
+        if (p0 + MPPT <= P && ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0)) {
+            *reinterpret_cast<uint32_t*>(dst) = packed;
+        } else {
+#pragma unroll
+            for (int i = 0; i < MPPT; ++i) if (p0 + i < P) dst[i] = (uint8_t)(packed >> (8 * i));
+        }
     }
     cnt = warp_sum(cnt);
     if (lane == 0) s_red[warp] = cnt;
@@ -100,7 +119,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
     if (t == 0) {
         int c = 0;
         for (int w = 0; w < MT / 32; ++w) c += s_red[w];
-        if (c) atomicAdd(&npos[b], c);
+        if (c) atomicAdd(&npos_acc[b], c);
         __threadfence();
         const unsigned done = atomicAdd(&tile_counter[b], 1u);
         s_last = (done == gridDim.x - 1) ? 1 : 0;
@@ -126,24 +145,36 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         int ng = 0;
         for (int g2 = 0; g2 < G; ++g2) {
             const float4 gb = gt_xyxy[off0 + g2];
-            const float v = iou_xyxy(gb, box_area(gb), pbx, pax);
+            const float v = iou_sparse(gb, box_area(gb), pbx, pax);
             if (v > nb) { nb = v; ng = g2; }
         }
         const int c_nat = !(nb < pos_iou) ? (int)gt_cls[off0 + ng] : bg_class;  // what the tile pass counted
         const int c_new = (int)gt_cls[off0 + g];
         extra += (c_new != bg_class ? 1 : 0) - (c_nat != bg_class ? 1 : 0);
+        cls_u8[(size_t)b * P + p] = (uint8_t)c_new;
         if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + g;
         if (cls_out) cls_out[(size_t)b * P + p] = c_new;
     }
     extra = warp_sum(extra);
     __syncthreads();
     if (lane == 0) s_red[warp] = extra;
-    __syncthreads();
+    __syncthreads();                                                            // also: every best_key read above is done
+    for (int g = t; g < G; g += MT) best_key[off0 + g] = 0ull;                  // leave the workspace zeroed
     if (t == 0) {
         int e = 0;
         for (int w = 0; w < MT / 32; ++w) e += s_red[w];
-        const int total = atomicAdd(&npos[b], e) + e;
-        atomicAdd(&npos[B], total);
+        npos[b] = ld_cg_s32(&npos_acc[b]) + e;
+        npos_acc[b] = 0;
+        tile_counter[b] = 0u;
+        __threadfence();
+        const unsigned done = atomicAdd(image_counter, 1u);
+        if (done == gridDim.y - 1) {                                            // last image: batch total, fixed order
+            __threadfence();
+            int tot = 0;
+            for (int i = 0; i < B; ++i) tot += ld_cg_s32(&npos[i]);
+            npos[B] = tot;
+            *image_counter = 0u;
+        }
     }
 }
 
@@ -221,25 +252,27 @@ int ssdhead_iou_matrix(const float* a, int n1, const float* b, int n2, float* ou
 
 int ssdhead_match(const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, const float* pri_xyxy,
                   int B, int P, int C, int sumG, float pos_iou,
-                  int32_t* best_prior, int32_t* npos, int32_t* obj_idx, int32_t* cls,
+                  int32_t* best_prior, int32_t* npos, uint8_t* cls_u8, int32_t* obj_idx, int32_t* cls,
                   void* ws, size_t ws_bytes, void* stream)
 {
-    if (B < 0 || P <= 0 || C < 2 || sumG < 0) return SSDHEAD_E_BADARG;
+    if (B < 0 || P <= 0 || C < 2 || C > 256 || sumG < 0) return SSDHEAD_E_BADARG;
     if (B == 0) return 0;
-    if (!gt_off || !pri_xyxy || !npos || !ws) return SSDHEAD_E_BADARG;
+    if (!gt_off || !pri_xyxy || !npos || !cls_u8 || !ws) return SSDHEAD_E_BADARG;
     if (sumG > 0 && (!gt_xyxy || !gt_cls || !best_prior)) return SSDHEAD_E_BADARG;
     if (B > 65535) return SSDHEAD_E_UNSUPPORTED;
     if (!aligned16(pri_xyxy) || (sumG > 0 && !aligned16(gt_xyxy)) || !aligned16(ws)) return SSDHEAD_E_ALIGN;
     const size_t need = ssdhead_workspace_bytes(SSDHEAD_WS_MATCH, B, P, C, sumG);
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* best_key = (unsigned long long*)ws;
-    unsigned int* counter = (unsigned int*)((char*)ws + round_up((size_t)sumG * 8, 16));
-    SSD_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
-    SSD_CHECK_CUDA(cudaMemsetAsync(npos, 0, (size_t)(B + 1) * sizeof(int), st));
+    // workspace (zero on entry, zero on exit): best_key[sumG] u64 | tile_counter[B] | npos_acc[B] | image_counter
+    char* w = (char*)ws;
+    unsigned long long* best_key = (unsigned long long*)w;            w += round_up((size_t)sumG * 8, 16);
+    unsigned int* tile_counter = (unsigned int*)w;                    w += round_up((size_t)B * 4, 16);
+    int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
+    unsigned int* image_counter = (unsigned int*)w;
     dim3 grid((P + MTILE - 1) / MTILE, B);
     match_kernel<<<grid, MT, 0, st>>>((const float4*)gt_xyxy, gt_cls, gt_off, (const float4*)pri_xyxy, B, P, C - 1, pos_iou,
-                                      best_prior, npos, obj_idx, cls, best_key, counter);
+                                      best_prior, npos, cls_u8, obj_idx, cls, best_key, tile_counter, npos_acc, image_counter);
     count_launch();
     SSD_LAUNCH_CHECK();
     return 0;

@@ -94,6 +94,7 @@ class MultiboxHead:
         B = gt.B
         best_prior = torch.empty(max(gt.sumG, 1), dtype=torch.int32, device=self.dev)
         npos = torch.empty(B + 1, dtype=torch.int32, device=self.dev)
+        cls_u8 = torch.empty(B, self.P, dtype=torch.uint8, device=self.dev)
         obj = cls = None
         if want_maps:
             obj = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
@@ -102,9 +103,9 @@ class MultiboxHead:
         _lib.check(self.lib.ssdhead_match(
             _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off), _ptr(self.pri_xyxy),
             B, self.P, self.C, gt.sumG, pos_iou,
-            _ptr(best_prior), _ptr(npos), _ptr(obj), _ptr(cls),
+            _ptr(best_prior), _ptr(npos), _ptr(cls_u8), _ptr(obj), _ptr(cls),
             _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_match")
-        return dict(best_prior=best_prior, npos=npos, obj=obj, cls=cls)
+        return dict(best_prior=best_prior, npos=npos, cls_u8=cls_u8, obj=obj, cls=cls)
 
     # ------------------------------------------------------------------ loss
     def loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedGT, with_grads: bool,
@@ -141,7 +142,7 @@ class MultiboxHead:
         _lib.check(self.lib.ssdhead_multibox_loss(
             _ptr(loc), _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off),
             _ptr(self.pri_xyxy), _ptr(self.pri_cxcywh),
-            _ptr(m["best_prior"]), _ptr(npos), _ptr(npos_norm),
+            _ptr(m["best_prior"]), _ptr(npos), _ptr(npos_norm), _ptr(m["cls_u8"]),
             B, P, C, int(neg_ratio), float(pos_iou),
             _ptr(sums), _ptr(losses), _ptr(grad_loc), _ptr(grad_conf), _ptr(mined), _ptr(ce),
             _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_multibox_loss")
@@ -151,7 +152,7 @@ class MultiboxHead:
             _lib.check(self.lib.ssdhead_finish_loss(_ptr(sums), _ptr(npos_norm), _ptr(losses),
                                                     _stream(self.dev)), "ssdhead_finish_loss")
         return dict(losses=losses, sums=sums, npos=npos, npos_norm=npos_norm, grad_loc=grad_loc,
-                    grad_conf=grad_conf, mined_mask=mined, ce=ce, best_prior=m["best_prior"])
+                    grad_conf=grad_conf, mined_mask=mined, ce=ce, best_prior=m["best_prior"], cls_u8=m["cls_u8"])
 
     def scale_grads(self, grad_loc: torch.Tensor, grad_conf: torch.Tensor, gout: torch.Tensor):
         _lib.check(self.lib.ssdhead_scale_grads(_ptr(grad_loc), grad_loc.numel(), _ptr(grad_conf),

@@ -217,3 +217,20 @@ def test_image_without_gt_raises_like_reference():
     tc[1] = torch.zeros(0)
     with pytest.raises(IndexError):
         multibox_loss(_head(pri), loc.cuda(), conf.cuda(), tb, tc)
+
+
+def test_loss_misaligned_conf_pointer_uses_plain_loads():
+    """A conf view that is not 16-byte aligned cannot use bulk copies: the kernel falls back to plain loads."""
+    pri = H.priors()
+    loc, conf, tb, tc = H.train_inputs(12, 3, pri.shape[0])
+    head = _head(pri)
+    gt = _packed(tb, tc, head)
+    big = torch.empty(conf.numel() + 1, device="cuda")
+    view = big[1:].view_as(conf)
+    view.copy_(conf)
+    assert view.data_ptr() % 16 != 0
+    a = head.loss(loc.cuda(), view, gt, with_grads=True)
+    b = head.loss(loc.cuda(), conf.cuda(), gt, with_grads=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a["losses"], b["losses"])
+    assert torch.equal(a["grad_conf"], b["grad_conf"]) and torch.equal(a["grad_loc"], b["grad_loc"])
