@@ -182,119 +182,199 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return base + inc - v;
 }
 
+constexpr int MN_GC = 64;        // gt boxes staged in shared memory
+constexpr int MN_CAND = 512;     // boundary-bin candidates ranked directly (one per thread)
+
 template <int C, bool GRADS>
 __global__ void __launch_bounds__(MN_T)
 mine_kernel(const MineParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_raw);            // [P]   CE bit pattern, 0 for positives
-    uint32_t* s_list = s_key + p.P;                                      // [P]   selected rows: row | class << 24
-    uint32_t* s_hist = s_list + p.P;                                     // [MN_BINS]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_raw);            // [P]  CE bit pattern, 0 for positives; bit 31 = selected
+    uint32_t* s_hist = s_key + p.P;                                      // [MN_BINS]
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_hist + MN_BINS);    // [P]  rows that carry a gradient (P < 65536)
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_list + ((p.P + 1) & ~1)); // [P]  class bytes
     __shared__ uint32_t s_warp[MN_W + 1];
     __shared__ uint32_t s_sel[3];
-    __shared__ uint32_t s_nsel;
+    __shared__ uint32_t s_nsel, s_ncand, s_max;
+    __shared__ uint32_t s_ckey[MN_CAND], s_cidx[MN_CAND];
+    __shared__ float4 s_gbox[MN_GC];
+    __shared__ float s_garea[MN_GC];
+    __shared__ int s_gbp[MN_GC];
     __shared__ double s_redd[2][MN_W];
     __shared__ int s_is_last;
 
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int P = p.P;
     const size_t row0 = (size_t)b * P;
+    const int off0 = p.gt_off[b];
+    const int G = p.gt_off[b + 1] - off0;
     double acc_l1 = 0.0, acc_ce = 0.0;
 
-    // ---- 1. keys: CE bits for negatives, 0 for positives (Losses.py:188-190) ----
-    if (t == 0) s_nsel = 0u;
-    for (int j = t; j < P; j += MN_T) {
-        const float ce = p.ce[row0 + j];
-        const bool pos = (int)p.cls_u8[row0 + j] != p.bg_class;
-        if (pos) acc_ce += (double)ce;
-        s_key[j] = pos ? 0u : __float_as_uint(ce);
+    // ---- 1. keys: CE bits for negatives, 0 for positives (Losses.py:188-190); class bytes; gts ----
+    if (t == 0) { s_nsel = 0u; s_ncand = 0u; s_max = 0u; }
+    if (t < min(G, MN_GC)) {
+        const float4 bx = p.gt_xyxy[off0 + t];
+        s_gbox[t] = bx;
+        s_garea[t] = box_area(bx);
+        s_gbp[t] = p.best_prior[off0 + t];
     }
     __syncthreads();
+    uint32_t kmax = 0u;
+    for (int j = t; j < P; j += MN_T) {
+        const float ce = p.ce[row0 + j];
+        const uint8_t c = p.cls_u8[row0 + j];
+        const bool pos = (int)c != p.bg_class;
+        if (pos) acc_ce += (double)ce;
+        const uint32_t key = pos ? 0u : (__float_as_uint(ce) & 0x7fffffffu);
+        s_key[j] = key;
+        s_cls[j] = c;
+        kmax = max(kmax, key);
+    }
+    kmax = __reduce_max_sync(FULL, kmax);
+    if (lane == 0) atomicMax(&s_max, kmax);
+    __syncthreads();
+    kmax = s_max;
 
-    // ---- 2. exact k-th largest key: radix select, digits of 11 / 11 / 10 bits ----
+    // ---- 2. the k largest keys, ties to the lower prior index (T4): mark them with bit 31 ----
     const long long kk = (long long)p.neg_ratio * (long long)p.npos[b];
     const uint32_t k = (uint32_t)min((long long)P, max(0ll, kk));
-    uint32_t T = 0u, need = 0u;                  // take every key > T and the first `need` keys == T in prior order
-    bool none = (k == 0u);
     if (k >= (uint32_t)P) {
-        T = 0u; need = 0xffffffffu;              // everything
+        for (int j = t; j < P; j += MN_T) s_key[j] |= 0x80000000u;
     } else if (k > 0u) {
-        uint32_t prefix = 0u, mask = 0u;
-        need = k;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-            const int bins = pass == 2 ? 1024 : 2048;
-            for (int i = t; i < bins; i += MN_T) s_hist[i] = 0u;
+        bool done = false;
+        const float vmax = __uint_as_float(kmax);
+        if (kmax > 0u && kmax < 0x7f800000u) {
+            // fast path: one histogram over 2048 LINEAR bins of [0, max] (monotone in the key), then the few
+            // keys of the boundary bin are ranked against each other directly.
+            const float scale = __fdiv_rn(2047.0f, vmax);
+            for (int i = t; i < MN_BINS; i += MN_T) s_hist[i] = 0u;
             __syncthreads();
-            for (int j = t; j < P; j += MN_T) {
-                const uint32_t key = s_key[j];
-                if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & (uint32_t)(bins - 1)], 1u);
-            }
+            for (int j = t; j < P; j += MN_T)
+                atomicAdd(&s_hist[(int)__fmul_rn(__uint_as_float(s_key[j]), scale)], 1u);
             __syncthreads();
-            // thread t owns bins taken from the TOP: an ordinary prefix scan then counts the keys above
-            const int per = bins / MN_T;          // 4 or 2
-            uint32_t c4[4] = {0u, 0u, 0u, 0u}, mine = 0u;
+            constexpr int per = MN_BINS / MN_T;
+            uint32_t c4[per], mine = 0u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < per) { c4[q] = s_hist[bins - 1 - (t * per + q)]; mine += c4[q]; }
+            for (int q = 0; q < per; ++q) { c4[q] = s_hist[MN_BINS - 1 - (t * per + q)]; mine += c4[q]; }
             uint32_t tot;
             uint32_t above = block_exclusive_scan(mine, s_warp, &tot);
-            if (above < need && above + mine >= need) {
+            if (above < k && above + mine >= k) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (q < per) {
-                    if (above + c4[q] >= need) { s_sel[0] = (uint32_t)(bins - 1 - (t * per + q)); s_sel[1] = above; s_sel[2] = c4[q]; break; }
+                for (int q = 0; q < per; ++q) {
+                    if (above + c4[q] >= k) { s_sel[0] = (uint32_t)(MN_BINS - 1 - (t * per + q)); s_sel[1] = above; s_sel[2] = c4[q]; break; }
                     above += c4[q];
                 }
             }
             __syncthreads();
-            prefix |= s_sel[0] << shift;
-            mask |= (uint32_t)(bins - 1) << shift;
-            need -= s_sel[1];
+            const int bq = (int)s_sel[0];
+            const uint32_t need = k - s_sel[1], cnt = s_sel[2];
+            if (cnt <= (uint32_t)MN_CAND) {
+                done = true;
+                for (int j = t; j < P; j += MN_T) {
+                    const uint32_t key = s_key[j];
+                    const int bin = (int)__fmul_rn(__uint_as_float(key), scale);
+                    if (bin > bq) s_key[j] = key | 0x80000000u;
+                    else if (bin == bq) { const uint32_t s = atomicAdd(&s_ncand, 1u); s_ckey[s] = key; s_cidx[s] = (uint32_t)j; }
+                }
+                __syncthreads();
+                if ((uint32_t)t < cnt) {
+                    const uint32_t mk = s_ckey[t], mi = s_cidx[t];
+                    uint32_t rank = 0u;
+                    for (uint32_t q = 0; q < cnt; ++q) {
+                        const uint32_t ok = s_ckey[q], oi = s_cidx[q];
+                        rank += (ok > mk || (ok == mk && oi < mi)) ? 1u : 0u;
+                    }
+                    if (rank < need) s_key[mi] = mk | 0x80000000u;
+                }
+            }
         }
-        T = prefix;
+        if (!done) {
+            // general path (many equal keys, or non-finite CE): exact radix select, digits of 11 / 11 / 10 bits
+            uint32_t prefix = 0u, mask = 0u, need = k;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+                const int bins = pass == 2 ? 1024 : 2048;
+                __syncthreads();
+                for (int i = t; i < bins; i += MN_T) s_hist[i] = 0u;
+                __syncthreads();
+                for (int j = t; j < P; j += MN_T) {
+                    const uint32_t key = s_key[j];
+                    if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & (uint32_t)(bins - 1)], 1u);
+                }
+                __syncthreads();
+                const int per = bins / MN_T;          // 4 or 2
+                uint32_t c4[4] = {0u, 0u, 0u, 0u}, mine = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q < per) { c4[q] = s_hist[bins - 1 - (t * per + q)]; mine += c4[q]; }
+                uint32_t tot;
+                uint32_t above = block_exclusive_scan(mine, s_warp, &tot);
+                if (above < need && above + mine >= need) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q < per) {
+                        if (above + c4[q] >= need) { s_sel[0] = (uint32_t)(bins - 1 - (t * per + q)); s_sel[1] = above; s_sel[2] = c4[q]; break; }
+                        above += c4[q];
+                    }
+                }
+                __syncthreads();
+                prefix |= s_sel[0] << shift;
+                mask |= (uint32_t)(bins - 1) << shift;
+                need -= s_sel[1];
+            }
+            const uint32_t T = prefix;               // take every key > T and the first `need` keys == T in prior order
+            int per = (P + MN_T - 1) / MN_T;
+            per |= 1;                                // odd stride: fewer shared-memory bank conflicts
+            const int j0 = min(P, t * per), j1 = min(P, j0 + per);
+            uint32_t ties = 0u;
+            for (int j = j0; j < j1; ++j) ties += (s_key[j] == T) ? 1u : 0u;
+            uint32_t tot_ties;
+            uint32_t rank = block_exclusive_scan(ties, s_warp, &tot_ties);
+            for (int j = j0; j < j1; ++j) {
+                const uint32_t key = s_key[j];
+                if (key > T) s_key[j] = key | 0x80000000u;
+                else if (key == T) { if (rank < need) s_key[j] = key | 0x80000000u; ++rank; }
+            }
+        }
     }
+    __syncthreads();
 
-    // ---- 3. ordered walk (thread t owns a contiguous prior range): rank the ties, build the row list ----
-    int per = (P + MN_T - 1) / MN_T;
-    per |= 1;                                     // odd stride: fewer shared-memory bank conflicts
-    const int j0 = min(P, t * per), j1 = min(P, j0 + per);
-    uint32_t ties = 0u;
-    if (!none) for (int j = j0; j < j1; ++j) ties += (s_key[j] == T) ? 1u : 0u;
-    uint32_t tot_ties;
-    uint32_t rank = block_exclusive_scan(ties, s_warp, &tot_ties);
-    for (int j = j0; j < j1; ++j) {
+    // ---- 3. mined CE sum, list of rows that carry a gradient ----
+    for (int j = t; j < P; j += MN_T) {
         const uint32_t key = s_key[j];
-        const int c = (int)p.cls_u8[row0 + j];
+        const int c = (int)s_cls[j];
         const bool pos = c != p.bg_class;
-        bool sel = false;
-        if (!none) {
-            if (key > T) sel = true;
-            else if (key == T) { sel = rank < need; ++rank; }
-        }
-        const bool mined = sel && !pos;
+        const bool mined = (key >> 31) && !pos;
         if (mined) {
-            acc_ce += (double)__uint_as_float(key);
+            acc_ce += (double)__uint_as_float(key & 0x7fffffffu);
             if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
         }
-        if (pos || (GRADS && mined)) s_list[atomicAdd(&s_nsel, 1u)] = (uint32_t)j | ((uint32_t)c << 24);
+        if (pos || (GRADS && mined)) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
     }
     __syncthreads();
 
     // ---- 4. the selected rows only: conf gradient, and for positives the L1 term + loc gradient ----
     const uint32_t nsel = s_nsel;
-    const int off0 = p.gt_off[b];
-    const int G = p.gt_off[b + 1] - off0;
     const float nrm = (float)(*p.npos_norm);
     const float gs_conf = __fdiv_rn(1.0f, nrm);
     const float gs_loc = __fdiv_rn(1.0f, __fmul_rn(4.0f, nrm));
     for (uint32_t idx = t; idx < nsel; idx += MN_T) {
-        const uint32_t e = s_list[idx];
-        const int j = (int)(e & 0xffffffu), c = (int)(e >> 24);
+        const int j = (int)s_list[idx];
+        const int c = (int)s_cls[j];
+        const bool pos = c != p.bg_class;
+        float x[C];
+        float4 pb, pc, l;
         if (GRADS) {
             const float* row = p.conf + (row0 + j) * C;
-            float x[C];
 #pragma unroll
             for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
+        }
+        if (pos) {                                   // issue every independent load before the first use
+            pb = p.pri_xyxy[j];
+            pc = p.pri_cxcywh[j];
+            l = reinterpret_cast<const float4*>(p.loc)[row0 + j];
+        }
+        if (GRADS) {
             float m = x[0];
 #pragma unroll
             for (int q = 1; q < C; ++q) m = fmaxf(m, x[q]);
@@ -307,21 +387,22 @@ mine_kernel(const MineParams p)
             for (int q = 0; q < C; ++q)
                 grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
         }
-        if (c != p.bg_class) {
+        if (pos) {
             // which gt: the forced one (T3: highest index wins) or the natural argmax (T1)
-            const float4 pb = p.pri_xyxy[j];
             const float pa = box_area(pb);
             int obj = -1, ng = 0;
-            float nb = -INFINITY;
+            float nb = 0.0f;
             for (int g = 0; g < G; ++g) {
-                if (p.best_prior[off0 + g] == j) obj = g;
-                const float4 gb = p.gt_xyxy[off0 + g];
-                const float v = iou_sparse(gb, box_area(gb), pb, pa);
+                float4 gb; float ga; int bp;
+                if (g < MN_GC) { gb = s_gbox[g]; ga = s_garea[g]; bp = s_gbp[g]; }
+                else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = p.best_prior[off0 + g]; }
+                if (bp == j) obj = g;
+                const float v = iou_sparse(gb, ga, pb, pa);
                 if (v > nb) { nb = v; ng = g; }
             }
             if (obj < 0) obj = ng;
-            const float4 tgt = encode_box(xyxy_to_cxcywh(p.gt_xyxy[off0 + obj]), p.pri_cxcywh[j]);
-            const float4 l = reinterpret_cast<const float4*>(p.loc)[row0 + j];
+            const float4 gbox = obj < MN_GC ? s_gbox[obj] : p.gt_xyxy[off0 + obj];
+            const float4 tgt = encode_box(xyxy_to_cxcywh(gbox), pc);
             const float dx = __fsub_rn(l.x, tgt.x), dy = __fsub_rn(l.y, tgt.y);
             const float dz = __fsub_rn(l.z, tgt.z), dw = __fsub_rn(l.w, tgt.w);
             acc_l1 += (double)fabsf(dx) + (double)fabsf(dy) + (double)fabsf(dz) + (double)fabsf(dw);
@@ -376,6 +457,7 @@ mine_kernel(const MineParams p)
     }
 }
 
+
 __global__ void finish_loss_kernel(const double* __restrict__ sums, const int* __restrict__ npos_norm, float* __restrict__ losses)
 {
     const double N = (double)(*npos_norm);
@@ -402,12 +484,12 @@ scale_grads_kernel(float4* __restrict__ gl, size_t n4_loc, float* __restrict__ g
     }
 }
 
-static size_t mine_smem_bytes(int P) { return (size_t)P * 8 + MN_BINS * 4; }
+static size_t mine_smem_bytes(int P) { return (size_t)P * 4 + MN_BINS * 4 + (size_t)((P + 1) & ~1) * 2 + round_up((size_t)P, 16); }
 
 // workspace: [0,16) done counter | partials double[2B] | CE float[B*P] (when the caller passes no ce buffer)
 size_t loss_workspace_bytes(int B, int P, int C)
 {
-    if (mine_smem_bytes(P) > 220 * 1024 || P >= (1 << 24)) return 0;
+    if (mine_smem_bytes(P) > 220 * 1024 || P >= 65536) return 0;   // P <= ~31 000 priors
     return 16 + round_up((size_t)B * 2 * sizeof(double), 16) + round_up((size_t)B * P * sizeof(float), 16);
 }
 

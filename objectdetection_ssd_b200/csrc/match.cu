@@ -47,7 +47,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
     for (int i = 0; i < MPPT; ++i) {
         pb[i] = (p0 + i < P) ? pri_xyxy[p0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         pa[i] = box_area(pb[i]);
-        best[i] = -INFINITY;
+        best[i] = 0.0f;            // IoU >= 0 and ties keep the first gt: starting at (0, gt 0) equals max() over the column
         bestg[i] = 0;
     }
     const bool first_warp = (tile == 0 && warp == 0);   // owns prior 0: the argmax of an all-zero IoU row (T2)
@@ -65,23 +65,28 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         for (int g = 0; g < gc; ++g) {
             const float4 gb = s_box[g];
             const float ga = s_area[g];
-            uint32_t tk = 0u;          // this thread's best key for gt g, lowest prior on ties
+            float tv = 0.0f;           // this thread's best IoU for gt g (IoU >= 0), lowest prior on ties
             int ti = 0;
 #pragma unroll
             for (int i = 0; i < MPPT; ++i) {
-                const float v = iou_sparse(gb, ga, pb[i], pa[i]);
-                if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }          // T1: strict > keeps the first gt
-                const uint32_t k = (p0 + i < P) ? float_order_key(v) : 0u;
-                if (k > tk) { tk = k; ti = i; }                               // strict > keeps the lower prior
+                // disjoint boxes (the common case) have IoU == +0 exactly: no multiply, no IEEE division
+                const float dx = __fsub_rn(fminf(gb.z, pb[i].z), fmaxf(gb.x, pb[i].x));
+                const float dy = __fsub_rn(fminf(gb.w, pb[i].w), fmaxf(gb.y, pb[i].y));
+                if (dx > 0.0f && dy > 0.0f) {
+                    const float inter = __fmul_rn(dx, dy);
+                    const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, pa[i]), inter));
+                    if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }      // T1: strict > keeps the first gt
+                    if (v > tv) { tv = v; ti = i; }                           // strict > keeps the lower prior
+                }
             }
-            const uint32_t m = __reduce_max_sync(FULL, tk);
-            if (m > 0x80000000u || (first_warp && m != 0u)) {                 // some IoU > 0, or the warp owning prior 0
-                const unsigned ball = __ballot_sync(FULL, tk == m);
+            const uint32_t m = __reduce_max_sync(FULL, __float_as_uint(tv));  // IoU >= 0: bits order like values
+            if (m != 0u || first_warp) {                                      // some IoU > 0, or the warp owning prior 0
+                const unsigned ball = __ballot_sync(FULL, __float_as_uint(tv) == m);
                 const int src = __ffs(ball) - 1;                              // T2: lowest lane = lowest prior
                 const int wi = __shfl_sync(FULL, ti, src);
                 if (lane == 0) {
                     const uint32_t wprior = (uint32_t)(tile * MTILE + (warp * 32 + src) * MPPT + wi);
-                    atomicMax(&s_key[g], ((unsigned long long)m << 32) | (unsigned long long)(0xffffffffu - wprior));
+                    atomicMax(&s_key[g], ((unsigned long long)(m | 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - wprior));
                 }
             }
         }
@@ -130,36 +135,71 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
 
     // ---- last tile of image b: forced-match override (Losses.py:164-167) ----
     int extra = 0;
-    for (int g = t; g < G; g += MT) {
-        const uint32_t p = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g]) & 0xffffffffull);
-        best_prior[off0 + g] = (int)p;
-        bool winner = true;                                                     // T3: the highest gt index keeps the prior
-        for (int g2 = g + 1; g2 < G; ++g2) {
-            const uint32_t p2 = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g2]) & 0xffffffffull);
-            if (p2 == p) { winner = false; break; }
+    if (G <= MGC) {
+        // all gts of the image are still staged in s_box / s_area: one round of loads, then shared memory only
+        uint32_t* s_bp = reinterpret_cast<uint32_t*>(s_key);                    // reuse: best prior per gt
+        uint32_t p = 0u;
+        if (t < G) {
+            p = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + t]) & 0xffffffffull);
+            best_key[off0 + t] = 0ull;                                          // leave the workspace zeroed
+            best_prior[off0 + t] = (int)p;
         }
-        if (!winner) continue;
-        const float4 pbx = pri_xyxy[p];
-        const float pax = box_area(pbx);
-        float nb = -INFINITY;
-        int ng = 0;
-        for (int g2 = 0; g2 < G; ++g2) {
-            const float4 gb = gt_xyxy[off0 + g2];
-            const float v = iou_sparse(gb, box_area(gb), pbx, pax);
-            if (v > nb) { nb = v; ng = g2; }
+        __syncthreads();
+        if (t < G) s_bp[t] = p;
+        __syncthreads();
+        if (t < G) {
+            bool winner = true;                                                 // T3: the highest gt index keeps the prior
+            for (int g2 = t + 1; g2 < G; ++g2) winner = winner && (s_bp[g2] != p);
+            if (winner) {
+                const float4 pbx = pri_xyxy[p];
+                const float pax = box_area(pbx);
+                float nb = 0.0f;
+                int ng = 0;
+                for (int g2 = 0; g2 < G; ++g2) {
+                    const float v = iou_sparse(s_box[g2], s_area[g2], pbx, pax);
+                    if (v > nb) { nb = v; ng = g2; }
+                }
+                const int c_nat = !(nb < pos_iou) ? (int)gt_cls[off0 + ng] : bg_class;   // what the tile pass counted
+                const int c_new = (int)gt_cls[off0 + t];
+                extra = (c_new != bg_class ? 1 : 0) - (c_nat != bg_class ? 1 : 0);
+                cls_u8[(size_t)b * P + p] = (uint8_t)c_new;
+                if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + t;
+                if (cls_out) cls_out[(size_t)b * P + p] = c_new;
+            }
         }
-        const int c_nat = !(nb < pos_iou) ? (int)gt_cls[off0 + ng] : bg_class;  // what the tile pass counted
-        const int c_new = (int)gt_cls[off0 + g];
-        extra += (c_new != bg_class ? 1 : 0) - (c_nat != bg_class ? 1 : 0);
-        cls_u8[(size_t)b * P + p] = (uint8_t)c_new;
-        if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + g;
-        if (cls_out) cls_out[(size_t)b * P + p] = c_new;
+    } else {
+        for (int g = t; g < G; g += MT) {
+            const uint32_t p = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g]) & 0xffffffffull);
+            best_prior[off0 + g] = (int)p;
+            bool winner = true;
+            for (int g2 = g + 1; g2 < G; ++g2) {
+                const uint32_t p2 = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g2]) & 0xffffffffull);
+                if (p2 == p) { winner = false; break; }
+            }
+            if (!winner) continue;
+            const float4 pbx = pri_xyxy[p];
+            const float pax = box_area(pbx);
+            float nb = 0.0f;
+            int ng = 0;
+            for (int g2 = 0; g2 < G; ++g2) {
+                const float4 gb = gt_xyxy[off0 + g2];
+                const float v = iou_sparse(gb, box_area(gb), pbx, pax);
+                if (v > nb) { nb = v; ng = g2; }
+            }
+            const int c_nat = !(nb < pos_iou) ? (int)gt_cls[off0 + ng] : bg_class;
+            const int c_new = (int)gt_cls[off0 + g];
+            extra += (c_new != bg_class ? 1 : 0) - (c_nat != bg_class ? 1 : 0);
+            cls_u8[(size_t)b * P + p] = (uint8_t)c_new;
+            if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + g;
+            if (cls_out) cls_out[(size_t)b * P + p] = c_new;
+        }
+        __syncthreads();                                                        // every best_key read above is done
+        for (int g = t; g < G; g += MT) best_key[off0 + g] = 0ull;              // leave the workspace zeroed
     }
     extra = warp_sum(extra);
     __syncthreads();
     if (lane == 0) s_red[warp] = extra;
-    __syncthreads();                                                            // also: every best_key read above is done
-    for (int g = t; g < G; g += MT) best_key[off0 + g] = 0ull;                  // leave the workspace zeroed
+    __syncthreads();
     if (t == 0) {
         int e = 0;
         for (int w = 0; w < MT / 32; ++w) e += s_red[w];

@@ -1,43 +1,55 @@
 """Join an ncu source-page CSV (SASS view) with nvdisasm line info: warp-stall samples per CUDA source line.
 
-usage: ncu_lines.py <report.ncu-rep> <cubin> <mangled kernel name> [min_samples]
+usage: ncu_lines.py <report.ncu-rep> <cubin> <kernel name substring> [min_samples]
 """
 import csv, re, subprocess, sys, collections
 
 rep, cubin, kname = sys.argv[1:4]
+kregex = sys.argv[5] if len(sys.argv) > 5 else kname
 min_s = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kregex], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
 hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hi + 1:]:
+    if len(r) != len(hdr): break
+    data.append(r)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(dis) if l.startswith(".text." + kname + ":"))
-lines = []   # per instruction: (file, line)
-cur = ("?", 0)
-for l in dis[start + 1:]:
-    if l.startswith(".text.") or l.startswith("\t.section"):
+cands = [i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l]
+best = None
+for start in cands:
+    lines = []
+    cur = ("?", 0)
+    for l in dis[start + 1:]:
+        if l.startswith(".text.") or l.startswith("\t.section"):
+            break
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cur = (m.group(1).split("/")[-1], int(m.group(2)))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
+            lines.append(cur)
+    if len(lines) == len(data):
+        best = lines
+        print("matched", dis[start])
         break
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m:
-        cur = (m.group(1).split("/")[-1], int(m.group(2)))
-        continue
-    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
-        lines.append(cur)
-print("sass rows", len(data), "disasm instrs", len(lines))
+if best is None:
+    sys.exit(f"no function with {len(data)} instructions among {[dis[c] for c in cands]}")
+lines = best
 agg = collections.Counter(); st_agg = collections.defaultdict(collections.Counter); instr = collections.Counter()
 tot = 0
 for i, r in enumerate(data):
     n = int(r[idx["# Samples"]] or 0)
-    key = lines[i] if i < len(lines) else ("?", -1)
+    key = lines[i]
     agg[key] += n; tot += n
     instr[key] += int(r[idx["Instructions Executed"]] or 0)
     for s in stalls:
         v = int(r[idx[s]] or 0)
         if v: st_agg[key][s[6:]] += v
-print("total samples", tot)
+print("total samples", tot, "total warp instructions", sum(instr.values()))
 src = {}
 for key, n in sorted(agg.items(), key=lambda x: (x[0][0], x[0][1])):
     if n < min_s: continue
