@@ -78,21 +78,47 @@ int ssdhead_match(const float* gt_xyxy_dev, const float* gt_cls_dev, const int32
                   void* ws_dev, size_t ws_bytes, void* stream);
 
 /* ---- multibox loss fwd(+bwd): ssd / ssd1_, Losses.py:119-199 ------------------------
- * Two kernels.  (1) A persistent streaming kernel reads conf exactly once through a 4-stage
- * TMA/mbarrier shared-memory ring, writes one cross-entropy value per prior and bulk-stores
- * the zero background of the gradients.  (2) One CTA per image selects the k = neg_ratio*npos
- * largest background CE exactly (radix select; descending CE, ties -> lower prior index, T4;
- * positives rank with value 0, Losses.py:190) and writes the gradient rows of positives and
- * mined negatives only, for unit upstream gradients.
+ * Two kernels, exposed separately so that the first can run CONCURRENTLY with ssdhead_match
+ * (it does not depend on the match) and so that a sharded batch can all-reduce the positive
+ * count between them:
+ *
+ * ssdhead_ce_stream  persistent streaming kernel: reads conf exactly once through a 4-stage
+ *                    TMA/mbarrier shared-memory ring and writes, per prior, the cross entropy
+ *                    against the BACKGROUND class (the class of ~99 % of the priors; positives
+ *                    are re-scored by ssdhead_mine from the row it re-reads anyway).  When
+ *                    grad_* are non-null it also bulk-stores the zero background of the dense
+ *                    gradients.
+ * ssdhead_mine       one CTA per image: selects the k = neg_ratio*npos largest background CE
+ *                    exactly (descending CE, ties -> lower prior index, T4; positives rank with
+ *                    value 0, Losses.py:190), sums the loss and writes the gradient rows of
+ *                    positives and mined negatives only, for unit upstream gradients.
+ * ssdhead_multibox_loss = both, back to back on one stream.
+ *
  * `npos_dev`, `best_prior_dev`, `cls_u8_dev` are ssdhead_match's outputs; `npos_norm_dev`
  * points to the int32 positive count the losses/gradients are normalised by (npos_dev+B on
  * one GPU; the all-reduced total when the batch is sharded by image).
  * Outputs: sums double[2] = { sum |loc-enc| over positives, sum CE over positives+mined };
  *          losses float[2] = { sums[0]/(4N), sums[1]/N }  (loc_loss, conf_loss of ssd());
- *          grad_loc [B,P,4], grad_conf [B,P,C] dense (nullable as a pair);
+ *          grad_loc [B,P,4], grad_conf [B,P,C] dense (nullable as a pair; pass the same pair
+ *                 to both calls);
  *          mined_mask uint32 [B, ceil(P/32)] bit p = mined negative (nullable; debug tap);
- *          ce [B,P] per-prior cross entropy (nullable: then it lives in the workspace).
- * The workspace must be zero-filled before its FIRST use; every call leaves its counter zeroed. */
+ *          ce [B,P] per-prior cross entropy (nullable: then it lives in the workspace; pass
+ *                 the same pointer to both calls).
+ * The workspace (same one for both calls) must be zero-filled before its FIRST use; every
+ * call leaves its counter zeroed.  P <= ~31 000 (shared-memory bound of ssdhead_mine).      */
+int ssdhead_ce_stream(const float* conf_dev, int B, int P, int C, float* ce_dev,
+                      float* grad_loc_dev, float* grad_conf_dev,
+                      void* ws_dev, size_t ws_bytes, void* stream);
+int ssdhead_mine(const float* loc_dev, const float* conf_dev,
+                 const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                 const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                 const int32_t* best_prior_dev, const int32_t* npos_dev, const int32_t* npos_norm_dev,
+                 const uint8_t* cls_u8_dev,
+                 int B, int P, int C, int neg_ratio, float pos_iou,
+                 double* sums_dev, float* losses_dev,
+                 float* grad_loc_dev, float* grad_conf_dev,
+                 uint32_t* mined_mask_dev, float* ce_dev,
+                 void* ws_dev, size_t ws_bytes, void* stream);
 int ssdhead_multibox_loss(const float* loc_dev, const float* conf_dev,
                           const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                           const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
@@ -143,7 +169,17 @@ void ssdhead_ctx_destroy(ssdhead_ctx* ctx);
 void* ssdhead_host_alloc(size_t bytes);
 void  ssdhead_host_free(void* p);
 
-/* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair. */
+/* One training-head step on DEVICE tensors in a single call: ssdhead_match on the context's auxiliary
+ * stream beside ssdhead_ce_stream on `stream`, joined before ssdhead_mine.  Asynchronous on `stream`;
+ * sums double[2], losses float[2], grads nullable as a pair (all device pointers). */
+int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* ctx, const float* loc_dev, const float* conf_dev,
+                                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                  int B, int sumG, int neg_ratio, float pos_iou,
+                                  double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                                  void* stream);
+/* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair.
+ * Copies, kernels and copies back are pipelined in image chunks on the context's streams; pass
+ * page-locked buffers (ssdhead_host_alloc) so the copies are asynchronous.  Blocks until done. */
 int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host,
                                    const float* gt_xyxy_host, const float* gt_cls_host, const int32_t* gt_off_host,
                                    int B, int neg_ratio, float pos_iou,

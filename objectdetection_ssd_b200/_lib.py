@@ -31,6 +31,9 @@ SIGNATURES = {
     "ssdhead_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_multibox_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_ce_stream": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_mine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                          _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_finish_loss": (_i, [_vp, _vp, _vp, _vp]),
     "ssdhead_scale_grads": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "ssdhead_detect": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -39,6 +42,7 @@ SIGNATURES = {
     "ssdhead_ctx_destroy": (None, [_vp]),
     "ssdhead_host_alloc": (_vp, [_sz]),
     "ssdhead_host_free": (None, [_vp]),
+    "ssdhead_ctx_multibox_loss_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "ssdhead_ctx_detect_host": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
 }

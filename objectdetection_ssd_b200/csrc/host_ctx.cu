@@ -1,11 +1,279 @@
+// Context front end: owns streams, events, device buffers and workspaces so that one C call runs a
+// whole step - either on device-resident tensors (fork/join of the match beside the CE stream kernel)
+// or on HOST buffers, with the copies pipelined against the kernels in image chunks.
+// Reference call sites: ssd() train_function.py:82 (loss), inference() Losses.py:11-98 (detect).
+#include <algorithm>
+#include <cstring>
+#include <vector>
 #include "common.cuh"
-extern "C" {
-int  ssdhead_ctx_create(ssdhead_ctx**, int, int, int, int, int, int, const float*) { return SSDHEAD_E_UNSUPPORTED; }
-void ssdhead_ctx_destroy(ssdhead_ctx*) {}
-void* ssdhead_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
-void  ssdhead_host_free(void* p) { if (p) cudaFreeHost(p); }
-int ssdhead_ctx_multibox_loss_host(ssdhead_ctx*, const float*, const float*, const float*, const float*, const int32_t*,
-                                   int, int, float, float*, float*, float*) { return SSDHEAD_E_UNSUPPORTED; }
-int ssdhead_ctx_detect_host(ssdhead_ctx*, const float*, const float*, int, float, float,
-                            float*, float*, int32_t*, int32_t*, int32_t*) { return SSDHEAD_E_UNSUPPORTED; }
+
+using namespace ssdhead;
+
+namespace ssdhead {
+// Util.py:93-96 on the host for the one-off prior table (same fp32 operations as the device helper)
+static void priors_xyxy_host(const float* cxcywh, float* xyxy, int P)
+{
+    for (int i = 0; i < P; ++i) {
+        const float cx = cxcywh[4 * i], cy = cxcywh[4 * i + 1];
+        const volatile float hw = cxcywh[4 * i + 2] / 2.0f, hh = cxcywh[4 * i + 3] / 2.0f;
+        xyxy[4 * i] = cx - hw; xyxy[4 * i + 1] = cy - hh; xyxy[4 * i + 2] = cx + hw; xyxy[4 * i + 3] = cy + hh;
+    }
 }
+__global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nchunks, const int* __restrict__ npos_norm,
+                                  double* __restrict__ sums, float* __restrict__ losses)
+{
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < nchunks; ++i) { a += chunk_sums[2 * i]; c += chunk_sums[2 * i + 1]; }
+    sums[0] = a; sums[1] = c;
+    const double N = (double)(*npos_norm);
+    losses[0] = (float)(a / (4.0 * N));
+    losses[1] = (float)(c / N);
+}
+}  // namespace ssdhead
+
+struct ssdhead_ctx {
+    int device, maxB, P, C, max_sumG, top_k;
+    cudaStream_t s_main, s_aux, s_h2d, s_d2h;
+    cudaEvent_t ev_fork, ev_join, ev_gt, ev_done;
+    std::vector<cudaEvent_t> ev_in, ev_out;            // per chunk
+    // prior tables
+    float *pri_cxcywh, *pri_xyxy;
+    // gt + match outputs
+    float *gt_xyxy, *gt_cls;
+    int32_t *gt_off, *best_prior, *npos;
+    uint8_t* cls_u8;
+    // head tensors (host-buffer path)
+    float *loc, *conf, *grad_loc, *grad_conf;
+    double *sums, *chunk_sums;
+    float *losses;
+    // workspaces
+    void *ws_match, *ws_loss, *ws_detect;
+    size_t ws_match_bytes, ws_loss_bytes, ws_detect_bytes;
+    // detect outputs (host-buffer path)
+    float *det_boxes, *det_prob;
+    int32_t *det_cls, *det_prior, *det_cnt;
+    // pinned scratch for small results
+    float* h_losses;
+};
+
+#define CTX_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
+
+static const int kMaxChunks = 8;
+
+extern "C" {
+
+void* ssdhead_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void ssdhead_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void ssdhead_ctx_destroy(ssdhead_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    void* bufs[] = {c->pri_cxcywh, c->pri_xyxy, c->gt_xyxy, c->gt_cls, c->gt_off, c->best_prior, c->npos, c->cls_u8,
+                    c->loc, c->conf, c->grad_loc, c->grad_conf, c->sums, c->chunk_sums, c->losses,
+                    c->ws_match, c->ws_loss, c->ws_detect, c->det_boxes, c->det_prob, c->det_cls, c->det_prior, c->det_cnt};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (c->h_losses) cudaFreeHost(c->h_losses);
+    cudaStream_t st[] = {c->s_main, c->s_aux, c->s_h2d, c->s_d2h};
+    for (cudaStream_t s : st) if (s) cudaStreamDestroy(s);
+    cudaEvent_t ev[] = {c->ev_fork, c->ev_join, c->ev_gt, c->ev_done};
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_out) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+int ssdhead_ctx_create(ssdhead_ctx** out, int device, int maxB, int P, int C, int max_sumG, int top_k,
+                       const float* pri_cxcywh_host)
+{
+    if (!out || maxB <= 0 || P <= 0 || C < 2 || max_sumG < 0 || top_k <= 0 || !pri_cxcywh_host) return SSDHEAD_E_BADARG;
+    int rc = 0;
+    ssdhead_ctx* c = new ssdhead_ctx();
+    c->device = device; c->maxB = maxB; c->P = P; c->C = C; c->max_sumG = std::max(max_sumG, 1); c->top_k = top_k;
+    {
+        const size_t nrow = (size_t)maxB * P;
+        std::vector<float> xy((size_t)P * 4);
+        priors_xyxy_host(pri_cxcywh_host, xy.data(), P);
+        CTX_CUDA(cudaSetDevice(device));
+        CTX_CUDA(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+        CTX_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+        CTX_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CTX_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        CTX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CTX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CTX_CUDA(cudaEventCreateWithFlags(&c->ev_gt, cudaEventDisableTiming));
+        CTX_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        c->ev_in.assign(kMaxChunks, nullptr);
+        c->ev_out.assign(kMaxChunks, nullptr);
+        for (int i = 0; i < kMaxChunks; ++i) {
+            CTX_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CTX_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        }
+        CTX_CUDA(cudaMalloc(&c->pri_cxcywh, (size_t)P * 16));
+        CTX_CUDA(cudaMalloc(&c->pri_xyxy, (size_t)P * 16));
+        CTX_CUDA(cudaMemcpy(c->pri_cxcywh, pri_cxcywh_host, (size_t)P * 16, cudaMemcpyHostToDevice));
+        CTX_CUDA(cudaMemcpy(c->pri_xyxy, xy.data(), (size_t)P * 16, cudaMemcpyHostToDevice));
+        CTX_CUDA(cudaMalloc(&c->gt_xyxy, (size_t)c->max_sumG * 16));
+        CTX_CUDA(cudaMalloc(&c->gt_cls, (size_t)c->max_sumG * 4));
+        CTX_CUDA(cudaMalloc(&c->gt_off, (size_t)(maxB + 1) * 4));
+        CTX_CUDA(cudaMalloc(&c->best_prior, (size_t)c->max_sumG * 4));
+        CTX_CUDA(cudaMalloc(&c->npos, (size_t)(maxB + 1) * 4));
+        CTX_CUDA(cudaMalloc(&c->cls_u8, round_up(nrow, 16)));
+        CTX_CUDA(cudaMalloc(&c->loc, nrow * 16));
+        CTX_CUDA(cudaMalloc(&c->conf, nrow * C * 4));
+        CTX_CUDA(cudaMalloc(&c->grad_loc, nrow * 16));
+        CTX_CUDA(cudaMalloc(&c->grad_conf, nrow * C * 4));
+        CTX_CUDA(cudaMalloc(&c->sums, 2 * sizeof(double)));
+        CTX_CUDA(cudaMalloc(&c->chunk_sums, 2 * kMaxChunks * sizeof(double)));
+        CTX_CUDA(cudaMalloc(&c->losses, 2 * sizeof(float)));
+        c->ws_match_bytes = ssdhead_workspace_bytes(SSDHEAD_WS_MATCH, maxB, P, C, c->max_sumG);
+        c->ws_loss_bytes = ssdhead_workspace_bytes(SSDHEAD_WS_LOSS, maxB, P, C, 0);
+        c->ws_detect_bytes = ssdhead_workspace_bytes(SSDHEAD_WS_DETECT, maxB, P, C, 0);
+        CTX_CUDA(cudaMalloc(&c->ws_match, c->ws_match_bytes));
+        CTX_CUDA(cudaMemset(c->ws_match, 0, c->ws_match_bytes));
+        if (c->ws_loss_bytes) {
+            // one workspace per chunk slot so chunk i+1 can stream while chunk i is being mined
+            CTX_CUDA(cudaMalloc(&c->ws_loss, c->ws_loss_bytes * kMaxChunks));
+            CTX_CUDA(cudaMemset(c->ws_loss, 0, c->ws_loss_bytes * kMaxChunks));
+        }
+        if (c->ws_detect_bytes) {
+            CTX_CUDA(cudaMalloc(&c->ws_detect, c->ws_detect_bytes));
+            CTX_CUDA(cudaMemset(c->ws_detect, 0, c->ws_detect_bytes));
+        }
+        CTX_CUDA(cudaMalloc(&c->det_boxes, (size_t)maxB * top_k * 16));
+        CTX_CUDA(cudaMalloc(&c->det_prob, (size_t)maxB * top_k * 4));
+        CTX_CUDA(cudaMalloc(&c->det_cls, (size_t)maxB * top_k * 4));
+        CTX_CUDA(cudaMalloc(&c->det_prior, (size_t)maxB * top_k * 4));
+        CTX_CUDA(cudaMalloc(&c->det_cnt, (size_t)maxB * 4));
+        CTX_CUDA(cudaHostAlloc(&c->h_losses, 64, cudaHostAllocDefault));
+    }
+    *out = c;
+    return 0;
+fail:
+    ssdhead_ctx_destroy(c);
+    return rc;
+}
+
+// One training-head step on DEVICE tensors: the match runs on the context's auxiliary stream beside the CE
+// streaming kernel (which does not depend on it); both join before the mining kernel.  Asynchronous on `stream`.
+int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float* conf,
+                                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
+                                  int neg_ratio, float pos_iou,
+                                  double* sums, float* losses, float* grad_loc, float* grad_conf, void* stream)
+{
+    if (!c) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    SSD_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
+    SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+    int rc = ssdhead_match(gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
+                           c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
+    if (rc) return rc;
+    SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
+    rc = ssdhead_ce_stream(conf, B, c->P, c->C, nullptr, grad_loc, grad_conf, c->ws_loss, c->ws_loss_bytes, st);
+    if (rc) return rc;
+    SSD_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+    return ssdhead_mine(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, c->best_prior, c->npos, c->npos + B,
+                        c->cls_u8, B, c->P, c->C, neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, nullptr, nullptr,
+                        c->ws_loss, c->ws_loss_bytes, st);
+}
+
+// ssd() on HOST buffers (pass page-locked memory, e.g. ssdhead_host_alloc, for asynchronous copies).
+// gt goes first and the match starts at once; conf/loc travel in image chunks, each chunk is streamed
+// (CE) and mined as soon as it lands while the next one is in flight, and its gradient slice returns on a
+// third stream: H2D, kernels and D2H overlap.  Blocks until the results are in host memory.
+int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const float* conf_h,
+                                   const float* gt_xyxy_h, const float* gt_cls_h, const int32_t* gt_off_h,
+                                   int B, int neg_ratio, float pos_iou,
+                                   float* losses_h, float* grad_loc_h, float* grad_conf_h)
+{
+    if (!c || !loc_h || !conf_h || !gt_off_h || !losses_h) return SSDHEAD_E_BADARG;
+    if ((grad_loc_h == nullptr) != (grad_conf_h == nullptr)) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB) return SSDHEAD_E_STATE;
+    const int sumG = gt_off_h[B];
+    if (sumG < 0 || sumG > c->max_sumG || (sumG > 0 && (!gt_xyxy_h || !gt_cls_h))) return SSDHEAD_E_STATE;
+    SSD_CHECK_CUDA(cudaSetDevice(c->device));
+    const int P = c->P, C = c->C;
+    const bool grads = grad_loc_h != nullptr;
+
+    // gt -> device, match on the auxiliary stream
+    if (sumG > 0) {
+        SSD_CHECK_CUDA(cudaMemcpyAsync(c->gt_xyxy, gt_xyxy_h, (size_t)sumG * 16, cudaMemcpyHostToDevice, c->s_aux));
+        SSD_CHECK_CUDA(cudaMemcpyAsync(c->gt_cls, gt_cls_h, (size_t)sumG * 4, cudaMemcpyHostToDevice, c->s_aux));
+    }
+    SSD_CHECK_CUDA(cudaMemcpyAsync(c->gt_off, gt_off_h, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, c->s_aux));
+    int rc = ssdhead_match(c->gt_xyxy, c->gt_cls, c->gt_off, c->pri_xyxy, B, P, C, sumG, pos_iou,
+                           c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
+    if (rc) return rc;
+    SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
+
+    const int nchunks = std::min(kMaxChunks, std::max(1, B / 8));
+    const int per = (B + nchunks - 1) / nchunks;
+    int used = 0;
+    for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+        const int nb = std::min(per, B - b0);
+        const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
+        SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf + r0 * C, conf_h + r0 * C, nr * C * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc + r0 * 4, loc_h + r0 * 4, nr * 16, cudaMemcpyHostToDevice, c->s_h2d));
+        SSD_CHECK_CUDA(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_in[k], 0));
+        void* ws = (char*)c->ws_loss + (size_t)k * c->ws_loss_bytes;
+        float* gl = grads ? c->grad_loc + r0 * 4 : nullptr;
+        float* gc = grads ? c->grad_conf + r0 * C : nullptr;
+        rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, gl, gc, ws, c->ws_loss_bytes, c->s_main);
+        if (rc) return rc;
+        if (k == 0) SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
+        rc = ssdhead_mine(c->loc + r0 * 4, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
+                          c->best_prior, c->npos + b0, c->npos + B, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
+                          c->chunk_sums + 2 * k, c->losses, gl, gc, nullptr, nullptr, ws, c->ws_loss_bytes, c->s_main);
+        if (rc) return rc;
+        if (grads) {
+            SSD_CHECK_CUDA(cudaEventRecord(c->ev_out[k], c->s_main));
+            SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_out[k], 0));
+            SSD_CHECK_CUDA(cudaMemcpyAsync(grad_conf_h + r0 * C, gc, nr * C * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            SSD_CHECK_CUDA(cudaMemcpyAsync(grad_loc_h + r0 * 4, gl, nr * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        used = k + 1;
+    }
+    sum_chunks_kernel<<<1, 1, 0, c->s_main>>>(c->chunk_sums, used, c->npos + B, c->sums, c->losses);
+    count_launch();
+    SSD_LAUNCH_CHECK();
+    SSD_CHECK_CUDA(cudaMemcpyAsync(c->h_losses, c->losses, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->s_main));
+    SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_main));
+    if (grads) SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_d2h));
+    losses_h[0] = c->h_losses[0];
+    losses_h[1] = c->h_losses[1];
+    return 0;
+}
+
+// inference() over a batch on HOST buffers: copies in, ssdhead_detect, detections out.  Blocks.
+int ssdhead_ctx_detect_host(ssdhead_ctx* c, const float* loc_h, const float* conf_h, int B,
+                            float min_score, float iou_thr,
+                            float* out_boxes_h, float* out_prob_h, int32_t* out_cls_h, int32_t* out_prior_h, int32_t* out_cnt_h)
+{
+    if (!c || !loc_h || !conf_h || !out_boxes_h || !out_prob_h || !out_cls_h || !out_cnt_h) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB || !c->ws_detect) return SSDHEAD_E_STATE;
+    SSD_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t nr = (size_t)B * c->P;
+    SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf, conf_h, nr * c->C * 4, cudaMemcpyHostToDevice, c->s_main));
+    SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc, loc_h, nr * 16, cudaMemcpyHostToDevice, c->s_main));
+    const int rc = ssdhead_detect(c->loc, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k,
+                                  c->det_boxes, c->det_prob, c->det_cls, c->det_prior, c->det_cnt,
+                                  c->ws_detect, c->ws_detect_bytes, c->s_main);
+    if (rc) return rc;
+    const size_t nk = (size_t)B * c->top_k;
+    SSD_CHECK_CUDA(cudaMemcpyAsync(out_boxes_h, c->det_boxes, nk * 16, cudaMemcpyDeviceToHost, c->s_main));
+    SSD_CHECK_CUDA(cudaMemcpyAsync(out_prob_h, c->det_prob, nk * 4, cudaMemcpyDeviceToHost, c->s_main));
+    SSD_CHECK_CUDA(cudaMemcpyAsync(out_cls_h, c->det_cls, nk * 4, cudaMemcpyDeviceToHost, c->s_main));
+    if (out_prior_h) SSD_CHECK_CUDA(cudaMemcpyAsync(out_prior_h, c->det_prior, nk * 4, cudaMemcpyDeviceToHost, c->s_main));
+    SSD_CHECK_CUDA(cudaMemcpyAsync(out_cnt_h, c->det_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, c->s_main));
+    SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_main));
+    return 0;
+}
+
+}  // extern "C"

@@ -61,7 +61,7 @@ constexpr int CE_THREADS = CE_ROWS + 32;          // + one producer warp
 
 template <int C, bool ZERO_FILL>
 __global__ void __launch_bounds__(CE_THREADS, 2)
-ce_stream_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ cls_u8, float* __restrict__ ce_out,
+ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
                  float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma)
 {
     constexpr uint32_t TILE_BYTES = CE_ROWS * C * 4;
@@ -109,9 +109,8 @@ ce_stream_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ cls
         uint32_t ph = 0;
         for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
             const long long row = tile * CE_ROWS + t;
-            const int c = (int)cls_u8[row];
             mbar_wait(&s_full[s], ph);
-            const float ce = row_cross_entropy<C>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, c);
+            const float ce = row_cross_entropy<C>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
             ce_out[row] = ce;
@@ -120,7 +119,7 @@ ce_stream_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ cls
         // rows past the last full tile (or every row when the pointers are not 16-byte aligned): plain loads
         const long long rest0 = full_tiles * CE_ROWS;
         for (long long row = rest0 + (long long)blockIdx.x * CE_ROWS + t; row < total_rows; row += (long long)gridDim.x * CE_ROWS) {
-            ce_out[row] = row_cross_entropy<C>(conf + (size_t)row * C, (int)cls_u8[row]);
+            ce_out[row] = row_cross_entropy<C>(conf + (size_t)row * C, C - 1);
             if (ZERO_FILL) {
 #pragma unroll
                 for (int q = 0; q < C; ++q) grad_conf[(size_t)row * C + q] = 0.0f;
@@ -141,7 +140,8 @@ constexpr int MN_BINS = 2048;
 struct MineParams {
     const float* loc;
     const float* conf;
-    const float* ce;
+    const float* ce;             // CE of every row against the BACKGROUND class (ce_stream_kernel)
+    float* ce_tap;               // nullable: receives the true CE of positive rows (debug tap)
     const uint8_t* cls_u8;
     const float4* gt_xyxy;
     const float* gt_cls;
@@ -193,7 +193,7 @@ mine_kernel(const MineParams p)
     uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_raw);            // [P]  CE bit pattern, 0 for positives; bit 31 = selected
     uint32_t* s_hist = s_key + p.P;                                      // [MN_BINS]
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_hist + MN_BINS);    // [P]  rows that carry a gradient (P < 65536)
-    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_list + ((p.P + 1) & ~1)); // [P]  class bytes
+    uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_list + ((p.P + 7) & ~7)); // [P]  class bytes (16-byte aligned)
     __shared__ uint32_t s_warp[MN_W + 1];
     __shared__ uint32_t s_sel[3];
     __shared__ uint32_t s_nsel, s_ncand, s_max;
@@ -221,15 +221,39 @@ mine_kernel(const MineParams p)
     }
     __syncthreads();
     uint32_t kmax = 0u;
-    for (int j = t; j < P; j += MN_T) {
-        const float ce = p.ce[row0 + j];
-        const uint8_t c = p.cls_u8[row0 + j];
-        const bool pos = (int)c != p.bg_class;
-        if (pos) acc_ce += (double)ce;
-        const uint32_t key = pos ? 0u : (__float_as_uint(ce) & 0x7fffffffu);
-        s_key[j] = key;
-        s_cls[j] = c;
-        kmax = max(kmax, key);
+    const bool vec_ok = ((P & 3) == 0) && (((row0 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.ce) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.cls_u8) & 3) == 0);
+    if (vec_ok) {
+        // 16-byte CE loads + 4-byte class loads, several in flight per thread
+        const float4* ce4 = reinterpret_cast<const float4*>(p.ce + row0);
+        const uchar4* cl4 = reinterpret_cast<const uchar4*>(p.cls_u8 + row0);
+        const int nvec = P >> 2;
+#pragma unroll 4
+        for (int v = t; v < nvec; v += MN_T) {
+            const float4 e = ce4[v];
+            const uchar4 c = cl4[v];
+            const float ev[4] = {e.x, e.y, e.z, e.w};
+            const uint8_t cv[4] = {c.x, c.y, c.z, c.w};
+            uint32_t kv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool pos = (int)cv[q] != p.bg_class;
+                kv[q] = pos ? 0u : (__float_as_uint(ev[q]) & 0x7fffffffu);
+                kmax = max(kmax, kv[q]);
+            }
+            reinterpret_cast<uint4*>(s_key)[v] = make_uint4(kv[0], kv[1], kv[2], kv[3]);
+            reinterpret_cast<uchar4*>(s_cls)[v] = c;
+        }
+    } else {
+        for (int j = t; j < P; j += MN_T) {
+            const float ce = p.ce[row0 + j];
+            const uint8_t c = p.cls_u8[row0 + j];
+            const bool pos = (int)c != p.bg_class;
+            const uint32_t key = pos ? 0u : (__float_as_uint(ce) & 0x7fffffffu);
+            s_key[j] = key;
+            s_cls[j] = c;
+            kmax = max(kmax, key);
+        }
     }
     kmax = __reduce_max_sync(FULL, kmax);
     if (lane == 0) atomicMax(&s_max, kmax);
@@ -239,6 +263,7 @@ mine_kernel(const MineParams p)
     // ---- 2. the k largest keys, ties to the lower prior index (T4): mark them with bit 31 ----
     const long long kk = (long long)p.neg_ratio * (long long)p.npos[b];
     const uint32_t k = (uint32_t)min((long long)P, max(0ll, kk));
+    bool listed = false;                         // the row list was already built by the fast path
     if (k >= (uint32_t)P) {
         for (int j = t; j < P; j += MN_T) s_key[j] |= 0x80000000u;
     } else if (k > 0u) {
@@ -271,21 +296,44 @@ mine_kernel(const MineParams p)
             const uint32_t need = k - s_sel[1], cnt = s_sel[2];
             if (cnt <= (uint32_t)MN_CAND) {
                 done = true;
+                listed = true;
+                // one pass: rows above the boundary bin are mined, rows in it become candidates, positives are listed
                 for (int j = t; j < P; j += MN_T) {
                     const uint32_t key = s_key[j];
+                    const bool pos = (int)s_cls[j] != p.bg_class;
                     const int bin = (int)__fmul_rn(__uint_as_float(key), scale);
-                    if (bin > bq) s_key[j] = key | 0x80000000u;
-                    else if (bin == bq) { const uint32_t s = atomicAdd(&s_ncand, 1u); s_ckey[s] = key; s_cidx[s] = (uint32_t)j; }
+                    if (pos) {
+                        s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
+                    } else if (bin > bq) {
+                        acc_ce += (double)__uint_as_float(key);
+                        if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
+                        if (GRADS) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
+                    } else if (bin == bq) {
+                        const uint32_t s = atomicAdd(&s_ncand, 1u);
+                        s_ckey[s] = key;
+                        s_cidx[s] = (uint32_t)j;
+                    }
                 }
                 __syncthreads();
-                if ((uint32_t)t < cnt) {
+                // positives in the boundary bin (key 0, only when bq == 0) were listed above, not made candidates;
+                // they still occupy ranks: `need` counts them, so rank them through the candidate count of bin 0
+                const uint32_t ncand = s_ncand;
+                if ((uint32_t)t < ncand) {
                     const uint32_t mk = s_ckey[t], mi = s_cidx[t];
                     uint32_t rank = 0u;
-                    for (uint32_t q = 0; q < cnt; ++q) {
+                    for (uint32_t q = 0; q < ncand; ++q) {
                         const uint32_t ok = s_ckey[q], oi = s_cidx[q];
                         rank += (ok > mk || (ok == mk && oi < mi)) ? 1u : 0u;
                     }
-                    if (rank < need) s_key[mi] = mk | 0x80000000u;
+                    if (bq == 0) {
+                        // positives (value 0) tie with zero-CE negatives: ties go to the lower prior index
+                        if (mk == 0u) for (int j = 0; j < (int)mi; ++j) rank += ((int)s_cls[j] != p.bg_class) ? 1u : 0u;
+                    }
+                    if (rank < need) {
+                        acc_ce += (double)__uint_as_float(mk);
+                        if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (mi >> 5)], 1u << (mi & 31));
+                        if (GRADS) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)mi;
+                    }
                 }
             }
         }
@@ -340,16 +388,17 @@ mine_kernel(const MineParams p)
     __syncthreads();
 
     // ---- 3. mined CE sum, list of rows that carry a gradient ----
-    for (int j = t; j < P; j += MN_T) {
-        const uint32_t key = s_key[j];
-        const int c = (int)s_cls[j];
-        const bool pos = c != p.bg_class;
-        const bool mined = (key >> 31) && !pos;
-        if (mined) {
-            acc_ce += (double)__uint_as_float(key & 0x7fffffffu);
-            if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
+    if (!listed) {
+        for (int j = t; j < P; j += MN_T) {
+            const uint32_t key = s_key[j];
+            const bool pos = (int)s_cls[j] != p.bg_class;
+            const bool mined = (key >> 31) && !pos;
+            if (mined) {
+                acc_ce += (double)__uint_as_float(key & 0x7fffffffu);
+                if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
+            }
+            if (pos || (GRADS && mined)) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
         }
-        if (pos || (GRADS && mined)) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
     }
     __syncthreads();
 
@@ -364,7 +413,7 @@ mine_kernel(const MineParams p)
         const bool pos = c != p.bg_class;
         float x[C];
         float4 pb, pc, l;
-        if (GRADS) {
+        if (GRADS || pos) {
             const float* row = p.conf + (row0 + j) * C;
 #pragma unroll
             for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
@@ -373,6 +422,13 @@ mine_kernel(const MineParams p)
             pb = p.pri_xyxy[j];
             pc = p.pri_cxcywh[j];
             l = reinterpret_cast<const float4*>(p.loc)[row0 + j];
+        }
+        if (pos) {
+            // the streaming kernel scored every row against the background class; a positive row gets its
+            // true-class CE here, from the row it re-reads anyway (same code -> same bits as a direct evaluation)
+            const float ce = row_cross_entropy<C>(x, c);
+            acc_ce += (double)ce;
+            if (p.ce_tap) p.ce_tap[row0 + j] = ce;
         }
         if (GRADS) {
             float m = x[0];
@@ -484,7 +540,7 @@ scale_grads_kernel(float4* __restrict__ gl, size_t n4_loc, float* __restrict__ g
     }
 }
 
-static size_t mine_smem_bytes(int P) { return (size_t)P * 4 + MN_BINS * 4 + (size_t)((P + 1) & ~1) * 2 + round_up((size_t)P, 16); }
+static size_t mine_smem_bytes(int P) { return (size_t)P * 4 + MN_BINS * 4 + (size_t)((P + 7) & ~7) * 2 + round_up((size_t)P, 16); }
 
 // workspace: [0,16) done counter | partials double[2B] | CE float[B*P] (when the caller passes no ce buffer)
 size_t loss_workspace_bytes(int B, int P, int C)
@@ -505,20 +561,24 @@ static int num_sms()
 }
 
 template <int C, bool GRADS>
-static int launch_loss(const float* conf, const uint8_t* cls_u8, float* ce, MineParams& prm, cudaStream_t st)
+static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, float* grad_loc, long long rows, cudaStream_t st)
 {
-    const long long rows = (long long)prm.B * prm.P;
     constexpr size_t tile = (size_t)CE_ROWS * C * 4;
     const size_t smem_ce = tile * CE_STAGES + (GRADS ? tile : 0);
     auto kce = ce_stream_kernel<C, GRADS>;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ce));
-    const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(prm.grad_conf) && aligned16(prm.grad_loc)))) ? 1 : 0;
+    const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(grad_conf) && aligned16(grad_loc)))) ? 1 : 0;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS;
     const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
-    kce<<<grid_ce, CE_THREADS, smem_ce, st>>>(conf, cls_u8, ce, prm.grad_conf, prm.grad_loc, rows, use_tma);
+    kce<<<grid_ce, CE_THREADS, smem_ce, st>>>(conf, ce, grad_conf, grad_loc, rows, use_tma);
     count_launch();
     SSD_LAUNCH_CHECK();
+    return 0;
+}
 
+template <int C, bool GRADS>
+static int launch_mine(const MineParams& prm, cudaStream_t st)
+{
     auto kmn = mine_kernel<C, GRADS>;
     const size_t smem_mn = mine_smem_bytes(prm.P);
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
@@ -528,26 +588,45 @@ static int launch_loss(const float* conf, const uint8_t* cls_u8, float* ce, Mine
     return 0;
 }
 
+static float* ws_ce(void* ws, int B) { return (float*)((char*)ws + 16 + round_up((size_t)B * 2 * sizeof(double), 16)); }
+
 }  // namespace ssdhead
 
 using namespace ssdhead;
 
 extern "C" {
 
-int ssdhead_multibox_loss(const float* loc, const float* conf,
-                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
-                          const float* pri_xyxy, const float* pri_cxcywh,
-                          const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
-                          int B, int P, int C, int neg_ratio, float pos_iou,
-                          double* sums, float* losses, float* grad_loc, float* grad_conf,
-                          uint32_t* mined_mask, float* ce,
-                          void* ws, size_t ws_bytes, void* stream)
+int ssdhead_ce_stream(const float* conf, int B, int P, int C, float* ce, float* grad_loc, float* grad_conf,
+                      void* ws, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || P <= 0 || !conf || !ws) return SSDHEAD_E_BADARG;
+    if ((grad_loc == nullptr) != (grad_conf == nullptr)) return SSDHEAD_E_BADARG;
+    if (C != 21) return SSDHEAD_E_UNSUPPORTED;          // VOC head of the reference (Losses.py:184 hard-codes 21)
+    if (B == 0) return 0;
+    if ((grad_loc && !aligned16(grad_loc)) || !aligned16(ws)) return SSDHEAD_E_ALIGN;
+    const size_t need = loss_workspace_bytes(B, P, C);
+    if (need == 0) return SSDHEAD_E_UNSUPPORTED;
+    if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
+    float* ce_buf = ce ? ce : ws_ce(ws, B);
+    const long long rows = (long long)B * P;
+    return grad_loc ? launch_ce_stream<21, true>(conf, ce_buf, grad_conf, grad_loc, rows, (cudaStream_t)stream)
+                    : launch_ce_stream<21, false>(conf, ce_buf, nullptr, nullptr, rows, (cudaStream_t)stream);
+}
+
+int ssdhead_mine(const float* loc, const float* conf,
+                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                 const float* pri_xyxy, const float* pri_cxcywh,
+                 const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
+                 int B, int P, int C, int neg_ratio, float pos_iou,
+                 double* sums, float* losses, float* grad_loc, float* grad_conf,
+                 uint32_t* mined_mask, float* ce,
+                 void* ws, size_t ws_bytes, void* stream)
 {
     if (B < 0 || P <= 0 || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!loc || !conf || !gt_off || !pri_xyxy || !pri_cxcywh || !npos || !npos_norm || !cls_u8 || !sums || !losses || !ws)
         return SSDHEAD_E_BADARG;
     if ((grad_loc == nullptr) != (grad_conf == nullptr)) return SSDHEAD_E_BADARG;
-    if (C != 21) return SSDHEAD_E_UNSUPPORTED;          // VOC head of the reference (Losses.py:184 hard-codes 21)
+    if (C != 21) return SSDHEAD_E_UNSUPPORTED;
     if (B == 0) return 0;
     if (!aligned16(loc) || !aligned16(pri_xyxy) || !aligned16(pri_cxcywh) || (gt_xyxy && !aligned16(gt_xyxy)) ||
         (grad_loc && !aligned16(grad_loc)) || !aligned16(ws))
@@ -567,12 +646,25 @@ int ssdhead_multibox_loss(const float* loc, const float* conf,
     prm.mined_mask = mined_mask;
     prm.done_counter = (unsigned int*)ws;
     prm.partials = (double*)((char*)ws + 16);
-    float* ce_buf = ce ? ce : (float*)((char*)ws + 16 + round_up((size_t)B * 2 * sizeof(double), 16));
-    prm.ce = ce_buf;
+    prm.ce = ce ? ce : ws_ce(ws, B);
+    prm.ce_tap = ce;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
+    return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
+}
 
-    return grad_loc ? launch_loss<21, true>(conf, cls_u8, ce_buf, prm, st)
-                    : launch_loss<21, false>(conf, cls_u8, ce_buf, prm, st);
+int ssdhead_multibox_loss(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
+                          int B, int P, int C, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint32_t* mined_mask, float* ce,
+                          void* ws, size_t ws_bytes, void* stream)
+{
+    const int rc = ssdhead_ce_stream(conf, B, P, C, ce, grad_loc, grad_conf, ws, ws_bytes, stream);
+    if (rc != 0) return rc;
+    return ssdhead_mine(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, best_prior, npos, npos_norm, cls_u8,
+                        B, P, C, neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, mined_mask, ce, ws, ws_bytes, stream);
 }
 
 int ssdhead_finish_loss(const double* sums, const int32_t* npos_norm, float* losses, void* stream)

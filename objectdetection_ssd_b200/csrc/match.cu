@@ -12,6 +12,7 @@
 // publishes the batch total npos[B].  The workspace is left zeroed (self-cleaning): no memsets.
 // HBM traffic is negligible (gt + priors in, one class byte per prior out); the kernel exists so the
 // loss kernels know the class of every prior and the batch-global positive count.
+#include <algorithm>
 #include "common.cuh"
 
 namespace ssdhead {
@@ -21,7 +22,7 @@ constexpr int MPPT = 4;          // consecutive priors per thread
 constexpr int MTILE = MT * MPPT; // priors per CTA
 constexpr int MGC = 64;          // gt boxes staged per chunk
 
-__global__ void __launch_bounds__(MT)
+__global__ void __launch_bounds__(MT, 5)
 match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cls, const int* __restrict__ gt_off,
              const float4* __restrict__ pri_xyxy, int B, int P, int bg_class, float pos_iou,
              int* __restrict__ best_prior, int* __restrict__ npos, uint8_t* __restrict__ cls_u8,
@@ -35,81 +36,114 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
     __shared__ int s_red[MT / 32];
     __shared__ int s_last;
 
-    const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int off0 = gt_off[b];
     const int G = gt_off[b + 1] - off0;
-    const int p0 = tile * MTILE + t * MPPT;          // first prior of this thread
+    const int ntiles = (P + MTILE - 1) / MTILE;
+    const bool one_chunk = G <= MGC;                 // the usual case: gts staged once, per-gt keys merged over the CTA's tiles
+    int cnt = 0;
 
-    float4 pb[MPPT];
-    float pa[MPPT], best[MPPT];
-    int bestg[MPPT];
-#pragma unroll
-    for (int i = 0; i < MPPT; ++i) {
-        pb[i] = (p0 + i < P) ? pri_xyxy[p0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        pa[i] = box_area(pb[i]);
-        best[i] = 0.0f;            // IoU >= 0 and ties keep the first gt: starting at (0, gt 0) equals max() over the column
-        bestg[i] = 0;
-    }
-    const bool first_warp = (tile == 0 && warp == 0);   // owns prior 0: the argmax of an all-zero IoU row (T2)
-
-    for (int g0 = 0; g0 < G; g0 += MGC) {
-        const int gc = min(MGC, G - g0);
-        __syncthreads();
-        if (t < gc) {
-            const float4 bx = gt_xyxy[off0 + g0 + t];
+    if (one_chunk) {
+        if (t < G) {
+            const float4 bx = gt_xyxy[off0 + t];
             s_box[t] = bx;
             s_area[t] = box_area(bx);
             s_key[t] = 0ull;
         }
         __syncthreads();
-        for (int g = 0; g < gc; ++g) {
-            const float4 gb = s_box[g];
-            const float ga = s_area[g];
-            float tv = 0.0f;           // this thread's best IoU for gt g (IoU >= 0), lowest prior on ties
-            int ti = 0;
-#pragma unroll
-            for (int i = 0; i < MPPT; ++i) {
-                // disjoint boxes (the common case) have IoU == +0 exactly: no multiply, no IEEE division
-                const float dx = __fsub_rn(fminf(gb.z, pb[i].z), fmaxf(gb.x, pb[i].x));
-                const float dy = __fsub_rn(fminf(gb.w, pb[i].w), fmaxf(gb.y, pb[i].y));
-                if (dx > 0.0f && dy > 0.0f) {
-                    const float inter = __fmul_rn(dx, dy);
-                    const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, pa[i]), inter));
-                    if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }      // T1: strict > keeps the first gt
-                    if (v > tv) { tv = v; ti = i; }                           // strict > keeps the lower prior
-                }
-            }
-            const uint32_t m = __reduce_max_sync(FULL, __float_as_uint(tv));  // IoU >= 0: bits order like values
-            if (m != 0u || first_warp) {                                      // some IoU > 0, or the warp owning prior 0
-                const unsigned ball = __ballot_sync(FULL, __float_as_uint(tv) == m);
-                const int src = __ffs(ball) - 1;                              // T2: lowest lane = lowest prior
-                const int wi = __shfl_sync(FULL, ti, src);
-                if (lane == 0) {
-                    const uint32_t wprior = (uint32_t)(tile * MTILE + (warp * 32 + src) * MPPT + wi);
-                    atomicMax(&s_key[g], ((unsigned long long)(m | 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - wprior));
-                }
-            }
-        }
-        __syncthreads();
-        if (t < gc && s_key[t] != 0ull) atomicMax(&best_key[off0 + g0 + t], s_key[t]);
     }
 
-    // natural (pre-override) match of this tile: one class byte per prior
-    int cnt = 0;
-    uint32_t packed = 0u;
+    // a CTA walks several tiles of its image so that the fixed latencies (gt fetch, fences, counters) are paid once
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * MTILE + t * MPPT;      // first prior of this thread
+        float4 pb[MPPT];
+        float pa[MPPT], best[MPPT];
+        int bestg[MPPT];
 #pragma unroll
-    for (int i = 0; i < MPPT; ++i) {
-        const int p = p0 + i;
-        const bool hit = (G > 0) && !(best[i] < pos_iou);                       // T6: matched <=> not (iou < thr)
-        const int c = (hit && p < P) ? (int)gt_cls[off0 + bestg[i]] : bg_class;
-        packed |= (uint32_t)(c & 0xff) << (8 * i);
-        if (p < P) {
-            cnt += (c != bg_class) ? 1 : 0;                                     // positive <=> class != bg (Losses.py:179)
-            if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + bestg[i];
-            if (cls_out) cls_out[(size_t)b * P + p] = c;
+        for (int i = 0; i < MPPT; ++i) {
+            pb[i] = (p0 + i < P) ? pri_xyxy[p0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            pa[i] = box_area(pb[i]);
+            best[i] = 0.0f;        // IoU >= 0 and ties keep the first gt: starting at (0, gt 0) equals max() over the column
+            bestg[i] = 0;
         }
-    }
-    {
+        const bool first_warp = (tile == 0 && warp == 0);   // owns prior 0: the argmax of an all-zero IoU row (T2)
+        // bounding box of the warp's 128 priors: a gt that misses it has IoU 0 with all of them (warp-uniform skip)
+        float wx1 = fminf(fminf(pb[0].x, pb[1].x), fminf(pb[2].x, pb[3].x));
+        float wy1 = fminf(fminf(pb[0].y, pb[1].y), fminf(pb[2].y, pb[3].y));
+        float wx2 = fmaxf(fmaxf(pb[0].z, pb[1].z), fmaxf(pb[2].z, pb[3].z));
+        float wy2 = fmaxf(fmaxf(pb[0].w, pb[1].w), fmaxf(pb[2].w, pb[3].w));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            wx1 = fminf(wx1, __shfl_xor_sync(FULL, wx1, d));
+            wy1 = fminf(wy1, __shfl_xor_sync(FULL, wy1, d));
+            wx2 = fmaxf(wx2, __shfl_xor_sync(FULL, wx2, d));
+            wy2 = fmaxf(wy2, __shfl_xor_sync(FULL, wy2, d));
+        }
+
+        for (int g0 = 0; g0 < G; g0 += MGC) {
+            const int gc = min(MGC, G - g0);
+            if (!one_chunk) {
+                __syncthreads();
+                if (t < gc) {
+                    const float4 bx = gt_xyxy[off0 + g0 + t];
+                    s_box[t] = bx;
+                    s_area[t] = box_area(bx);
+                    s_key[t] = 0ull;
+                }
+                __syncthreads();
+            }
+            for (int g = 0; g < gc; ++g) {
+                const float4 gb = s_box[g];
+                const float ga = s_area[g];
+                float tv = 0.0f;       // this thread's best IoU for gt g (IoU >= 0), lowest prior on ties
+                int ti = 0;
+                const bool near = (gb.z > wx1) && (gb.x < wx2) && (gb.w > wy1) && (gb.y < wy2);
+                if (!near && !first_warp) continue;
+                if (near) {
+#pragma unroll
+                    for (int i = 0; i < MPPT; ++i) {
+                        // disjoint boxes (the common case) have IoU == +0 exactly: no multiply, no IEEE division
+                        const float dx = __fsub_rn(fminf(gb.z, pb[i].z), fmaxf(gb.x, pb[i].x));
+                        const float dy = __fsub_rn(fminf(gb.w, pb[i].w), fmaxf(gb.y, pb[i].y));
+                        if (dx > 0.0f && dy > 0.0f) {
+                            const float inter = __fmul_rn(dx, dy);
+                            const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, pa[i]), inter));
+                            if (v > best[i]) { best[i] = v; bestg[i] = g0 + g; }  // T1: strict > keeps the first gt
+                            if (v > tv) { tv = v; ti = i; }                       // strict > keeps the lower prior
+                        }
+                    }
+                }
+                const uint32_t m = __reduce_max_sync(FULL, __float_as_uint(tv));  // IoU >= 0: bits order like values
+                if (m != 0u || first_warp) {                                      // some IoU > 0, or the warp owning prior 0
+                    const unsigned ball = __ballot_sync(FULL, __float_as_uint(tv) == m);
+                    const int src = __ffs(ball) - 1;                              // T2: lowest lane = lowest prior
+                    const int wi = __shfl_sync(FULL, ti, src);
+                    if (lane == 0) {
+                        const uint32_t wprior = (uint32_t)(tile * MTILE + (warp * 32 + src) * MPPT + wi);
+                        atomicMax(&s_key[g], ((unsigned long long)(m | 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - wprior));
+                    }
+                }
+            }
+            if (!one_chunk) {
+                __syncthreads();
+                if (t < gc && s_key[t] != 0ull) atomicMax(&best_key[off0 + g0 + t], s_key[t]);
+            }
+        }
+
+        // natural (pre-override) match of this tile: one class byte per prior
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int i = 0; i < MPPT; ++i) {
+            const int p = p0 + i;
+            const bool hit = (G > 0) && !(best[i] < pos_iou);                   // T6: matched <=> not (iou < thr)
+            const int c = (hit && p < P) ? (int)gt_cls[off0 + bestg[i]] : bg_class;
+            packed |= (uint32_t)(c & 0xff) << (8 * i);
+            if (p < P) {
+                cnt += (c != bg_class) ? 1 : 0;                                 // positive <=> class != bg (Losses.py:179)
+                if (obj_idx) obj_idx[(size_t)b * P + p] = off0 + bestg[i];
+                if (cls_out) cls_out[(size_t)b * P + p] = c;
+            }
+        }
         uint8_t* dst = cls_u8 + (size_t)b * P + p0;
         if (p0 + MPPT <= P && ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0)) {
             *reinterpret_cast<uint32_t*>(dst) = packed;
@@ -118,6 +152,11 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
             for (int i = 0; i < MPPT; ++i) if (p0 + i < P) dst[i] = (uint8_t)(packed >> (8 * i));
         }
     }
+    if (one_chunk) {
+        __syncthreads();
+        if (t < G && s_key[t] != 0ull) atomicMax(&best_key[off0 + t], s_key[t]);
+    }
+
     cnt = warp_sum(cnt);
     if (lane == 0) s_red[warp] = cnt;
     __syncthreads();
@@ -135,7 +174,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
 
     // ---- last tile of image b: forced-match override (Losses.py:164-167) ----
     int extra = 0;
-    if (G <= MGC) {
+    if (one_chunk) {
         // all gts of the image are still staged in s_box / s_area: one round of loads, then shared memory only
         uint32_t* s_bp = reinterpret_cast<uint32_t*>(s_key);                    // reuse: best prior per gt
         uint32_t p = 0u;
@@ -310,7 +349,10 @@ int ssdhead_match(const float* gt_xyxy, const float* gt_cls, const int32_t* gt_o
     unsigned int* tile_counter = (unsigned int*)w;                    w += round_up((size_t)B * 4, 16);
     int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
     unsigned int* image_counter = (unsigned int*)w;
-    dim3 grid((P + MTILE - 1) / MTILE, B);
+    // enough CTAs per image to fill the machine about once (5 CTAs/SM), never more than the image has tiles
+    const int ntiles = (P + MTILE - 1) / MTILE;
+    const int per_image = std::max(1, std::min(ntiles, (5 * 148) / B));
+    dim3 grid(per_image, B);
     match_kernel<<<grid, MT, 0, st>>>((const float4*)gt_xyxy, gt_cls, gt_off, (const float4*)pri_xyxy, B, P, C - 1, pos_iou,
                                       best_prior, npos, cls_u8, obj_idx, cls, best_key, tile_counter, npos_acc, image_counter);
     count_launch();

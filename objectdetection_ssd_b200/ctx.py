@@ -1,0 +1,93 @@
+"""Python handle of ``ssdhead_ctx`` (include/ssdhead.h): one C call per step.
+
+``SSDHeadContext.loss_host`` / ``detect_host`` take HOST arrays (numpy, ideally page-locked via
+``pinned_empty``) - the same buffers the reference's CPU path works on - and run the whole step
+(copies in, kernels, copies out, pipelined in image chunks) inside the library.
+``loss_dev`` runs one training-head step on device tensors with the match overlapped with the
+CE streaming kernel.  No torch arithmetic is involved; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """Page-locked host array (cudaHostAlloc through the library) so copies are asynchronous."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.ssdhead_host_alloc(max(n, 16))
+    if not ptr:
+        raise RuntimeError("ssdhead_host_alloc failed")
+    buf = (C.c_uint8 * max(n, 16)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = (ptr, buf)
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr: np.ndarray) -> None:
+    ent = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    if ent is not None:
+        _lib.load().ssdhead_host_free(ent[0])
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SSDHeadContext:
+    def __init__(self, priors_cxcywh: np.ndarray, max_batch: int, num_classes: int = 21, max_total_gt: int = 0,
+                 top_k: int = 200, device: int = 0):
+        self.lib = _lib.load()
+        pri = np.ascontiguousarray(priors_cxcywh, dtype=np.float32)
+        self.P, self.C, self.maxB, self.top_k = int(pri.shape[0]), int(num_classes), int(max_batch), int(top_k)
+        self.max_total_gt = int(max_total_gt) if max_total_gt > 0 else 128 * self.maxB
+        h = C.c_void_p()
+        _lib.check(self.lib.ssdhead_ctx_create(C.byref(h), device, self.maxB, self.P, self.C, self.max_total_gt,
+                                               self.top_k, _p(pri)), "ssdhead_ctx_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ssdhead_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ host-buffer entry points
+    def loss_host(self, loc, conf, gt_xyxy, gt_cls, gt_off, grad_loc=None, grad_conf=None,
+                  neg_ratio: int = 3, pos_iou: float = 0.5):
+        """ssd() on host arrays.  Returns (loc_loss, conf_loss); gradients are written into
+        ``grad_loc`` / ``grad_conf`` when given (pass both or neither)."""
+        B = int(loc.shape[0])
+        losses = np.zeros(2, np.float32)
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_host(
+            self._h, _p(loc), _p(conf), _p(gt_xyxy), _p(gt_cls), _p(gt_off), B, int(neg_ratio), float(pos_iou),
+            _p(losses), _p(grad_loc), _p(grad_conf)), "ssdhead_ctx_multibox_loss_host")
+        return float(losses[0]), float(losses[1])
+
+    def detect_host(self, loc, conf, out_boxes, out_prob, out_cls, out_prior, out_cnt,
+                    min_score: float = 0.2, iou_thr: float = 0.45):
+        """inference() over a batch of host arrays; outputs as ``ssdhead_detect``."""
+        B = int(loc.shape[0])
+        _lib.check(self.lib.ssdhead_ctx_detect_host(
+            self._h, _p(loc), _p(conf), B, float(min_score), float(iou_thr),
+            _p(out_boxes), _p(out_prob), _p(out_cls), _p(out_prior), _p(out_cnt)), "ssdhead_ctx_detect_host")
+
+    # ------------------------------------------------------------------ device-resident step
+    def loss_dev(self, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, sums_ptr, losses_ptr,
+                 grad_loc_ptr, grad_conf_ptr, stream, neg_ratio: int = 3, pos_iou: float = 0.5):
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_dev(
+            self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
+            float(pos_iou), sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_dev")

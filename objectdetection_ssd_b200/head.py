@@ -75,6 +75,7 @@ class MultiboxHead:
         self.pri_cxcywh = pc.to(self.dev)
         self.pri_xyxy = cxcywh_to_xyxy_host(pc).to(self.dev)     # same fp32 ops as Util.py:93-96
         self._ws = {}
+        self._aux = torch.cuda.Stream(self.dev)                  # the match runs here, beside the CE stream kernel
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, which: int, B: int, n: int) -> torch.Tensor:
@@ -89,23 +90,27 @@ class MultiboxHead:
         return cur
 
     # ------------------------------------------------------------------ match
-    def match(self, gt: PackedGT, want_maps: bool = False, pos_iou: float = POS_IOU):
-        """Losses.py:150-171.  Returns dict(best_prior, npos[B+1], obj[B,P]|None, cls[B,P]|None)."""
+    def _match_outputs(self, gt: PackedGT, want_maps: bool):
         B = gt.B
-        best_prior = torch.empty(max(gt.sumG, 1), dtype=torch.int32, device=self.dev)
-        npos = torch.empty(B + 1, dtype=torch.int32, device=self.dev)
-        cls_u8 = torch.empty(B, self.P, dtype=torch.uint8, device=self.dev)
-        obj = cls = None
+        outs = dict(best_prior=torch.empty(max(gt.sumG, 1), dtype=torch.int32, device=self.dev),
+                    npos=torch.empty(B + 1, dtype=torch.int32, device=self.dev),
+                    cls_u8=torch.empty(B, self.P, dtype=torch.uint8, device=self.dev), obj=None, cls=None)
         if want_maps:
-            obj = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
-            cls = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
+            outs["obj"] = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
+            outs["cls"] = torch.empty(B, self.P, dtype=torch.int32, device=self.dev)
+        return outs
+
+    def match(self, gt: PackedGT, want_maps: bool = False, pos_iou: float = POS_IOU, outs=None):
+        """Losses.py:150-171.  Returns dict(best_prior, npos[B+1], cls_u8[B,P], obj[B,P]|None, cls[B,P]|None)."""
+        B = gt.B
+        o = outs if outs is not None else self._match_outputs(gt, want_maps)
         ws = self._workspace(_lib.WS_MATCH, B, gt.sumG)
         _lib.check(self.lib.ssdhead_match(
             _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off), _ptr(self.pri_xyxy),
             B, self.P, self.C, gt.sumG, pos_iou,
-            _ptr(best_prior), _ptr(npos), _ptr(cls_u8), _ptr(obj), _ptr(cls),
+            _ptr(o["best_prior"]), _ptr(o["npos"]), _ptr(o["cls_u8"]), _ptr(o["obj"]), _ptr(o["cls"]),
             _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_match")
-        return dict(best_prior=best_prior, npos=npos, cls_u8=cls_u8, obj=obj, cls=cls)
+        return o
 
     # ------------------------------------------------------------------ loss
     def loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedGT, with_grads: bool,
@@ -122,13 +127,6 @@ class MultiboxHead:
                              f"{tuple(loc.shape)}, {tuple(conf.shape)}, {gt.B}")
         loc = loc.detach().to(device=self.dev, dtype=torch.float32).contiguous()
         conf = conf.detach().to(device=self.dev, dtype=torch.float32).contiguous()
-        m = match if match is not None else self.match(gt, pos_iou=pos_iou)
-        npos = m["npos"]
-        npos_norm = npos[B:B + 1]
-        if group is not None:
-            import torch.distributed as dist
-            npos_norm = npos_norm.clone()
-            dist.all_reduce(npos_norm, op=dist.ReduceOp.SUM, group=group)
         sums = torch.empty(2, dtype=torch.float64, device=self.dev)
         losses = torch.empty(2, dtype=torch.float32, device=self.dev)
         grad_loc = grad_conf = mined = ce = None
@@ -139,13 +137,33 @@ class MultiboxHead:
             mined = torch.empty(B, (P + 31) // 32, dtype=torch.int32, device=self.dev)
             ce = torch.empty(B, P, dtype=torch.float32, device=self.dev)
         ws = self._workspace(_lib.WS_LOSS, B, 0)
-        _lib.check(self.lib.ssdhead_multibox_loss(
+        cur = torch.cuda.current_stream(self.dev)
+        m = match
+        if m is None:
+            # fork: the match (latency-bound, tiny traffic) runs on the auxiliary stream while the CE streaming
+            # kernel (HBM-bound, independent of the match) runs on the caller's stream
+            outs = self._match_outputs(gt, False)
+            self._aux.wait_stream(cur)
+            with torch.cuda.stream(self._aux):
+                m = self.match(gt, pos_iou=pos_iou, outs=outs)
+        _lib.check(self.lib.ssdhead_ce_stream(
+            _ptr(conf), B, P, C, _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
+            _ptr(ws), ws.numel(), cur.cuda_stream), "ssdhead_ce_stream")
+        if match is None:
+            cur.wait_stream(self._aux)           # join
+        npos = m["npos"]
+        npos_norm = npos[B:B + 1]
+        if group is not None:
+            import torch.distributed as dist
+            npos_norm = npos_norm.clone()
+            dist.all_reduce(npos_norm, op=dist.ReduceOp.SUM, group=group)
+        _lib.check(self.lib.ssdhead_mine(
             _ptr(loc), _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off),
             _ptr(self.pri_xyxy), _ptr(self.pri_cxcywh),
             _ptr(m["best_prior"]), _ptr(npos), _ptr(npos_norm), _ptr(m["cls_u8"]),
             B, P, C, int(neg_ratio), float(pos_iou),
             _ptr(sums), _ptr(losses), _ptr(grad_loc), _ptr(grad_conf), _ptr(mined), _ptr(ce),
-            _ptr(ws), ws.numel(), _stream(self.dev)), "ssdhead_multibox_loss")
+            _ptr(ws), ws.numel(), cur.cuda_stream), "ssdhead_mine")
         if group is not None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)

@@ -1,0 +1,80 @@
+"""GPU: the one-call context front end (host buffers / device tensors) gives the same results as the
+step-by-step C ABI and matches the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from objectdetection_ssd_b200 import synth
+from oracle import ssd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed, B):
+    pri = H.priors()
+    gb, gc = synth.make_gt(seed, B)
+    loc, conf = synth.make_head(seed, B, pri.shape[0])
+    gx, gcl, off = synth.pack_gt(gb, gc)
+    return pri, loc, conf, gb, gc, gx, gcl, off
+
+
+@pytest.mark.parametrize("B", [3, 32])
+def test_loss_host_matches_oracle_and_device_path(B):
+    from objectdetection_ssd_b200.ctx import SSDHeadContext, pinned_empty, pinned_free
+    pri, loc, conf, gb, gc, gx, gcl, off = _inputs(21, B)
+    ctx = SSDHeadContext(pri.numpy(), max_batch=B)
+    hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    hl[:] = loc
+    hc[:] = conf
+    gl, gcf = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    l1, l2 = ctx.loss_host(hl, hc, gx, gcl, off, gl, gcf)
+    f1, f2 = ctx.loss_host(hl, hc, gx, gcl, off)           # forward only
+    tb = [torch.from_numpy(b) for b in gb]
+    tc = [torch.from_numpy(c) for c in gc]
+    tl, tcf = torch.from_numpy(loc), torch.from_numpy(conf)
+    ref = O.multibox_loss(tl, tcf, tb, tc, pri)
+    assert abs(l1 - ref["loc_loss"].item()) <= 1e-5 * abs(ref["loc_loss"].item())
+    assert abs(l2 - ref["conf_loss"].item()) <= 1e-5 * abs(ref["conf_loss"].item())
+    assert (f1, f2) == (l1, l2)
+    rgl, rgc = O.multibox_grads(tl, tcf, ref)
+    assert torch.allclose(torch.from_numpy(gl.copy()), rgl, rtol=1e-5, atol=1e-9)
+    got = torch.from_numpy(gcf.copy())
+    same_rows = torch.equal(got.abs().sum(-1) != 0, rgc.abs().sum(-1) != 0)
+    if same_rows:                                          # mined sets agree (no ulp-level boundary flip)
+        assert torch.allclose(got, rgc, rtol=1e-4, atol=1e-8)
+    # bit-identical to the step-by-step device path
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    head = MultiboxHead(pri, "cuda")
+    out = head.loss(tl.cuda(), tcf.cuda(), PackedGT(tb, tc, head.dev), with_grads=True)
+    assert torch.equal(out["grad_conf"].cpu(), got)
+    assert torch.equal(out["grad_loc"].cpu(), torch.from_numpy(gl.copy()))
+    assert abs(out["losses"][0].item() - l1) <= 1e-6 * abs(l1) and abs(out["losses"][1].item() - l2) <= 1e-6 * abs(l2)
+    for a in (hl, hc, gl, gcf):
+        pinned_free(a)
+    ctx.close()
+
+
+def test_loss_dev_single_call():
+    from objectdetection_ssd_b200.ctx import SSDHeadContext
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    B = 16
+    pri, loc, conf, gb, gc, gx, gcl, off = _inputs(22, B)
+    ctx = SSDHeadContext(pri.numpy(), max_batch=B)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tl, tcf, tgx, tgc, toff = d(loc), d(conf), d(gx), d(gcl), d(off)
+    sums = torch.empty(2, dtype=torch.float64, device="cuda")
+    losses = torch.empty(2, device="cuda")
+    gl, gcf = torch.empty_like(tl), torch.empty_like(tcf)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        ctx.loss_dev(tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
+                     sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
+    torch.cuda.synchronize()
+    head = MultiboxHead(pri, "cuda")
+    out = head.loss(tl, tcf, PackedGT([torch.from_numpy(b) for b in gb], [torch.from_numpy(c) for c in gc], head.dev),
+                    with_grads=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out["losses"], losses) and torch.equal(out["sums"], sums)
+    assert torch.equal(out["grad_conf"], gcf) and torch.equal(out["grad_loc"], gl)
+    ctx.close()
