@@ -143,11 +143,19 @@ int ssdhead_scale_grads(float* grad_loc_dev, size_t n_loc, float* grad_conf_dev,
  * Per image: decode, softmax, per foreground class (0..C-2) keep prob >= min_score, sort by
  * descending prob (ties -> lower prior, T5), greedy NMS (suppress iou >= iou_thr), concatenate
  * class-major, and if more than top_k survive take the global top_k by descending prob
- * (ties -> earlier class-major position, T7).  Boxes are fractional xyxy, not clamped.
+ * (ties -> earlier class-major position, T7).  Boxes are corner form, NOT clamped; fractional,
+ * or multiplied by the image size when `img_wh_dev` [B,2] (w,h) is given (Losses.py:87-89).
+ * `max_candidates` caps the candidate list of one (image, class) to bound the workspace
+ * (0 = P = no cap, the reference's behaviour); if a list overflows, out_cnt[b] = -1.
+ * Only the first top_k boxes kept in a class can reach the global top-k, so the NMS sweep of
+ * a class stops once it has kept top_k boxes - the output is identical to the full sweep.
  * Outputs: out_boxes [B,top_k,4], out_prob [B,top_k], out_cls int32 [B,top_k],
- *          out_prior int32 [B,top_k] (prior id of each detection), out_cnt int32 [B].      */
+ *          out_prior int32 [B,top_k] (prior id of each detection; nullable), out_cnt int32 [B].
+ * Three kernels (score/decode/threshold; per-(image,class) sort + NMS; per-image top-k).
+ * The workspace must be zero-filled before its FIRST use; every call leaves its counters zeroed. */
 int ssdhead_detect(const float* loc_dev, const float* conf_dev, const float* pri_cxcywh_dev,
                    int B, int P, int C, float min_score, float iou_thr, int top_k,
+                   const float* img_wh_dev, int max_candidates,
                    float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
                    int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
@@ -155,6 +163,7 @@ int ssdhead_detect(const float* loc_dev, const float* conf_dev, const float* pri
  * probabilities [B,P,C] as given (the oracle's), so keep lists can be compared bit-exactly. */
 int ssdhead_detect_from_scores(const float* boxes_cxcywh_dev, const float* probs_dev,
                                int B, int P, int C, float min_score, float iou_thr, int top_k,
+                               const float* img_wh_dev, int max_candidates,
                                float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
                                int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
 

@@ -262,7 +262,7 @@ int ssdhead_ctx_detect_host(ssdhead_ctx* c, const float* loc_h, const float* con
     const size_t nr = (size_t)B * c->P;
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf, conf_h, nr * c->C * 4, cudaMemcpyHostToDevice, c->s_main));
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc, loc_h, nr * 16, cudaMemcpyHostToDevice, c->s_main));
-    const int rc = ssdhead_detect(c->loc, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k,
+    const int rc = ssdhead_detect(c->loc, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k, nullptr, 0,
                                   c->det_boxes, c->det_prob, c->det_cls, c->det_prior, c->det_cnt,
                                   c->ws_detect, c->ws_detect_bytes, c->s_main);
     if (rc) return rc;

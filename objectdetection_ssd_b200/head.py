@@ -214,3 +214,43 @@ def multibox_loss(head: MultiboxHead, loc: torch.Tensor, conf: torch.Tensor,
     """(loc_loss, conf_loss) as 0-dim tensors with grad_fn - the return of ``ssd()`` (Losses.py:134)."""
     gt = PackedGT(gt_boxes, gt_classes, head.dev)
     return _MultiboxLossFn.apply(loc, conf, head, gt, neg_ratio, pos_iou, group)
+
+
+def _detect(head: MultiboxHead, a: torch.Tensor, b: torch.Tensor, min_score: float, iou_thr: float, top_k: int,
+            img_wh: Optional[torch.Tensor], max_candidates: int, from_scores: bool):
+    """inference() over a batch (Losses.py:11-98).  ``a, b`` = (loc, conf) or, stage-isolated, (boxes_cxcywh, probs).
+    Returns dict(boxes [B,top_k,4], prob [B,top_k], cls int32, prior int32, cnt int32 [B])."""
+    B, P, C = int(a.shape[0]), head.P, head.C
+    if tuple(a.shape) != (B, P, 4) or tuple(b.shape) != (B, P, C):
+        raise ValueError(f"expected [B,{P},4] and [B,{P},{C}], got {tuple(a.shape)}, {tuple(b.shape)}")
+    dev = head.dev
+    a = a.detach().to(device=dev, dtype=torch.float32).contiguous()
+    b = b.detach().to(device=dev, dtype=torch.float32).contiguous()
+    wh = None if img_wh is None else img_wh.to(device=dev, dtype=torch.float32).contiguous()
+    out = dict(boxes=torch.empty(B, top_k, 4, device=dev), prob=torch.empty(B, top_k, device=dev),
+               cls=torch.empty(B, top_k, dtype=torch.int32, device=dev),
+               prior=torch.empty(B, top_k, dtype=torch.int32, device=dev),
+               cnt=torch.empty(B, dtype=torch.int32, device=dev))
+    ws = head._workspace(_lib.WS_DETECT, B, int(max_candidates))
+    if from_scores:
+        rc = head.lib.ssdhead_detect_from_scores(
+            _ptr(a), _ptr(b), B, P, C, float(min_score), float(iou_thr), int(top_k), _ptr(wh), int(max_candidates),
+            _ptr(out["boxes"]), _ptr(out["prob"]), _ptr(out["cls"]), _ptr(out["prior"]), _ptr(out["cnt"]),
+            _ptr(ws), ws.numel(), _stream(dev))
+    else:
+        rc = head.lib.ssdhead_detect(
+            _ptr(a), _ptr(b), _ptr(head.pri_cxcywh), B, P, C, float(min_score), float(iou_thr), int(top_k),
+            _ptr(wh), int(max_candidates),
+            _ptr(out["boxes"]), _ptr(out["prob"]), _ptr(out["cls"]), _ptr(out["prior"]), _ptr(out["cnt"]),
+            _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "ssdhead_detect")
+    return out
+
+
+def detect(head: MultiboxHead, loc, conf, min_score=0.2, iou_thr=0.45, top_k=200, img_wh=None, max_candidates=0):
+    return _detect(head, loc, conf, min_score, iou_thr, top_k, img_wh, max_candidates, False)
+
+
+def detect_from_scores(head: MultiboxHead, boxes_cxcywh, probs, min_score=0.2, iou_thr=0.45, top_k=200,
+                       img_wh=None, max_candidates=0):
+    return _detect(head, boxes_cxcywh, probs, min_score, iou_thr, top_k, img_wh, max_candidates, True)

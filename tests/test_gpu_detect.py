@@ -1,0 +1,138 @@
+"""GPU parity: decode + score threshold + per-class NMS + global top-k against the CPU oracle.
+
+Stage-isolated (the oracle's decoded boxes and probabilities are fed to the kernels): keep lists, classes,
+prior ids and order are bit-exact under T5-T7.  End to end (the kernels' own expf): decoded boxes and
+probabilities agree to 1e-5 and the detections match except where a score or IoU sits within a few ulp of
+its threshold, which the test accounts for explicitly.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ssd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _head(pri):
+    from objectdetection_ssd_b200.head import MultiboxHead
+    return MultiboxHead(pri, "cuda")
+
+
+def _oracle_stage(boxes, probs, min_score, iou_thr, top_k):
+    return [O.detect_from_scores(boxes[i], probs[i], min_score, iou_thr, top_k) for i in range(boxes.shape[0])]
+
+
+def _check_exact(out, ref, top_k):
+    cnt = out["cnt"].cpu()
+    for i, (rb, rc, rp, ri) in enumerate(ref):
+        k = int(cnt[i])
+        assert k == rb.shape[0], f"image {i}: {k} detections, oracle {rb.shape[0]}"
+        assert torch.equal(out["prior"][i, :k].cpu().long(), ri), f"image {i}: prior ids / order"
+        assert torch.equal(out["cls"][i, :k].cpu().long(), rc), f"image {i}: classes"
+        assert torch.equal(out["prob"][i, :k].cpu(), rp), f"image {i}: scores"
+        assert torch.equal(out["boxes"][i, :k].cpu(), rb), f"image {i}: boxes"
+
+
+@pytest.mark.parametrize("bias,min_score,B", [(8.0, 0.01, 4), (6.0, 0.01, 2), (6.0, 0.2, 3), (2.0, 0.05, 2)])
+def test_detect_from_scores_exact(bias, min_score, B):
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    loc, conf = H.detect_inputs(31, B, pri.shape[0], bg_bias=bias)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(B)])
+    probs = F.softmax(conf, dim=2)
+    out = detect_from_scores(_head(pri), boxes, probs, min_score, 0.45, 200)
+    torch.cuda.synchronize()
+    _check_exact(out, _oracle_stage(boxes, probs, min_score, 0.45, 200), 200)
+
+
+def test_detect_fewer_than_topk_is_class_major_unsorted():
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    loc, conf = H.detect_inputs(32, 3, pri.shape[0], bg_bias=9.0)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(3)])
+    probs = F.softmax(conf, dim=2)
+    ref = _oracle_stage(boxes, probs, 0.05, 0.45, 200)
+    assert all(0 < r[0].shape[0] <= 200 for r in ref), [r[0].shape for r in ref]
+    out = detect_from_scores(_head(pri), boxes, probs, 0.05, 0.45, 200)
+    torch.cuda.synchronize()
+    _check_exact(out, ref, 200)
+
+
+def test_detect_no_candidates_and_ties():
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    P = pri.shape[0]
+    boxes = pri.unsqueeze(0).repeat(2, 1, 1).contiguous()
+    probs = torch.zeros(2, P, 21)
+    probs[0, :, 20] = 1.0                        # image 0: nothing above threshold -> 0 detections (Losses.py:62-63)
+    probs[1, :, 20] = 0.4
+    probs[1, :, 3] = 0.3                         # image 1: every prior ties at 0.3 in classes 3 and 7 (T5, T7)
+    probs[1, :, 7] = 0.3
+    out = detect_from_scores(_head(pri), boxes, probs, 0.2, 0.45, 200)
+    torch.cuda.synchronize()
+    ref = _oracle_stage(boxes, probs, 0.2, 0.45, 200)
+    assert int(out["cnt"][0]) == 0 and ref[0][0].shape[0] == 0
+    _check_exact(out, ref, 200)
+
+
+def test_detect_small_topk_and_pixel_scale():
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    loc, conf = H.detect_inputs(33, 2, pri.shape[0], bg_bias=6.0)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(2)])
+    probs = F.softmax(conf, dim=2)
+    wh = torch.tensor([[500., 375.], [320., 480.]])
+    out = detect_from_scores(_head(pri), boxes, probs, 0.01, 0.45, 17, img_wh=wh)
+    torch.cuda.synchronize()
+    ref = _oracle_stage(boxes, probs, 0.01, 0.45, 17)
+    ref = [(rb * torch.tensor([w, h, w, h]), rc, rp, ri) for (rb, rc, rp, ri), (w, h) in zip(ref, wh.tolist())]
+    _check_exact(out, ref, 17)
+
+
+def test_detect_candidate_cap_overflow_is_flagged():
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    loc, conf = H.detect_inputs(34, 2, pri.shape[0], bg_bias=6.0)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(2)])
+    probs = F.softmax(conf, dim=2)
+    out = detect_from_scores(_head(pri), boxes, probs, 0.01, 0.45, 200, max_candidates=64)
+    torch.cuda.synchronize()
+    assert (out["cnt"].cpu() == -1).all()
+
+
+def test_detect_ssd512_priors():
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors("ssd512")
+    loc, conf = H.detect_inputs(35, 1, pri.shape[0], bg_bias=7.0)
+    boxes = torch.stack([O.decode(loc[0], pri)])
+    probs = F.softmax(conf, dim=2)
+    out = detect_from_scores(_head(pri), boxes, probs, 0.01, 0.45, 200)
+    torch.cuda.synchronize()
+    _check_exact(out, _oracle_stage(boxes, probs, 0.01, 0.45, 200), 200)
+
+
+def test_detect_end_to_end_close():
+    """The fused path (own decode + softmax): probabilities/boxes to 1e-5; detections equal up to threshold flips."""
+    from objectdetection_ssd_b200.head import detect
+    pri = H.priors()
+    B = 4
+    loc, conf = H.detect_inputs(36, B, pri.shape[0], bg_bias=7.0)
+    out = detect(_head(pri), loc, conf, 0.01, 0.45, 200)
+    torch.cuda.synchronize()
+    mism = 0
+    for i in range(B):
+        rb, rc, rp, ri = O.detect_image(loc[i], conf[i], pri, 0.01, 0.45, 200)
+        k = int(out["cnt"][i])
+        gp, gi = out["prob"][i, :k].cpu(), out["prior"][i, :k].cpu().long()
+        gc, gb = out["cls"][i, :k].cpu().long(), out["boxes"][i, :k].cpu()
+        ref = {(int(a), int(b)): j for j, (a, b) in enumerate(zip(ri, rc))}
+        hit = [ref.get((int(a), int(b)), -1) for a, b in zip(gi, gc)]
+        common = [(j, h) for j, h in enumerate(hit) if h >= 0]
+        mism += (k - len(common)) + (rb.shape[0] - len(common))
+        j = torch.tensor([c[0] for c in common])
+        h = torch.tensor([c[1] for c in common])
+        assert torch.allclose(gp[j], rp[h], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(gb[j], rb[h], rtol=1e-5, atol=1e-6)
+    assert mism <= 2 * B, f"{mism} detections differ (expected only ulp-level threshold flips)"
