@@ -63,6 +63,17 @@ int ssdhead_decode(const float* gcxgcy_dev, const float* pri_cxcywh_dev, float* 
 int ssdhead_iou_matrix(const float* a_xyxy_dev, int n1, const float* b_xyxy_dev, int n2,
                        float* out_dev /*[n1,n2]*/, void* stream);
 
+/* find_intersection, Util.py:252-265: the [n1,n2] intersection areas only. */
+int ssdhead_intersection_matrix(const float* a_xyxy_dev, int n1, const float* b_xyxy_dev, int n2,
+                                float* out_dev /*[n1,n2]*/, void* stream);
+
+/* map_prior_to_bb, Util.py:333-352: single-image match from a GIVEN jaccard matrix [G,P] and classes [G]
+ * (fp32).  Outputs cls fp32 [P] (bg_class where overlap < thr), obj int64 [P] (local gt index after the
+ * forced override, T1-T3).  overlap_ws fp32 [P] and best_prior_ws int32 [G] are scratch. */
+int ssdhead_match_from_iou(const float* jacc_dev, const float* classes_dev, int G, int P, float thr, int bg_class,
+                           float* cls_out_dev, long long* obj_out_dev, float* overlap_ws_dev, int32_t* best_prior_ws_dev,
+                           void* stream);
+
 /* ---- matching: Losses.py:150-171 (batched) / map_prior_to_bb Util.py:333-352 --------
  * Outputs: best_prior int32 [sumG] (argmax over priors per gt, T2);
  *          npos int32 [B+1]: positives per image, npos[B] = batch total;
@@ -184,6 +195,20 @@ void  ssdhead_host_free(void* p);
 int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* ctx, const float* loc_dev, const float* conf_dev,
                                   const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                                   int B, int sumG, int neg_ratio, float pos_iou,
+                                  double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                                  void* stream);
+/* The same step in two halves for a batch sharded by image over several GPUs: `begin` runs the match and
+ * the CE streaming kernel and hands back a device pointer to this rank's int32 positive count; the
+ * caller all-reduces it (NCCL, 4 bytes) and passes the total to `end` as npos_norm_dev (null = local
+ * count), which mines and writes the gradients; the caller then all-reduces sums[2] and calls
+ * ssdhead_finish_loss. */
+int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* ctx, const float* conf_dev,
+                                    const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                    int B, int sumG, float pos_iou, float* grad_loc_dev, float* grad_conf_dev,
+                                    int32_t** npos_total_dev, void* stream);
+int ssdhead_ctx_multibox_loss_end(ssdhead_ctx* ctx, const float* loc_dev, const float* conf_dev,
+                                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                  int B, int neg_ratio, float pos_iou, const int32_t* npos_norm_dev,
                                   double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
                                   void* stream);
 /* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair.

@@ -28,6 +28,8 @@ SIGNATURES = {
     "ssdhead_encode": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ssdhead_decode": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ssdhead_iou_matrix": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "ssdhead_intersection_matrix": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "ssdhead_match_from_iou": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_multibox_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -43,6 +45,8 @@ SIGNATURES = {
     "ssdhead_host_alloc": (_vp, [_sz]),
     "ssdhead_host_free": (None, [_vp]),
     "ssdhead_ctx_multibox_loss_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ssdhead_ctx_multibox_loss_begin": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, C.POINTER(_vp), _vp]),
+    "ssdhead_ctx_multibox_loss_end": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "ssdhead_ctx_detect_host": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -159,12 +159,12 @@ fail:
     return rc;
 }
 
-// One training-head step on DEVICE tensors: the match runs on the context's auxiliary stream beside the CE
-// streaming kernel (which does not depend on it); both join before the mining kernel.  Asynchronous on `stream`.
-int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float* conf,
-                                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
-                                  int neg_ratio, float pos_iou,
-                                  double* sums, float* losses, float* grad_loc, float* grad_conf, void* stream)
+// Sharded batches: the step in two halves around the all-reduce of the positive count.
+// begin: match on the auxiliary stream beside the CE streaming kernel, joined on `stream`; on return
+// *npos_total_dev points to this rank's int32 positive count (device memory owned by the context).
+int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
+                                    const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
+                                    float pos_iou, float* grad_loc, float* grad_conf, int32_t** npos_total_dev, void* stream)
 {
     if (!c) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
@@ -178,9 +178,35 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
     rc = ssdhead_ce_stream(conf, B, c->P, c->C, nullptr, grad_loc, grad_conf, c->ws_loss, c->ws_loss_bytes, st);
     if (rc) return rc;
     SSD_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
-    return ssdhead_mine(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, c->best_prior, c->npos, c->npos + B,
+    if (npos_total_dev) *npos_total_dev = c->npos + B;
+    return 0;
+}
+
+// end: the mining kernel, normalised by *npos_norm_dev (null = this rank's own count).
+int ssdhead_ctx_multibox_loss_end(ssdhead_ctx* c, const float* loc, const float* conf,
+                                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B,
+                                  int neg_ratio, float pos_iou, const int32_t* npos_norm_dev,
+                                  double* sums, float* losses, float* grad_loc, float* grad_conf, void* stream)
+{
+    if (!c) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB) return SSDHEAD_E_STATE;
+    return ssdhead_mine(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, c->best_prior, c->npos,
+                        npos_norm_dev ? npos_norm_dev : c->npos + B,
                         c->cls_u8, B, c->P, c->C, neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, nullptr, nullptr,
-                        c->ws_loss, c->ws_loss_bytes, st);
+                        c->ws_loss, c->ws_loss_bytes, (cudaStream_t)stream);
+}
+
+// One training-head step on DEVICE tensors: the match runs on the context's auxiliary stream beside the CE
+// streaming kernel (which does not depend on it); both join before the mining kernel.  Asynchronous on `stream`.
+int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float* conf,
+                                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
+                                  int neg_ratio, float pos_iou,
+                                  double* sums, float* losses, float* grad_loc, float* grad_conf, void* stream)
+{
+    int rc = ssdhead_ctx_multibox_loss_begin(c, conf, gt_xyxy, gt_cls, gt_off, B, sumG, pos_iou, grad_loc, grad_conf, nullptr, stream);
+    if (rc) return rc;
+    return ssdhead_ctx_multibox_loss_end(c, loc, conf, gt_xyxy, gt_cls, gt_off, B, neg_ratio, pos_iou, nullptr,
+                                         sums, losses, grad_loc, grad_conf, stream);
 }
 
 // ssd() on HOST buffers (pass page-locked memory, e.g. ssdhead_host_alloc, for asynchronous copies).

@@ -258,6 +258,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
 }
 
 // ------------------------------------------------------------------------------- dense IoU
+template <bool INTERSECTION_ONLY>
 __global__ void __launch_bounds__(256)
 iou_matrix_kernel(const float4* __restrict__ a, int n1, const float4* __restrict__ bxs, int n2, float* __restrict__ out)
 {
@@ -271,8 +272,64 @@ iou_matrix_kernel(const float4* __restrict__ a, int n1, const float4* __restrict
         const int i = i0 + r;
         if (i >= n1) break;
         const float4 gb = a[i];
-        out[(size_t)i * n2 + j] = iou_xyxy(gb, box_area(gb), pb, pa);
+        if (INTERSECTION_ONLY) {                                  // find_intersection, Util.py:252-265
+            const float dx = fmaxf(__fsub_rn(fminf(gb.z, pb.z), fmaxf(gb.x, pb.x)), 0.0f);
+            const float dy = fmaxf(__fsub_rn(fminf(gb.w, pb.w), fmaxf(gb.y, pb.y)), 0.0f);
+            out[(size_t)i * n2 + j] = __fmul_rn(dx, dy);
+        } else {
+            out[(size_t)i * n2 + j] = iou_xyxy(gb, box_area(gb), pb, pa);
+        }
     }
+}
+
+// ------------------------------------------------------------------------------- match from a given IoU matrix
+// map_prior_to_bb (Util.py:333-352): the legacy single-image entry takes the [G,P] jaccard matrix itself.
+__global__ void __launch_bounds__(256)
+match_iou_cols_kernel(const float* __restrict__ jacc, int G, int P, float* __restrict__ overlap, long long* __restrict__ obj)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float best = jacc[p];
+    int bg = 0;
+    for (int g = 1; g < G; ++g) {
+        const float v = jacc[(size_t)g * P + p];
+        if (v > best) { best = v; bg = g; }                       // T1: first maximal gt
+    }
+    overlap[p] = best;
+    obj[p] = bg;
+}
+
+__global__ void __launch_bounds__(256)
+match_iou_rows_kernel(const float* __restrict__ jacc, int G, int P, int* __restrict__ best_prior)
+{
+    __shared__ unsigned long long s_best;
+    const int g = blockIdx.x, t = threadIdx.x;
+    if (t == 0) s_best = 0ull;
+    __syncthreads();
+    unsigned long long mine = 0ull;
+    for (int p = t; p < P; p += blockDim.x) {
+        const unsigned long long k = ((unsigned long long)float_order_key(jacc[(size_t)g * P + p]) << 32) |
+                                     (unsigned long long)(0xffffffffu - (unsigned)p);
+        mine = max(mine, k);                                      // T2: lowest prior index on ties
+    }
+    atomicMax(&s_best, mine);
+    __syncthreads();
+    if (t == 0) best_prior[g] = (int)(0xffffffffu - (unsigned)(s_best & 0xffffffffull));
+}
+
+__global__ void match_iou_finish_kernel(const float* __restrict__ classes, const int* __restrict__ best_prior, int G, int P,
+                                        float thr, float bg_class, float* __restrict__ overlap, long long* __restrict__ obj,
+                                        float* __restrict__ cls_out)
+{
+    // forced override, sequential over gts so the last write wins (T3), then classes and the threshold
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int g = 0; g < G; ++g) { obj[best_prior[g]] = g; overlap[best_prior[g]] = 1.0f; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (blockIdx.x != 0) return;
+    for (int p = threadIdx.x; p < P; p += blockDim.x)
+        cls_out[p] = (overlap[p] < thr) ? bg_class : classes[obj[p]];
 }
 
 // ------------------------------------------------------------------------------- elementwise box ops
@@ -323,8 +380,35 @@ int ssdhead_iou_matrix(const float* a, int n1, const float* b, int n2, float* ou
     if (!aligned16(a) || !aligned16(b)) return SSDHEAD_E_ALIGN;
     dim3 grid((n2 + 255) / 256, (n1 + 7) / 8);
     if (grid.y > 65535) return SSDHEAD_E_UNSUPPORTED;
-    iou_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, n1, (const float4*)b, n2, out);
+    iou_matrix_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, n1, (const float4*)b, n2, out);
     count_launch();
+    SSD_LAUNCH_CHECK();
+    return 0;
+}
+
+int ssdhead_intersection_matrix(const float* a, int n1, const float* b, int n2, float* out, void* stream)
+{
+    if (n1 < 0 || n2 < 0) return SSDHEAD_E_BADARG;
+    if (n1 == 0 || n2 == 0) return 0;
+    if (!a || !b || !out) return SSDHEAD_E_BADARG;
+    if (!aligned16(a) || !aligned16(b)) return SSDHEAD_E_ALIGN;
+    dim3 grid((n2 + 255) / 256, (n1 + 7) / 8);
+    if (grid.y > 65535) return SSDHEAD_E_UNSUPPORTED;
+    iou_matrix_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, n1, (const float4*)b, n2, out);
+    count_launch();
+    SSD_LAUNCH_CHECK();
+    return 0;
+}
+
+int ssdhead_match_from_iou(const float* jacc, const float* classes, int G, int P, float thr, int bg_class,
+                           float* cls_out, long long* obj_out, float* overlap_ws, int32_t* best_prior_ws, void* stream)
+{
+    if (G <= 0 || P <= 0 || !jacc || !classes || !cls_out || !obj_out || !overlap_ws || !best_prior_ws) return SSDHEAD_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    match_iou_cols_kernel<<<(P + 255) / 256, 256, 0, st>>>(jacc, G, P, overlap_ws, obj_out);
+    match_iou_rows_kernel<<<G, 256, 0, st>>>(jacc, G, P, best_prior_ws);
+    match_iou_finish_kernel<<<1, 256, 0, st>>>(classes, best_prior_ws, G, P, thr, (float)bg_class, overlap_ws, obj_out, cls_out);
+    count_launch(3);
     SSD_LAUNCH_CHECK();
     return 0;
 }

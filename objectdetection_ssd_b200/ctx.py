@@ -91,3 +91,21 @@ class SSDHeadContext:
         _lib.check(self.lib.ssdhead_ctx_multibox_loss_dev(
             self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
             float(pos_iou), sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_dev")
+
+    def loss_begin(self, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, grad_loc_ptr, grad_conf_ptr, stream,
+                   pos_iou: float = 0.5) -> int:
+        """First half of a sharded step; returns the device address of this rank's int32 positive count."""
+        out = C.c_void_p()
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_begin(
+            self._h, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), float(pos_iou),
+            grad_loc_ptr, grad_conf_ptr, C.byref(out), stream), "ssdhead_ctx_multibox_loss_begin")
+        return int(out.value)
+
+    def loss_end(self, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, npos_norm_ptr, sums_ptr, losses_ptr,
+                 grad_loc_ptr, grad_conf_ptr, stream, neg_ratio: int = 3, pos_iou: float = 0.5):
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_end(
+            self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(neg_ratio), float(pos_iou),
+            npos_norm_ptr, sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_end")
+
+    def finish_loss(self, sums_ptr, npos_norm_ptr, losses_ptr, stream):
+        _lib.check(self.lib.ssdhead_finish_loss(sums_ptr, npos_norm_ptr, losses_ptr, stream), "ssdhead_finish_loss")

@@ -1,0 +1,112 @@
+"""GPU: the drop-in call surface (Losses.py / Util.py names of the reference) against the oracle."""
+import pytest
+import torch
+
+from oracle import ssd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_util_box_functions():
+    from objectdetection_ssd_b200 import Util
+    pri = H.priors()
+    g = torch.randn(8732, 4, generator=torch.Generator().manual_seed(1)) * 0.5
+    dec = Util.gcxgcy_to_cxcy(g, pri)
+    assert dec.is_cuda and torch.allclose(dec.cpu(), O.decode(g, pri), rtol=1e-6, atol=1e-7)
+    xy = Util.xywh_to_xyxy(pri)
+    assert torch.equal(xy.cpu(), O.cxcywh_to_xyxy(pri))
+    back = Util.xyxy_to_xywh(xy)
+    assert not back.is_cuda and torch.equal(back, O.xyxy_to_cxcywh(O.cxcywh_to_xyxy(pri)))
+    boxes = O.cxcywh_to_xyxy(pri[100:400])
+    enc = Util.get_offsets_coords(O.xyxy_to_cxcywh(boxes), pri[:300])
+    assert torch.allclose(enc.cpu(), O.encode(O.xyxy_to_cxcywh(boxes), pri[:300]), rtol=1e-5, atol=1e-6)
+
+
+def test_util_iou_and_match_from_matrix():
+    from objectdetection_ssd_b200 import Util
+    pri = H.priors()
+    pxy = O.cxcywh_to_xyxy(pri)
+    _, _, tb, tc = H.train_inputs(41, 3, pri.shape[0])
+    for b, c in zip(tb, tc):
+        j = Util.get_jaccard_tensor1(b, pxy)
+        ref = O.iou_matrix(b, pxy)
+        assert torch.equal(j.cpu(), ref)                                   # bit-exact IoU (T8)
+        assert torch.equal(Util.get_jaccard_tensor11(b, pxy), ref)         # CPU twin
+        assert torch.equal(Util.find_intersection(b.cuda(), pxy.cuda()).cpu(), Util.find_intersection(b, pxy))
+        cls, obj = Util.map_prior_to_bb(j, c)
+        rc, ro, _, _ = O.match_image(ref, c)
+        assert torch.equal(cls.cpu(), rc) and torch.equal(obj.cpu(), ro)
+    # T3 through the matrix entry: identical gts
+    box = torch.tensor([[0.2, 0.2, 0.6, 0.7]]).repeat(3, 1)
+    c = torch.tensor([3., 7., 5.])
+    cls, obj = Util.map_prior_to_bb(O.iou_matrix(box, pxy), c)
+    rc, ro, _, _ = O.match_image(O.iou_matrix(box, pxy), c)
+    assert torch.equal(cls.cpu(), rc) and torch.equal(obj.cpu(), ro)
+
+
+def test_losses_ssd_surface_and_variants():
+    from objectdetection_ssd_b200 import Losses
+    pri = H.priors()
+    assert torch.equal(Losses.ancs_xywh, pri) and torch.equal(Losses.ancs_xyxy, O.cxcywh_to_xyxy(pri))
+    loc, conf, tb, tc = H.train_inputs(42, 6, pri.shape[0])
+    l = loc.cuda().requires_grad_(True)
+    c = conf.cuda().requires_grad_(True)
+    l1, l2 = Losses.ssd((l, c), [x.cuda() for x in tc], [x.cuda() for x in tb])
+    assert l1.dim() == 0 and l2.dim() == 0 and l1.grad_fn is not None
+    (l1 + l2).backward()
+    ref = O.multibox_loss(loc, conf, tb, tc, pri)
+    assert abs(l1.item() - ref["loc_loss"].item()) <= 1e-5 * ref["loc_loss"].item()
+    assert abs(l2.item() - ref["conf_loss"].item()) <= 1e-5 * ref["conf_loss"].item()
+    gl, gc = O.multibox_grads(loc, conf, ref)
+    assert torch.allclose(l.grad.cpu(), gl, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(c.grad.cpu(), gc, rtol=1e-4, atol=1e-8)
+    assert torch.equal(Losses.obj_forEach_prior___.cpu().long(), ref["cls"])     # debug tap (Losses.py:172-173)
+    # inner function returns the pair swapped (Losses.py:199)
+    a, b = Losses.ssd1_(loc.cuda(), conf.cuda(), tb, tc, None, None)
+    assert abs(a.item() - l2.item()) < 1e-7 and abs(b.item() - l1.item()) < 1e-7
+    # legacy per-image mean (Losses.py:100-117)
+    o1, o2 = Losses.ssd_old((loc.cuda(), conf.cuda()), tc, tb)
+    r1, r2 = O.ssd_per_image_mean((loc, conf), tc, tb, pri, O.cxcywh_to_xyxy(pri))
+    assert abs(o1.item() - r1.item()) <= 1e-5 * r1.item() and abs(o2.item() - r2.item()) <= 1e-5 * r2.item()
+    # no grad requested -> forward only
+    with torch.no_grad():
+        f1, f2 = Losses.ssd((loc.cuda(), conf.cuda()), tc, tb)
+    assert abs(f1.item() - l1.item()) < 1e-7 and not f1.requires_grad
+
+
+def test_losses_inference_surface(monkeypatch):
+    from objectdetection_ssd_b200 import Losses
+    pri = H.priors()
+    loc, conf = H.detect_inputs(43, 2, pri.shape[0], bg_bias=8.0)
+    monkeypatch.setattr(Losses, "_image_size", lambda phase, index: (500, 375))
+    for i in range(2):
+        boxes, cls, prob = Losses.inference(loc[i].cuda(), conf[i].cuda(), 0, toDraw=False, min_score=0.01)
+        rb, rc, rp, _ = O.detect_image(loc[i], conf[i], pri, 0.01, 0.45, 200)
+        assert boxes.shape == (rb.shape[0], 4) and cls.dtype == torch.int64
+        scale = torch.tensor([500., 375., 500., 375.])
+        hit = (cls.cpu()[:, None] == rc[None, :]) & ((prob.cpu()[:, None] - rp[None, :]).abs() < 1e-6)
+        assert hit.any(1).float().mean() > 0.98
+        j = hit.float().argmax(1)
+        ok = hit.any(1)
+        assert torch.allclose(boxes.cpu()[ok], (rb * scale)[j[ok]], rtol=1e-5, atol=1e-3)
+    # nothing above the threshold -> three empty lists (Losses.py:62-63)
+    conf0 = torch.zeros(pri.shape[0], 21)
+    conf0[:, 20] = 30.0
+    assert Losses.inference(loc[0].cuda(), conf0.cuda(), 0, toDraw=False) == ([], [], [])
+
+
+def test_stress_prior_table_by_overwriting_module_global():
+    """The 24 564-prior configuration is driven the way the reference would be: by replacing Losses.ancs_xywh."""
+    from objectdetection_ssd_b200 import Losses
+    pri = H.priors("ssd512")
+    old = Losses.ancs_xywh
+    try:
+        Losses.ancs_xywh = pri
+        loc, conf, tb, tc = H.train_inputs(44, 2, pri.shape[0], min_gt=100, max_gt=100)
+        l1, l2 = Losses.ssd((loc.cuda(), conf.cuda()), tc, tb)
+        ref = O.multibox_loss(loc, conf, tb, tc, pri)
+        assert abs(l1.item() - ref["loc_loss"].item()) <= 1e-5 * ref["loc_loss"].item()
+        assert abs(l2.item() - ref["conf_loss"].item()) <= 1e-5 * ref["conf_loss"].item()
+    finally:
+        Losses.ancs_xywh = old
