@@ -1,0 +1,52 @@
+"""CPU: libssdhead.so loads without a GPU and exports every symbol include/ssdhead.h declares; the ctypes
+table mirrors the header; no compute entry point is called."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ssdhead.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssdhead_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from objectdetection_ssd_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ssdhead.h but not exported by libssdhead.so"
+
+
+def test_ctypes_table_covers_the_header(lib):
+    from objectdetection_ssd_b200 import _lib
+    assert set(header_symbols()) == set(_lib.SIGNATURES), set(header_symbols()) ^ set(_lib.SIGNATURES)
+
+
+def test_metadata_entry_points(lib):
+    from objectdetection_ssd_b200 import _lib
+    assert lib.ssdhead_abi_version() == 1
+    assert lib.ssdhead_error_string(0) == b"ok"
+    assert b"workspace" in lib.ssdhead_error_string(-3)
+    assert lib.ssdhead_workspace_bytes(_lib.WS_MATCH, 32, 8732, 21, 200) > 0
+    assert lib.ssdhead_workspace_bytes(_lib.WS_LOSS, 32, 8732, 21, 0) >= 32 * 8732 * 4
+    assert lib.ssdhead_workspace_bytes(_lib.WS_LOSS, 1, 100000, 21, 0) == 0          # beyond the shared-memory bound
+    assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 0) > 64 * 8732 * 16
+    assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 1024) < lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 0)
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    assert lib.ssdhead_match(None, None, None, None, 4, 8732, 21, 10, 0.5, None, None, None, None, None, None, 0, None) == -1
+    assert lib.ssdhead_ce_stream(None, 4, 8732, 21, None, None, None, None, 0, None) == -1
+    assert lib.ssdhead_iou_matrix(None, -1, None, 3, None, None) == -1
+    assert lib.ssdhead_ctx_multibox_loss_dev(None, None, None, None, None, None, 1, 1, 3, 0.5, None, None, None, None, None) == -1
