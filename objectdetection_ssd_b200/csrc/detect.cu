@@ -163,7 +163,95 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
     }
 }
 
-constexpr int SORT_SMEM = 4096;    // keys sorted in shared memory up to this many; larger lists sort in place in L2
+constexpr int SORT_SMEM = 4096;    // keys of one slice sorted in shared memory; larger tie groups sort in place in L2
+constexpr int NMS_BINS = 2048;     // linear probability bins used to cut the candidate list into score slices
+
+// One block of up to 64 sorted candidates against the kept list, then inside the block (Losses.py:44-55).
+// Returns the new kept count.  s_kkey / s_kbox / s_karea hold the kept set (capacity top_k + 64).
+struct NmsShared {
+    float4 cbox[64];
+    float carea[64];
+    unsigned long long ckey[64];
+    unsigned long long mask[64];
+    unsigned int supp[2];
+    unsigned long long alive;
+};
+
+__device__ __forceinline__ int nms_block(NmsShared& s, const unsigned long long* keys, int base, int m, const float4* bx,
+                                         float4* s_kbox, float* s_karea, unsigned long long* s_kkey, int K, int kcap,
+                                         float iou_thr, float thr_lo, float thr_hi)
+{
+    const int t = threadIdx.x;
+    if (t < 64) {
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned long long key = 0ull;
+        if (t < m) {
+            key = keys[base + t];
+            box = bx[0xffffffffu - (unsigned)(key & 0xffffffffull)];
+        }
+        s.cbox[t] = box;
+        s.carea[t] = box_area(box);
+        s.ckey[t] = key;
+        s.mask[t] = 0ull;
+    }
+    if (t < 2) s.supp[t] = 0u;
+    __syncthreads();
+    {
+        // (a) against the boxes kept so far: candidate = t & 63, the kept list is split four ways
+        const int cnd = t & 63, part = t >> 6;
+        if (cnd < m) {
+            const float4 cb = s.cbox[cnd];
+            const float ca = s.carea[cnd];
+            for (int k = part; k < K; k += 4) {
+                if (iou_ge(s_kbox[k], s_karea[k], cb, ca, iou_thr, thr_lo, thr_hi)) {
+                    atomicOr(&s.supp[cnd >> 5], 1u << (cnd & 31));
+                    break;
+                }
+            }
+        }
+        // (b) inside the block: row = t & 63 tests the 16 columns [16*part, 16*part+16) that come after it
+        const int rowi = t & 63;
+        if (rowi < m) {
+            const float4 rb = s.cbox[rowi];
+            const float ra = s.carea[rowi];
+            unsigned long long bits = 0ull;
+#pragma unroll 4
+            for (int q = 0; q < 16; ++q) {
+                const int col = part * 16 + q;
+                if (col > rowi && col < m && iou_ge(rb, ra, s.cbox[col], s.carea[col], iou_thr, thr_lo, thr_hi))
+                    bits |= 1ull << col;
+            }
+            if (bits) atomicOr(&s.mask[rowi], bits);
+        }
+    }
+    __syncthreads();
+    if (t < 32) {
+        // (c) serial resolve: a box that is still alive suppresses the later boxes it overlaps.  The 64 mask rows are
+        // pulled into registers first (two per lane, independent loads) so the dependent chain is pure ALU + shuffles.
+        const unsigned long long m_lo = s.mask[t], m_hi = s.mask[t + 32];
+        unsigned long long alive = (m == 64 ? ~0ull : ((1ull << m) - 1ull)) &
+                                   ~((unsigned long long)s.supp[0] | ((unsigned long long)s.supp[1] << 32));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned long long mk = __shfl_sync(FULL, m_lo, i);
+            alive &= ((alive >> i) & 1ull) ? ~mk : ~0ull;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned long long mk = __shfl_sync(FULL, m_hi, i);
+            alive &= ((alive >> (i + 32)) & 1ull) ? ~mk : ~0ull;
+        }
+        if (t == 0) s.alive = alive;
+    }
+    __syncthreads();
+    const unsigned long long alive = s.alive;
+    if (t < m && ((alive >> t) & 1ull)) {
+        const int pos = K + __popcll(alive & ((1ull << t) - 1ull));
+        if (pos < kcap) { s_kbox[pos] = s.cbox[t]; s_karea[pos] = s.carea[t]; s_kkey[pos] = s.ckey[t]; }
+    }
+    __syncthreads();
+    return K + __popcll(alive);
+}
 
 __global__ void __launch_bounds__(DT)
 detect_nms_kernel(const float4* __restrict__ boxes, unsigned long long* __restrict__ cand,
@@ -171,17 +259,17 @@ detect_nms_kernel(const float4* __restrict__ boxes, unsigned long long* __restri
                   int P, int NF, int cap, int capp, int top_k, float iou_thr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: kept boxes float4[top_k+64] | kept areas float[top_k+64] | sort buffer u64[min(capp,SORT_SMEM)]
+    // layout: kept boxes float4[kcap] | kept keys u64[kcap] | kept areas float[kcap] | sort buffer u64[SORT_SMEM] | hist u32[NMS_BINS]
     const int kcap = top_k + 64;
     float4* s_kbox = reinterpret_cast<float4*>(smem_raw);
-    float* s_karea = reinterpret_cast<float*>(s_kbox + kcap);
-    unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)kcap * 20 + 15) & ~(size_t)15));
-    __shared__ float4 s_cbox[64];
-    __shared__ float s_carea[64];
-    __shared__ unsigned long long s_ckey[64];
-    __shared__ unsigned int s_supp[2];
-    __shared__ unsigned long long s_mask[64];
-    __shared__ unsigned long long s_alive;
+    unsigned long long* s_kkey = reinterpret_cast<unsigned long long*>(s_kbox + kcap);
+    float* s_karea = reinterpret_cast<float*>(s_kkey + kcap);
+    unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)kcap * 28 + 15) & ~(size_t)15));
+    unsigned int* s_hist = reinterpret_cast<unsigned int*>(s_sort + SORT_SMEM);
+    __shared__ NmsShared s;
+    __shared__ int s_lo, s_cnt;
+    __shared__ unsigned int s_fill;
+    __shared__ unsigned int s_wsum[DT / 32];
 
     const int c = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const size_t seg_id = (size_t)b * NF + c;
@@ -193,91 +281,107 @@ detect_nms_kernel(const float4* __restrict__ boxes, unsigned long long* __restri
     }
     const float thr_lo = __fmul_rn(iou_thr, 1.0f - 9.5367431640625e-07f);   // thr * (1 - 2^-20)
     const float thr_hi = __fmul_rn(iou_thr, 1.0f + 9.5367431640625e-07f);
-
-    // ---- sort: descending prob, ties -> lower prior index (T5) ----
-    const int n_pad = pow2ceil(n);
-    unsigned long long* keys;
-    if (n_pad <= SORT_SMEM) {
-        keys = s_sort;
-        for (int i = t; i < n_pad; i += DT) keys[i] = i < n ? seg[i] : 0ull;
-    } else {
-        keys = seg;
-        for (int i = n + t; i < n_pad; i += DT) keys[i] = 0ull;
-    }
-    __syncthreads();
-    bitonic_sort_desc(keys, n_pad);
-
-    // ---- greedy NMS over the sorted candidates, 64 at a time (Losses.py:44-55) ----
-    int K = 0;
     const float4* bx = boxes + (size_t)b * P;
-    for (int base = 0; base < n && K < top_k; base += 64) {
-        const int m = min(64, n - base);
-        if (t < 64) {
-            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned long long key = 0ull;
-            if (t < m) {
-                key = keys[base + t];
-                box = bx[0xffffffffu - (unsigned)(key & 0xffffffffull)];
-            }
-            s_cbox[t] = box;
-            s_carea[t] = box_area(box);
-            s_ckey[t] = key;
-            s_mask[t] = 0ull;
-        }
-        if (t < 2) s_supp[t] = 0u;
+    int K = 0;
+    bool full_sort = false;
+
+    // The sweep stops once top_k boxes are kept, so usually only the top few hundred candidates matter.  The list
+    // is therefore consumed in SLICES of descending score: a histogram over linear probability bins (monotone in
+    // the key) finds bin ranges holding about 2*top_k candidates; each slice is compacted into shared memory,
+    // bitonic-sorted (descending prob, ties -> lower prior, T5) and swept, continuing with the same kept set.
+    const int slice_target = max(2 * top_k, 256);
+    auto bin_of = [](unsigned long long key) {
+        const float p = __uint_as_float((unsigned)(key >> 32));
+        return min(NMS_BINS - 1, max(0, (int)__fmul_rn(p, (float)(NMS_BINS - 1))));
+    };
+    if (n <= slice_target * 2 && n <= SORT_SMEM) {
+        // short list: one slice = everything
+        const int n_pad = pow2ceil(n);
+        for (int i = t; i < n_pad; i += DT) s_sort[i] = i < n ? seg[i] : 0ull;
         __syncthreads();
-        {
-            // (a) against the boxes kept so far: candidate = t & 63, the kept list is split four ways
-            const int cnd = t & 63, part = t >> 6;
-            if (cnd < m) {
-                const float4 cb = s_cbox[cnd];
-                const float ca = s_carea[cnd];
-                for (int k = part; k < K; k += 4) {
-                    if (iou_ge(s_kbox[k], s_karea[k], cb, ca, iou_thr, thr_lo, thr_hi)) {
-                        atomicOr(&s_supp[cnd >> 5], 1u << (cnd & 31));
-                        break;
+        bitonic_sort_desc(s_sort, n_pad);
+        for (int base = 0; base < n && K < top_k; base += 64)
+            K = nms_block(s, s_sort, base, min(64, n - base), bx, s_kbox, s_karea, s_kkey, K, kcap, iou_thr, thr_lo, thr_hi);
+    } else {
+        for (int i = t; i < NMS_BINS; i += DT) s_hist[i] = 0u;
+        __syncthreads();
+        for (int i = t; i < n; i += DT) atomicAdd(&s_hist[bin_of(seg[i])], 1u);
+        __syncthreads();
+        int hi = NMS_BINS;                       // bins >= hi are done
+        int done = 0;
+        while (K < top_k && done < n) {
+            {
+                // walk down from `hi` until the slice holds slice_target candidates (a bin is never split):
+                // thread t owns 8 bins counted from the top, a block prefix sum finds where the target is crossed
+                constexpr int per = NMS_BINS / DT;
+                unsigned c8[per], mine = 0u;
+#pragma unroll
+                for (int q = 0; q < per; ++q) {
+                    const int idx = NMS_BINS - 1 - (t * per + q);
+                    c8[q] = idx < hi ? s_hist[idx] : 0u;
+                    mine += c8[q];
+                }
+                unsigned inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned o = __shfl_up_sync(FULL, inc, d);
+                    if ((t & 31) >= d) inc += o;
+                }
+                if ((t & 31) == 31) s_wsum[t >> 5] = inc;
+                if (t == 0) { s_lo = 0; s_cnt = -1; s_fill = 0u; }
+                __syncthreads();
+                unsigned wbase = 0u, total = 0u;
+#pragma unroll
+                for (int w = 0; w < DT / 32; ++w) { const unsigned cw = s_wsum[w]; if (w < (t >> 5)) wbase += cw; total += cw; }
+                unsigned above = wbase + inc - mine;
+                if (above < (unsigned)slice_target && above + mine >= (unsigned)slice_target) {
+#pragma unroll
+                    for (int q = 0; q < per; ++q) {
+                        above += c8[q];
+                        if (above >= (unsigned)slice_target) { s_lo = NMS_BINS - 1 - (t * per + q); s_cnt = (int)above; break; }
                     }
                 }
+                __syncthreads();
+                if (t == 0 && s_cnt < 0) s_cnt = (int)total;      // fewer than the target left: the rest is one slice (lo = 0)
             }
-            // (b) inside the block: row = t & 63 tests the 16 columns [16*part, 16*part+16) that come after it
-            const int rowi = t & 63;
-            if (rowi < m) {
-                const float4 rb = s_cbox[rowi];
-                const float ra = s_carea[rowi];
-                unsigned long long bits = 0ull;
-#pragma unroll 4
-                for (int q = 0; q < 16; ++q) {
-                    const int col = part * 16 + q;
-                    if (col > rowi && col < m && iou_ge(rb, ra, s_cbox[col], s_carea[col], iou_thr, thr_lo, thr_hi))
-                        bits |= 1ull << col;
-                }
-                if (bits) atomicOr(&s_mask[rowi], bits);
+            __syncthreads();
+            const int lo = s_lo, cnt = s_cnt;
+            if (cnt > SORT_SMEM) { full_sort = true; break; }       // a crowd of (near-)equal scores: general path
+            const int n_pad = pow2ceil(max(cnt, 1));
+            for (int i = t; i < n_pad; i += DT) s_sort[i] = 0ull;
+            __syncthreads();
+            for (int i = t; i < n; i += DT) {
+                const unsigned long long key = seg[i];
+                const int bn = bin_of(key);
+                if (bn >= lo && bn < hi) s_sort[atomicAdd(&s_fill, 1u)] = key;
             }
+            __syncthreads();
+            bitonic_sort_desc(s_sort, n_pad);
+            for (int base = 0; base < cnt && K < top_k; base += 64)
+                K = nms_block(s, s_sort, base, min(64, cnt - base), bx, s_kbox, s_karea, s_kkey, K, kcap, iou_thr, thr_lo, thr_hi);
+            hi = lo;
+            done += cnt;
         }
-        __syncthreads();
-        if (t == 0) {
-            // (c) serial resolve: a box that is still alive suppresses the later boxes it overlaps
-            unsigned long long alive = (m == 64 ? ~0ull : ((1ull << m) - 1ull)) &
-                                       ~((unsigned long long)s_supp[0] | ((unsigned long long)s_supp[1] << 32));
-            for (int i = 0; i < m; ++i)
-                if ((alive >> i) & 1ull) alive &= ~s_mask[i];
-            s_alive = alive;
-        }
-        __syncthreads();
-        const unsigned long long alive = s_alive;
-        if (t < m && ((alive >> t) & 1ull)) {
-            const int pos = K + __popcll(alive & ((1ull << t) - 1ull));
-            if (pos < kcap) { s_kbox[pos] = s_cbox[t]; s_karea[pos] = s_carea[t]; }
-            seg[pos] = s_ckey[t];            // kept keys compact to the front of the segment (pos <= base + t)
-        }
-        K += __popcll(alive);
-        __syncthreads();
     }
+    if (full_sort) {
+        // general path: sort the whole list in place in global memory (L2) and sweep from the start
+        const int n_pad = pow2ceil(n);
+        for (int i = n + t; i < n_pad; i += DT) seg[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(seg, n_pad);
+        K = 0;
+        for (int base = 0; base < n && K < top_k; base += 64)
+            K = nms_block(s, seg, base, min(64, n - base), bx, s_kbox, s_karea, s_kkey, K, kcap, iou_thr, thr_lo, thr_hi);
+    }
+    // kept keys, in descending score order, to the front of the segment
+    for (int i = t; i < K; i += DT) seg[i] = s_kkey[i];
     if (t == 0) { kept_cnt[seg_id] = (unsigned)K; cand_cnt[seg_id] = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DT)
+constexpr int TK_T = 1024;
+
+__global__ void __launch_bounds__(TK_T)
 detect_topk_kernel(const float4* __restrict__ boxes, const unsigned long long* __restrict__ cand,
                    const unsigned int* __restrict__ kept_cnt, unsigned int* __restrict__ overflow,
                    const float* __restrict__ img_wh, int P, int NF, int capp, int top_k,
@@ -287,11 +391,16 @@ detect_topk_kernel(const float4* __restrict__ boxes, const unsigned long long* _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);    // [pow2ceil(NF*top_k)]
     __shared__ int s_pref[33];
+    __shared__ int s_m[33];
+    __shared__ unsigned int s_tlow;
     const int b = blockIdx.x, t = threadIdx.x;
+    if (t < NF) s_m[t] = (int)kept_cnt[(size_t)b * NF + t];
+    __syncthreads();
     if (t == 0) {
         int acc = 0;
-        for (int c = 0; c < NF; ++c) { s_pref[c] = acc; acc += (int)kept_cnt[(size_t)b * NF + c]; }
+        for (int c = 0; c < NF; ++c) { s_pref[c] = acc; acc += s_m[c]; }
         s_pref[NF] = acc;
+        s_tlow = 0u;
     }
     __syncthreads();
     const int total = s_pref[NF];
@@ -319,28 +428,46 @@ detect_topk_kernel(const float4* __restrict__ boxes, const unsigned long long* _
         for (int c = 0; c < NF; ++c) {
             const int kc = s_pref[c + 1] - s_pref[c];
             const unsigned long long* seg = cand + ((size_t)b * NF + c) * capp;
-            for (int r = t; r < kc; r += DT) emit(s_pref[c] + r, seg[r], c);
+            for (int r = t; r < kc; r += TK_T) emit(s_pref[c] + r, seg[r], c);
         }
     } else {
         // global top_k by descending prob, ties -> earlier class-major position (T7).  Only the first top_k kept
-        // boxes of a class can qualify.  Sort key: prob bits << 32 | ~(class * top_k + rank).
+        // boxes of a class can qualify, and nothing scoring below the top_k-th score of any single class can either:
+        // T_low = max over classes of that score prunes the merge to a few hundred keys.
         nout = top_k;
+        if (t < NF) {
+            const int kc = s_pref[t + 1] - s_pref[t];
+            if (kc >= top_k) atomicMax(&s_tlow, (unsigned)(cand[((size_t)b * NF + t) * capp + top_k - 1] >> 32));
+        }
+        __syncthreads();
+        const unsigned tlow = s_tlow;
+        if (t < NF) {
+            // lists are sorted by descending prob: binary search for the first entry below T_low
+            const unsigned long long* seg = cand + ((size_t)b * NF + t) * capp;
+            int lo = 0, hi = min(s_pref[t + 1] - s_pref[t], top_k);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((unsigned)(seg[mid] >> 32) >= tlow) lo = mid + 1; else hi = mid;
+            }
+            s_m[t] = lo;
+        }
+        __syncthreads();
         int m_total = 0;
-        for (int c = 0; c < NF; ++c) m_total += min(s_pref[c + 1] - s_pref[c], top_k);
+        for (int c = 0; c < NF; ++c) m_total += s_m[c];
         const int n_pad = pow2ceil(m_total);
-        for (int i = t; i < n_pad; i += DT) s_keys[i] = 0ull;
+        for (int i = t; i < n_pad; i += TK_T) s_keys[i] = 0ull;
         __syncthreads();
         int acc = 0;
         for (int c = 0; c < NF; ++c) {
-            const int mc = min(s_pref[c + 1] - s_pref[c], top_k);
+            const int mc = s_m[c];
             const unsigned long long* seg = cand + ((size_t)b * NF + c) * capp;
-            for (int r = t; r < mc; r += DT)
+            for (int r = t; r < mc; r += TK_T)
                 s_keys[acc + r] = (seg[r] & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - (unsigned)(c * top_k + r));
             acc += mc;
         }
         __syncthreads();
         bitonic_sort_desc(s_keys, n_pad);
-        for (int s = t; s < top_k; s += DT) {
+        for (int s = t; s < top_k; s += TK_T) {
             const unsigned pos = 0xffffffffu - (unsigned)(s_keys[s] & 0xffffffffull);
             const int c = (int)(pos / (unsigned)top_k), r = (int)(pos % (unsigned)top_k);
             emit(s, cand[((size_t)b * NF + c) * capp + r], c);
@@ -378,7 +505,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     count_launch();
     SSD_LAUNCH_CHECK();
 
-    const size_t smem_nms = (((size_t)(top_k + 64) * 20 + 15) & ~(size_t)15) + (size_t)std::min(capp, SORT_SMEM) * 8;
+    const size_t smem_nms = (((size_t)(top_k + 64) * 28 + 15) & ~(size_t)15) + (size_t)SORT_SMEM * 8 + (size_t)NMS_BINS * 4;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
     detect_nms_kernel<<<dim3(NF, B), DT, smem_nms, st>>>(w.boxes, w.cand, w.cand_cnt, w.kept_cnt, P, NF, cap, capp, top_k, iou_thr);
     count_launch();
@@ -386,7 +513,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
 
     const size_t smem_topk = (size_t)pow2ceil(NF * top_k) * 8;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk));
-    detect_topk_kernel<<<B, DT, smem_topk, st>>>(w.boxes, w.cand, w.kept_cnt, w.overflow, img_wh, P, NF, capp, top_k,
+    detect_topk_kernel<<<B, TK_T, smem_topk, st>>>(w.boxes, w.cand, w.kept_cnt, w.overflow, img_wh, P, NF, capp, top_k,
                                                  (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt);
     count_launch();
     SSD_LAUNCH_CHECK();

@@ -171,12 +171,14 @@ int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
     cudaStream_t st = (cudaStream_t)stream;
     SSD_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
     SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-    int rc = ssdhead_match(gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
-                           c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
+    // The HBM-bound streaming kernel is submitted FIRST so its persistent CTAs are placed before the match's;
+    // the match (issue/latency bound, tiny footprint) then fills the remaining register / thread slots of every SM.
+    int rc = ssdhead_ce_stream(conf, B, c->P, c->C, nullptr, grad_loc, grad_conf, c->ws_loss, c->ws_loss_bytes, st);
+    if (rc) return rc;
+    rc = ssdhead_match(gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
+                       c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
     if (rc) return rc;
     SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
-    rc = ssdhead_ce_stream(conf, B, c->P, c->C, nullptr, grad_loc, grad_conf, c->ws_loss, c->ws_loss_bytes, st);
-    if (rc) return rc;
     SSD_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     if (npos_total_dev) *npos_total_dev = c->npos + B;
     return 0;

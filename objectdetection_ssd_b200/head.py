@@ -138,18 +138,19 @@ class MultiboxHead:
             ce = torch.empty(B, P, dtype=torch.float32, device=self.dev)
         ws = self._workspace(_lib.WS_LOSS, B, 0)
         cur = torch.cuda.current_stream(self.dev)
-        m = match
-        if m is None:
-            # fork: the match (latency-bound, tiny traffic) runs on the auxiliary stream while the CE streaming
-            # kernel (HBM-bound, independent of the match) runs on the caller's stream
-            outs = self._match_outputs(gt, False)
+        # The HBM-bound CE streaming kernel (independent of the match) is submitted first on the caller's stream so
+        # its persistent CTAs are placed first; the match (latency-bound, tiny traffic) runs beside it on the auxiliary
+        # stream and fills the remaining slots of every SM; both join before the mining kernel.
+        if match is None:
             self._aux.wait_stream(cur)
-            with torch.cuda.stream(self._aux):
-                m = self.match(gt, pos_iou=pos_iou, outs=outs)
         _lib.check(self.lib.ssdhead_ce_stream(
             _ptr(conf), B, P, C, _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
             _ptr(ws), ws.numel(), cur.cuda_stream), "ssdhead_ce_stream")
-        if match is None:
+        m = match
+        if m is None:
+            outs = self._match_outputs(gt, False)
+            with torch.cuda.stream(self._aux):
+                m = self.match(gt, pos_iou=pos_iou, outs=outs)
             cur.wait_stream(self._aux)           # join
         npos = m["npos"]
         npos_norm = npos[B:B + 1]
