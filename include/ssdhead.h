@@ -120,6 +120,18 @@ int ssdhead_match(const float* gt_xyxy_dev, const float* gt_cls_dev, const int32
 int ssdhead_ce_stream(const float* conf_dev, int B, int P, int C, float* ce_dev,
                       float* grad_loc_dev, float* grad_conf_dev,
                       void* ws_dev, size_t ws_bytes, void* stream);
+/* ssdhead_ce_stream with the NATURAL MATCH FUSED IN (the hot path of ssd()): the consumer thread that scores prior
+ * p of image b also finds the best gt of that prior and feeds the per-gt arg-max over priors; a small finaliser
+ * kernel then applies the forced-match override.  Produces cls_u8 / best_prior / npos exactly as ssdhead_match does
+ * (same IoU code, same tie rules), so no separate pass over the priors is needed.  `ws_match` is a
+ * SSDHEAD_WS_MATCH workspace (zero-filled once; left zeroed).  B*P < 2^31. */
+int ssdhead_ce_match_stream(const float* conf_dev, const float* gt_xyxy_dev, const float* gt_cls_dev,
+                            const int32_t* gt_off_dev, const float* pri_xyxy_dev,
+                            int B, int P, int C, int sumG, float pos_iou,
+                            float* ce_dev, float* grad_loc_dev, float* grad_conf_dev,
+                            uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                            void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                            void* stream);
 int ssdhead_mine(const float* loc_dev, const float* conf_dev,
                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                  const float* pri_xyxy_dev, const float* pri_cxcywh_dev,

@@ -160,7 +160,7 @@ fail:
 }
 
 // Sharded batches: the step in two halves around the all-reduce of the positive count.
-// begin: match on the auxiliary stream beside the CE streaming kernel, joined on `stream`; on return
+// begin: the CE streaming kernel with the fused natural match + the forced-match finaliser; on return
 // *npos_total_dev points to this rank's int32 positive count (device memory owned by the context).
 int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
                                     const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
@@ -169,17 +169,11 @@ int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
     if (!c) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
     cudaStream_t st = (cudaStream_t)stream;
-    SSD_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
-    SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-    // The HBM-bound streaming kernel is submitted FIRST so its persistent CTAs are placed before the match's;
-    // the match (issue/latency bound, tiny footprint) then fills the remaining register / thread slots of every SM.
-    int rc = ssdhead_ce_stream(conf, B, c->P, c->C, nullptr, grad_loc, grad_conf, c->ws_loss, c->ws_loss_bytes, st);
+    // the natural match rides inside the CE streaming kernel; a small finaliser applies the forced-match override
+    const int rc = ssdhead_ce_match_stream(conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
+                                           nullptr, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
+                                           c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, st);
     if (rc) return rc;
-    rc = ssdhead_match(gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
-                       c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
-    if (rc) return rc;
-    SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
-    SSD_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     if (npos_total_dev) *npos_total_dev = c->npos + B;
     return 0;
 }

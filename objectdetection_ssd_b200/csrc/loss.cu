@@ -31,7 +31,9 @@ namespace ssdhead {
 // ------------------------------------------------------------------------------------------------
 // per-row cross entropy, -(x_c - max - log(sum exp(x - max))): the order ATen's log_softmax uses
 // ------------------------------------------------------------------------------------------------
-template <int C>
+// FAST = true (streaming kernel only): exp through one ex2.approx per element (d <= 0; relative error
+// <= (2 + 1.16|d|) ulp, i.e. an absolute error of ~2e-7 on log(sum)); the gradient and positive-row paths use expf.
+template <int C, bool FAST = false>
 __device__ __forceinline__ float row_cross_entropy(const float* __restrict__ row, int c)
 {
     float x[C];
@@ -44,7 +46,7 @@ __device__ __forceinline__ float row_cross_entropy(const float* __restrict__ row
 #pragma unroll
     for (int q = 0; q < C; ++q) {
         const float d = __fsub_rn(x[q], m);
-        s = __fadd_rn(s, expf(d));
+        s = __fadd_rn(s, FAST ? __expf(d) : expf(d));
         if (q == c) xc = d;
     }
     const float ce = __fsub_rn(logf(s), xc);
@@ -55,14 +57,213 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Natural match fused into the streaming kernel (Losses.py:150-157): the consumer thread that scores prior p of
+// image b also finds the best gt of that prior (T1) and takes part in the per-gt arg-max over priors (T2, merged with
+// 64-bit atomicMax exactly as match_kernel does).  The streaming kernel is HBM-bound with issue slots to spare, so
+// the ~G*15 extra instructions per row ride along for free and the separate match kernel leaves the critical path.
+// Called by all 32 lanes of a warp together (`valid` masks rows past the end).
+// ------------------------------------------------------------------------------------------------
+struct FusedMatch {
+    const float4* gt_xyxy;
+    const float* gt_cls;
+    const int* gt_off;
+    const float4* pri_xyxy;
+    int P, bg_class;
+    float pos_iou;
+    uint8_t* cls_u8;
+    unsigned long long* best_key;
+    int* npos_acc;
+};
+
+// Everything the match of one row needs from global memory, fetched ONE TILE AHEAD so the two dependent L2 round trips
+// (gt offsets -> gt boxes) and the prior box are in flight while the previous tile is being scored.
+struct FusedPre {
+    float4 pb;          // prior box of this row
+    float4 gbox;        // lane l: gt l of the first image this warp touches (first 32 gts)
+    float gcls;         //         and its class
+    int b, p;           // image / prior of this row (-1 / 0 past the end)
+    int b_first, b_last, off0, G;
+};
+
+__device__ __forceinline__ FusedPre fused_prefetch(const FusedMatch& m, unsigned row, bool valid)
+{
+    FusedPre r;
+    const int lane = threadIdx.x & 31;
+    r.b = valid ? (int)(row / (unsigned)m.P) : -1;
+    r.p = valid ? (int)(row - (unsigned)r.b * (unsigned)m.P) : 0;
+    r.b_first = (int)__reduce_min_sync(FULL, valid ? (unsigned)r.b : 0x7fffffffu);
+    r.b_last = __reduce_max_sync(FULL, r.b);
+    r.pb = valid ? m.pri_xyxy[r.p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.off0 = 0; r.G = 0;
+    r.gbox = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.gcls = 0.0f;
+    if (r.b_last >= 0) {
+        r.off0 = m.gt_off[r.b_first];
+        r.G = m.gt_off[r.b_first + 1] - r.off0;
+        if (lane < min(r.G, 32)) { r.gbox = m.gt_xyxy[r.off0 + lane]; r.gcls = m.gt_cls[r.off0 + lane]; }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned row, bool valid, const FusedPre& pre)
+{
+    const int lane = threadIdx.x & 31;
+    if (pre.b_last < 0) return;                              // no valid row in this warp
+    const int b = pre.b, p = pre.p;
+    const float4 pb = pre.pb;
+    const float pa = box_area(pb);
+    float best = 0.0f;                 // IoU >= 0 and ties keep the first gt: (0, gt 0) equals max() over the column
+    int g_mine = 0;
+    float cls_mine = (float)m.bg_class;
+    // bounding box of the warp's 32 consecutive priors: a gt that misses it has IoU 0 with all of them, so the whole
+    // pair test, the reduction and the atomic are skipped for that gt (about 3 of 4 gts for the dense 38x38 level)
+    float wx1 = pb.x, wy1 = pb.y, wx2 = pb.z, wy2 = pb.w;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        wx1 = fminf(wx1, __shfl_xor_sync(FULL, wx1, d));
+        wy1 = fminf(wy1, __shfl_xor_sync(FULL, wy1, d));
+        wx2 = fmaxf(wx2, __shfl_xor_sync(FULL, wx2, d));
+        wy2 = fmaxf(wy2, __shfl_xor_sync(FULL, wy2, d));
+    }
+    for (int bb = pre.b_first; bb <= pre.b_last; ++bb) {     // one image per warp except where a warp straddles two
+        const bool first = (bb == pre.b_first);
+        const int off0 = first ? pre.off0 : m.gt_off[bb];
+        const int G = first ? pre.G : m.gt_off[bb + 1] - off0;
+        const bool act = (b == bb);
+        if (act) g_mine = G;
+        const bool owns_p0 = __any_sync(FULL, act && p == 0);   // the arg-max of an all-zero IoU row is prior 0 (T2)
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            // lane l holds gt g0+l (box + class): one coalesced round trip per 32 gts instead of one per gt;
+            // the loop below broadcasts them with shuffles
+            const int gc = min(32, G - g0);
+            float4 mybox = pre.gbox;
+            float mycls = pre.gcls;
+            if (!(first && g0 == 0)) {
+                mybox = make_float4(0.f, 0.f, 0.f, 0.f);
+                mycls = 0.0f;
+                if (lane < gc) { mybox = m.gt_xyxy[off0 + g0 + lane]; mycls = m.gt_cls[off0 + g0 + lane]; }
+            }
+            const float myarea = box_area(mybox);
+            int chunk_best = -1;
+            // lanes whose gt can touch the warp's priors (the warp owning prior 0 must visit every gt: an all-zero
+            // IoU row resolves to prior 0)
+            unsigned todo = __ballot_sync(FULL, lane < gc && (owns_p0 || (mybox.z > wx1 && mybox.x < wx2 && mybox.w > wy1 && mybox.y < wy2)));
+            while (todo) {
+                const int g = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float gx = __shfl_sync(FULL, mybox.x, g), gy = __shfl_sync(FULL, mybox.y, g);
+                const float gz = __shfl_sync(FULL, mybox.z, g), gw = __shfl_sync(FULL, mybox.w, g);
+                const float ga = __shfl_sync(FULL, myarea, g);
+                float v = 0.0f;
+                if (act) {
+                    const float dx = __fsub_rn(fminf(gz, pb.z), fmaxf(gx, pb.x));
+                    const float dy = __fsub_rn(fminf(gw, pb.w), fmaxf(gy, pb.y));
+                    if (dx > 0.0f && dy > 0.0f) {            // disjoint boxes have IoU == +0 exactly
+                        const float inter = __fmul_rn(dx, dy);
+                        v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, pa), inter));
+                        if (v > best) { best = v; chunk_best = g; }                   // T1: strict > keeps the first gt
+                    }
+                }
+                const uint32_t mx = __reduce_max_sync(FULL, __float_as_uint(v));      // IoU >= 0: bits order like values
+                if (mx != 0u || owns_p0) {
+                    const unsigned ball = __ballot_sync(FULL, act && __float_as_uint(v) == mx);
+                    const int wp = __shfl_sync(FULL, p, __ffs(ball) - 1);             // T2: lowest lane = lowest prior
+                    if (lane == 0)
+                        atomicMax(&m.best_key[off0 + g0 + g],
+                                  ((unsigned long long)(mx | 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)wp));
+                }
+            }
+            // class of the best gt so far: gt 0 by default (first chunk), else the arg-max found in this chunk
+            const float c_first = __shfl_sync(FULL, mycls, 0);
+            const float c_best = __shfl_sync(FULL, mycls, chunk_best < 0 ? 0 : chunk_best);
+            if (act) {
+                if (chunk_best >= 0) cls_mine = c_best;
+                else if (g0 == 0) cls_mine = c_first;
+            }
+        }
+    }
+    if (valid) {
+        const bool hit = (g_mine > 0) && !(best < m.pos_iou);                     // T6
+        const int c = hit ? (int)cls_mine : m.bg_class;
+        m.cls_u8[row] = (uint8_t)c;                                               // natural class; forced matches patched later
+        if (c != m.bg_class) atomicAdd(&m.npos_acc[b], 1);
+    }
+}
+
+// After the streaming kernel: forced-match override (Losses.py:164-167) + positive counts.  One small CTA per image.
+__global__ void __launch_bounds__(64)
+match_finalize_kernel(const float* __restrict__ gt_cls, const int* __restrict__ gt_off, int B, int P, int bg_class,
+                      int* __restrict__ best_prior, int* __restrict__ npos, uint8_t* __restrict__ cls_u8,
+                      unsigned long long* __restrict__ best_key, int* __restrict__ npos_acc, unsigned int* __restrict__ image_counter)
+{
+    constexpr int CAP = 128;                                 // gts handled out of shared memory
+    __shared__ int s_bp[CAP];
+    __shared__ int s_extra;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int off0 = gt_off[b];
+    const int G = gt_off[b + 1] - off0;
+    const int acc0 = ld_cg_s32(&npos_acc[b]);                // independent of the gts: issue early
+    if (t == 0) s_extra = 0;
+    // one round of loads: best prior + class of every gt of the image
+    int my_p[CAP / 64], my_c[CAP / 64];
+#pragma unroll
+    for (int q = 0; q < CAP / 64; ++q) {
+        const int g = t + 64 * q;
+        my_p[q] = -1; my_c[q] = bg_class;
+        if (g < G) {
+            my_p[q] = (int)(0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g]) & 0xffffffffull));
+            my_c[q] = (int)gt_cls[off0 + g];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < CAP / 64; ++q) {
+        const int g = t + 64 * q;
+        if (g < G) { s_bp[g] = my_p[q]; best_prior[off0 + g] = my_p[q]; best_key[off0 + g] = 0ull; }
+    }
+    for (int g = CAP + t; g < G; g += 64) {                  // images with more than CAP gts: through global memory
+        best_prior[off0 + g] = (int)(0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g]) & 0xffffffffull));
+        best_key[off0 + g] = 0ull;
+    }
+    __syncthreads();
+    int extra = 0;
+    for (int g = t; g < G; g += 64) {
+        const int p = g < CAP ? s_bp[g] : best_prior[off0 + g];
+        bool winner = true;                                  // T3: the highest gt index keeps the prior
+        for (int g2 = g + 1; g2 < G; ++g2) winner = winner && ((g2 < CAP ? s_bp[g2] : best_prior[off0 + g2]) != p);
+        if (winner) {
+            const int c_new = (g < CAP) ? my_c[g / 64] : (int)gt_cls[off0 + g];
+            const int c_nat = (int)cls_u8[(size_t)b * P + p];
+            extra += (c_new != bg_class ? 1 : 0) - (c_nat != bg_class ? 1 : 0);
+            cls_u8[(size_t)b * P + p] = (uint8_t)c_new;
+        }
+    }
+    if (extra) atomicAdd(&s_extra, extra);
+    __syncthreads();
+    if (t == 0) {
+        npos[b] = acc0 + s_extra;
+        npos_acc[b] = 0;
+        __threadfence();
+        const unsigned done = atomicAdd(image_counter, 1u);
+        if (done == gridDim.x - 1) {                         // last image: batch total, fixed order
+            __threadfence();
+            int tot = 0;
+            for (int i = 0; i < B; ++i) tot += ld_cg_s32(&npos[i]);
+            npos[B] = tot;
+            *image_counter = 0u;
+        }
+    }
+}
+
 constexpr int CE_ROWS = 256;                      // rows per tile = consumer threads
 constexpr int CE_STAGES = 4;
 constexpr int CE_THREADS = CE_ROWS + 32;          // + one producer warp
 
-template <int C, bool ZERO_FILL>
+template <int C, bool ZERO_FILL, bool MATCH>
 __global__ void __launch_bounds__(CE_THREADS, 2)
 ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
-                 float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma)
+                 float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma,
+                 const FusedMatch fm)
 {
     constexpr uint32_t TILE_BYTES = CE_ROWS * C * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -107,10 +308,18 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
         // ---------------- consumer warps: thread per row ----------------
         int s = 0;
         uint32_t ph = 0;
+        FusedPre pre, nxt;
+        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)(blockIdx.x * CE_ROWS + t), true);
         for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
             const long long row = tile * CE_ROWS + t;
+            if (MATCH) {
+                // issue the next tile's match inputs now; score this tile's match (independent of the conf tile)
+                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)((tile + gridDim.x) * CE_ROWS + t), true);
+                fused_match_rows(fm, (unsigned)row, true, pre);
+                pre = nxt;
+            }
             mbar_wait(&s_full[s], ph);
-            const float ce = row_cross_entropy<C>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
+            const float ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
             ce_out[row] = ce;
@@ -118,13 +327,18 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
         }
         // rows past the last full tile (or every row when the pointers are not 16-byte aligned): plain loads
         const long long rest0 = full_tiles * CE_ROWS;
-        for (long long row = rest0 + (long long)blockIdx.x * CE_ROWS + t; row < total_rows; row += (long long)gridDim.x * CE_ROWS) {
-            ce_out[row] = row_cross_entropy<C>(conf + (size_t)row * C, C - 1);
-            if (ZERO_FILL) {
+        for (long long row0 = rest0 + (long long)blockIdx.x * CE_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * CE_ROWS) {
+            const long long row = row0 + t;                  // the loop bound is CTA-uniform: warps stay converged
+            const bool valid = row < total_rows;
+            if (MATCH) fused_match_rows(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
+            if (valid) {
+                ce_out[row] = row_cross_entropy<C, true>(conf + (size_t)row * C, C - 1);
+                if (ZERO_FILL) {
 #pragma unroll
-                for (int q = 0; q < C; ++q) grad_conf[(size_t)row * C + q] = 0.0f;
+                    for (int q = 0; q < C; ++q) grad_conf[(size_t)row * C + q] = 0.0f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) grad_loc[(size_t)row * 4 + q] = 0.0f;
+                    for (int q = 0; q < 4; ++q) grad_loc[(size_t)row * 4 + q] = 0.0f;
+                }
             }
         }
     }
@@ -560,17 +774,18 @@ static int num_sms()
     return g_num_sms;
 }
 
-template <int C, bool GRADS>
-static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, float* grad_loc, long long rows, cudaStream_t st)
+template <int C, bool GRADS, bool MATCH>
+static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, float* grad_loc, long long rows,
+                            const FusedMatch& fm, cudaStream_t st)
 {
     constexpr size_t tile = (size_t)CE_ROWS * C * 4;
     const size_t smem_ce = tile * CE_STAGES + (GRADS ? tile : 0);
-    auto kce = ce_stream_kernel<C, GRADS>;
+    auto kce = ce_stream_kernel<C, GRADS, MATCH>;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ce));
     const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(grad_conf) && aligned16(grad_loc)))) ? 1 : 0;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS;
     const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
-    kce<<<grid_ce, CE_THREADS, smem_ce, st>>>(conf, ce, grad_conf, grad_loc, rows, use_tma);
+    kce<<<grid_ce, CE_THREADS, smem_ce, st>>>(conf, ce, grad_conf, grad_loc, rows, use_tma, fm);
     count_launch();
     SSD_LAUNCH_CHECK();
     return 0;
@@ -609,8 +824,51 @@ int ssdhead_ce_stream(const float* conf, int B, int P, int C, float* ce, float* 
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     float* ce_buf = ce ? ce : ws_ce(ws, B);
     const long long rows = (long long)B * P;
-    return grad_loc ? launch_ce_stream<21, true>(conf, ce_buf, grad_conf, grad_loc, rows, (cudaStream_t)stream)
-                    : launch_ce_stream<21, false>(conf, ce_buf, nullptr, nullptr, rows, (cudaStream_t)stream);
+    FusedMatch none = {};
+    return grad_loc ? launch_ce_stream<21, true, false>(conf, ce_buf, grad_conf, grad_loc, rows, none, (cudaStream_t)stream)
+                    : launch_ce_stream<21, false, false>(conf, ce_buf, nullptr, nullptr, rows, none, (cudaStream_t)stream);
+}
+
+// ssdhead_ce_stream with the natural match fused in, followed by the per-image forced-match finaliser: produces
+// everything ssdhead_match produces for the loss (cls_u8, best_prior, npos) without a separate pass over the priors.
+int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                            const float* pri_xyxy, int B, int P, int C, int sumG, float pos_iou,
+                            float* ce, float* grad_loc, float* grad_conf,
+                            uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    if (B < 0 || P <= 0 || sumG < 0 || !conf || !gt_off || !pri_xyxy || !cls_u8 || !npos || !ws_loss || !ws_match) return SSDHEAD_E_BADARG;
+    if (sumG > 0 && (!gt_xyxy || !gt_cls || !best_prior)) return SSDHEAD_E_BADARG;
+    if ((grad_loc == nullptr) != (grad_conf == nullptr)) return SSDHEAD_E_BADARG;
+    if (C != 21) return SSDHEAD_E_UNSUPPORTED;
+    if (B == 0) return 0;
+    if ((long long)B * P >= (1ll << 31)) return SSDHEAD_E_UNSUPPORTED;
+    if ((grad_loc && !aligned16(grad_loc)) || !aligned16(ws_loss) || !aligned16(ws_match) || !aligned16(pri_xyxy) ||
+        (sumG > 0 && !aligned16(gt_xyxy)))
+        return SSDHEAD_E_ALIGN;
+    const size_t need = loss_workspace_bytes(B, P, C);
+    if (need == 0) return SSDHEAD_E_UNSUPPORTED;
+    if (ws_loss_bytes < need) return SSDHEAD_E_WORKSPACE;
+    if (ws_match_bytes < ssdhead_workspace_bytes(SSDHEAD_WS_MATCH, B, P, C, sumG)) return SSDHEAD_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // match workspace layout (zero on entry, zero on exit): best_key[sumG] u64 | tile_counter[B] | npos_acc[B] | image_counter
+    char* w = (char*)ws_match;
+    unsigned long long* best_key = (unsigned long long*)w;            w += round_up((size_t)sumG * 8, 16);
+    w += round_up((size_t)B * 4, 16);
+    int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
+    unsigned int* image_counter = (unsigned int*)w;
+    FusedMatch fm;
+    fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
+    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc;
+    float* ce_buf = ce ? ce : ws_ce(ws_loss, B);
+    const long long rows = (long long)B * P;
+    const int rc = grad_loc ? launch_ce_stream<21, true, true>(conf, ce_buf, grad_conf, grad_loc, rows, fm, st)
+                            : launch_ce_stream<21, false, true>(conf, ce_buf, nullptr, nullptr, rows, fm, st);
+    if (rc) return rc;
+    match_finalize_kernel<<<B, 64, 0, st>>>(gt_cls, gt_off, B, P, C - 1, best_prior, npos, cls_u8, best_key, npos_acc, image_counter);
+    count_launch();
+    SSD_LAUNCH_CHECK();
+    return 0;
 }
 
 int ssdhead_mine(const float* loc, const float* conf,

@@ -75,7 +75,6 @@ class MultiboxHead:
         self.pri_cxcywh = pc.to(self.dev)
         self.pri_xyxy = cxcywh_to_xyxy_host(pc).to(self.dev)     # same fp32 ops as Util.py:93-96
         self._ws = {}
-        self._aux = torch.cuda.Stream(self.dev)                  # the match runs here, beside the CE stream kernel
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, which: int, B: int, n: int) -> torch.Tensor:
@@ -138,20 +137,22 @@ class MultiboxHead:
             ce = torch.empty(B, P, dtype=torch.float32, device=self.dev)
         ws = self._workspace(_lib.WS_LOSS, B, 0)
         cur = torch.cuda.current_stream(self.dev)
-        # The HBM-bound CE streaming kernel (independent of the match) is submitted first on the caller's stream so
-        # its persistent CTAs are placed first; the match (latency-bound, tiny traffic) runs beside it on the auxiliary
-        # stream and fills the remaining slots of every SM; both join before the mining kernel.
-        if match is None:
-            self._aux.wait_stream(cur)
-        _lib.check(self.lib.ssdhead_ce_stream(
-            _ptr(conf), B, P, C, _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
-            _ptr(ws), ws.numel(), cur.cuda_stream), "ssdhead_ce_stream")
         m = match
         if m is None:
-            outs = self._match_outputs(gt, False)
-            with torch.cuda.stream(self._aux):
-                m = self.match(gt, pos_iou=pos_iou, outs=outs)
-            cur.wait_stream(self._aux)           # join
+            # hot path: the natural match rides inside the HBM-bound CE streaming kernel (spare issue slots), a small
+            # finaliser applies the forced-match override; no separate pass over the priors
+            m = self._match_outputs(gt, False)
+            wm = self._workspace(_lib.WS_MATCH, B, gt.sumG)
+            _lib.check(self.lib.ssdhead_ce_match_stream(
+                _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off), _ptr(self.pri_xyxy),
+                B, P, C, gt.sumG, float(pos_iou), _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
+                _ptr(m["cls_u8"]), _ptr(m["best_prior"]), _ptr(m["npos"]),
+                _ptr(ws), ws.numel(), _ptr(wm), wm.numel(), cur.cuda_stream), "ssdhead_ce_match_stream")
+        else:
+            # a match computed beforehand with ssdhead_match (e.g. with the debug taps)
+            _lib.check(self.lib.ssdhead_ce_stream(
+                _ptr(conf), B, P, C, _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
+                _ptr(ws), ws.numel(), cur.cuda_stream), "ssdhead_ce_stream")
         npos = m["npos"]
         npos_norm = npos[B:B + 1]
         if group is not None:

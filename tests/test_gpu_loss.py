@@ -234,3 +234,62 @@ def test_loss_misaligned_conf_pointer_uses_plain_loads():
     torch.cuda.synchronize()
     assert torch.equal(a["losses"], b["losses"])
     assert torch.equal(a["grad_conf"], b["grad_conf"]) and torch.equal(a["grad_loc"], b["grad_loc"])
+
+
+def test_fused_match_equals_standalone_match():
+    """The match fused into the CE streaming kernel must reproduce ssdhead_match bit for bit (class bytes,
+    best prior per gt, positive counts), including the tie cases and a warp that straddles two images."""
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    pri = H.priors()
+    for seed, B, gts in ((51, 5, None), (52, 3, "ties")):
+        loc, conf, tb, tc = H.train_inputs(seed, B, pri.shape[0])
+        if gts == "ties":
+            box = torch.tensor([[0.2, 0.2, 0.6, 0.7]])
+            tb = [torch.cat([box, box, box]), torch.tensor([[0.5, 0.5, 0.5, 0.5], [0.1, 0.1, 0.3, 0.3]]),
+                  torch.tensor([[0.3, 0.3, 0.31, 0.31], [0.3, 0.3, 0.31, 0.31], [0.9, 0.9, 1.0, 1.0]])]
+            tc = [torch.tensor([3., 7., 5.]), torch.tensor([1., 2.]), torch.tensor([0., 4., 8.])]
+        head = MultiboxHead(pri, "cuda")
+        gt = PackedGT(tb, tc, head.dev)
+        ref = head.match(gt)
+        out = head.loss(loc.cuda(), conf.cuda(), gt, with_grads=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out["cls_u8"], ref["cls_u8"])
+        assert torch.equal(out["best_prior"][:gt.sumG], ref["best_prior"][:gt.sumG])
+        assert torch.equal(out["npos"], ref["npos"])
+        again = head.loss(loc.cuda(), conf.cuda(), gt, with_grads=True, match=ref)      # separate-match route
+        torch.cuda.synchronize()
+        assert torch.equal(again["losses"], out["losses"]) and torch.equal(again["grad_conf"], out["grad_conf"])
+
+
+def test_mining_stage_isolated_is_bit_exact():
+    """Stage-isolated T4 check: feed the ORACLE's cross entropies to ssdhead_mine (skipping the kernels' own exp/log)
+    and require the mined-negative set to equal the oracle's bit for bit, for random and tie-heavy inputs."""
+    from objectdetection_ssd_b200 import _lib
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    pri = H.priors()
+    P = pri.shape[0]
+    lib = _lib.load()
+    for seed, B, quant in ((61, 8, None), (62, 4, 0.25)):
+        loc, conf, tb, tc = H.train_inputs(seed, B, P)
+        if quant:
+            conf = torch.round(conf / quant) * quant          # many exactly equal CE values -> ties across the boundary
+        ref = O.multibox_loss(loc, conf, tb, tc, pri)
+        head = MultiboxHead(pri, "cuda")
+        gt = PackedGT(tb, tc, head.dev)
+        m = head.match(gt)
+        bg = torch.full((B, P), 20, dtype=torch.int64)
+        ce_bg = O.cross_entropy_rows(conf, bg).cuda().contiguous()        # what the streaming kernel would hand over
+        l, c = loc.cuda(), conf.cuda()
+        sums = torch.empty(2, dtype=torch.float64, device="cuda")
+        losses = torch.empty(2, device="cuda")
+        mined = torch.empty(B, (P + 31) // 32, dtype=torch.int32, device="cuda")
+        ws = head._workspace(_lib.WS_LOSS, B, 0)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.ssdhead_mine(l.data_ptr(), c.data_ptr(), gt.boxes.data_ptr(), gt.classes.data_ptr(), gt.off.data_ptr(),
+                                    head.pri_xyxy.data_ptr(), head.pri_cxcywh.data_ptr(), m["best_prior"].data_ptr(),
+                                    m["npos"].data_ptr(), m["npos"][B:].data_ptr(), m["cls_u8"].data_ptr(),
+                                    B, P, 21, 3, 0.5, sums.data_ptr(), losses.data_ptr(), None, None,
+                                    mined.data_ptr(), ce_bg.data_ptr(), ws.data_ptr(), ws.numel(), st), "ssdhead_mine")
+        torch.cuda.synchronize()
+        assert torch.equal(H.unpack_mask(mined, P), ref["mined"]), f"seed {seed}: mined set differs from the oracle"
+        assert abs(losses[1].item() - ref["conf_loss"].item()) <= 1e-6 * ref["conf_loss"].item()
