@@ -14,6 +14,9 @@
  *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*),
  *     allocate nothing, keep no global state and are re-entrant across streams when each
  *     call has its own workspace.  The caller owns every buffer.
+ *   - workspaces: sized by ssdhead_workspace_bytes(); must be zero-filled before their first use with a given
+ *     (B, P, C, n) - the kernels leave every counter zeroed again, so steady-state steps contain no memsets, but the
+ *     position of the counters depends on the shape: re-zero a buffer before reusing it with another shape.
  *   - there is no CPU fallback anywhere in this library.
  *   - gt layout: boxes packed [sumG,4] fractional xyxy, classes [sumG] fp32 (Dataset.py:26),
  *     offsets int32 [B+1] (the cumsum of Losses.py:130).  Background class id = C-1

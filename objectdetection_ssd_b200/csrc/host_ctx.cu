@@ -3,6 +3,7 @@
 // or on HOST buffers, with the copies pipelined against the kernels in image chunks.
 // Reference call sites: ssd() train_function.py:82 (loss), inference() Losses.py:11-98 (detect).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -32,7 +33,7 @@ __global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nch
 }  // namespace ssdhead
 
 struct ssdhead_ctx {
-    int device, maxB, P, C, max_sumG, top_k;
+    int device, maxB, P, C, max_sumG, top_k, last_detect_B;
     cudaStream_t s_main, s_aux, s_h2d, s_d2h;
     cudaEvent_t ev_fork, ev_join, ev_gt, ev_done;
     std::vector<cudaEvent_t> ev_in, ev_out;            // per chunk
@@ -58,7 +59,7 @@ struct ssdhead_ctx {
 
 #define CTX_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
 
-static const int kMaxChunks = 8;
+static const int kMaxChunks = 16;
 
 extern "C" {
 
@@ -234,7 +235,8 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     if (rc) return rc;
     SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
 
-    const int nchunks = std::min(kMaxChunks, std::max(1, B / 8));
+    // >= 8 images per chunk, at most 8 chunks (measured on B200/PCIe5: 1 chunk 8.2 ms, 4: 5.8, 8: 5.6, 16: 6.3 at B=256)
+    const int nchunks = std::min(8, std::max(1, B / 8));
     const int per = (B + nchunks - 1) / nchunks;
     int used = 0;
     for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
@@ -282,6 +284,11 @@ int ssdhead_ctx_detect_host(ssdhead_ctx* c, const float* loc_h, const float* con
     if (B <= 0 || B > c->maxB || !c->ws_detect) return SSDHEAD_E_STATE;
     SSD_CHECK_CUDA(cudaSetDevice(c->device));
     const size_t nr = (size_t)B * c->P;
+    if (c->last_detect_B != B) {
+        // the detect workspace keeps its counters zeroed, but their position depends on B: re-zero on a shape change
+        SSD_CHECK_CUDA(cudaMemsetAsync(c->ws_detect, 0, c->ws_detect_bytes, c->s_main));
+        c->last_detect_B = B;
+    }
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf, conf_h, nr * c->C * 4, cudaMemcpyHostToDevice, c->s_main));
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc, loc_h, nr * 16, cudaMemcpyHostToDevice, c->s_main));
     const int rc = ssdhead_detect(c->loc, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k, nullptr, 0,

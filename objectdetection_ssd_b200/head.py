@@ -82,10 +82,15 @@ class MultiboxHead:
         if need == 0:
             raise RuntimeError("ssdhead: unsupported shape for this entry point "
                                f"(B={B}, P={self.P}, C={self.C})")
-        cur = self._ws.get(which)
+        key = (B, n)
+        cur, last = self._ws.get(which, (None, None))
         if cur is None or cur.numel() < need:
             cur = torch.zeros(need + 4096, dtype=torch.uint8, device=self.dev)
-            self._ws[which] = cur
+        elif last != key:
+            # the kernels leave their counters zeroed, but the layout of the counters depends on (B, n): a buffer
+            # last used with another shape must be zero-filled again (include/ssdhead.h, "zero-filled before first use")
+            cur.zero_()
+        self._ws[which] = (cur, key)
         return cur
 
     # ------------------------------------------------------------------ match

@@ -78,3 +78,30 @@ def test_loss_dev_single_call():
     assert torch.equal(out["losses"], losses) and torch.equal(out["sums"], sums)
     assert torch.equal(out["grad_conf"], gcf) and torch.equal(out["grad_loc"], gl)
     ctx.close()
+
+
+def test_detect_host_matches_device_path_and_survives_batch_changes():
+    from objectdetection_ssd_b200.ctx import SSDHeadContext, pinned_empty
+    from objectdetection_ssd_b200.head import MultiboxHead, detect
+    pri = H.priors()
+    P = pri.shape[0]
+    ctx = SSDHeadContext(pri.numpy(), max_batch=6)
+    head = MultiboxHead(pri, "cuda")
+    for B in (6, 2, 5):                                   # one context, changing batch sizes
+        loc, conf = synth.make_head(80 + B, B, P, loc_scale=0.5, bg_bias=7.5)
+        hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+        hl[:] = loc
+        hc[:] = conf
+        ob, op = pinned_empty((B, 200, 4)), pinned_empty((B, 200))
+        oc, oi, on = pinned_empty((B, 200), np.int32), pinned_empty((B, 200), np.int32), pinned_empty((B,), np.int32)
+        ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
+        out = detect(head, torch.from_numpy(loc), torch.from_numpy(conf), 0.01, 0.45, 200)
+        torch.cuda.synchronize()
+        assert np.array_equal(on, out["cnt"].cpu().numpy())
+        for b in range(B):
+            k = int(on[b])
+            assert np.array_equal(oi[b, :k], out["prior"][b, :k].cpu().numpy())
+            assert np.array_equal(oc[b, :k], out["cls"][b, :k].cpu().numpy())
+            assert np.array_equal(op[b, :k], out["prob"][b, :k].cpu().numpy())
+            assert np.array_equal(ob[b, :k], out["boxes"][b, :k].cpu().numpy())
+    ctx.close()
