@@ -135,6 +135,21 @@ int ssdhead_ce_match_stream(const float* conf_dev, const float* gt_xyxy_dev, con
                             uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
                             void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
                             void* stream);
+/* The whole training-head step of ONE GPU in two kernels: ssdhead_ce_match_stream's streaming kernel, then the
+ * mining kernel with the forced-match finaliser fused in (cooperative launch: its CTAs exchange the batch positive
+ * count through a counter they wait on, so all B CTAs must be co-resident).  Falls back by itself to the
+ * three-kernel sequence (streaming, finaliser, mining) when B exceeds the co-resident capacity.  Outputs as
+ * ssdhead_match (cls_u8, best_prior, npos) + ssdhead_mine (sums, losses, gradients, taps).  Not for sharded batches
+ * (the all-reduce of the positive count has to sit between the kernels: use ce_match_stream + mine). */
+int ssdhead_multibox_step(const float* loc_dev, const float* conf_dev,
+                          const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                          const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                          uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                          uint32_t* mined_mask_dev, float* ce_dev,
+                          void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                          void* stream);
 int ssdhead_mine(const float* loc_dev, const float* conf_dev,
                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                  const float* pri_xyxy_dev, const float* pri_cxcywh_dev,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/ssdhead.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -133,6 +134,30 @@ __device__ __forceinline__ int ld_cg_s32(const int* p) {
     int v;
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor
+// in the stream is still running; it must call pdl_wait() before touching anything the predecessor produces (or
+// anything the predecessor still reads, before overwriting it).  pdl_trigger() lets the NEXT kernel start early.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    static const int mask = getenv("SSDHEAD_PDL") ? atoi(getenv("SSDHEAD_PDL")) : 5;   // measured: CE + mine (5) best; chaining finaliser + mine (6, 7) is slower
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (mask & which) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -200,10 +200,11 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
                                   int neg_ratio, float pos_iou,
                                   double* sums, float* losses, float* grad_loc, float* grad_conf, void* stream)
 {
-    int rc = ssdhead_ctx_multibox_loss_begin(c, conf, gt_xyxy, gt_cls, gt_off, B, sumG, pos_iou, grad_loc, grad_conf, nullptr, stream);
-    if (rc) return rc;
-    return ssdhead_ctx_multibox_loss_end(c, loc, conf, gt_xyxy, gt_cls, gt_off, B, neg_ratio, pos_iou, nullptr,
-                                         sums, losses, grad_loc, grad_conf, stream);
+    if (!c) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    return ssdhead_multibox_step(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
+                                 neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
+                                 nullptr, nullptr, c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, stream);
 }
 
 // ssd() on HOST buffers (pass page-locked memory, e.g. ssdhead_host_alloc, for asynchronous copies).

@@ -203,6 +203,8 @@ match_finalize_kernel(const float* __restrict__ gt_cls, const int* __restrict__ 
     const int b = blockIdx.x, t = threadIdx.x;
     const int off0 = gt_off[b];
     const int G = gt_off[b + 1] - off0;
+    pdl_trigger();                                           // let the mining kernel become resident behind us
+    pdl_wait();                                              // everything below reads what the streaming kernel wrote
     const int acc0 = ld_cg_s32(&npos_acc[b]);                // independent of the gts: issue early
     if (t == 0) s_extra = 0;
     // one round of loads: best prior + class of every gt of the image
@@ -284,6 +286,8 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
             reinterpret_cast<float4*>(zero_tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async_smem();
     }
+    pdl_trigger();                                           // the finaliser may become resident now (it waits for us)
+    pdl_wait();                                              // the previous step may still be reading the buffers we overwrite
     __syncthreads();
 
     if (warp == CE_ROWS / 32) {
@@ -374,6 +378,14 @@ struct MineParams {
     uint32_t* mined_mask;
     double* partials;            // [B][2]
     unsigned int* done_counter;  // self-resetting
+    // fused forced-match finaliser (FIN = true; cooperative launch, all CTAs co-resident):
+    uint8_t* cls_rw;             // class bytes, patched in place
+    int* best_prior_w;           // [sumG] out
+    int* npos_w;                 // [B+1] out
+    unsigned long long* best_key;   // match workspace: per-gt arg-max keys (left zeroed)
+    int* npos_acc;                  //                  natural positives per image (left zeroed)
+    unsigned int* arrive;           // workspace word: CTAs that published their count (left zeroed)
+    int* total_acc;                 // workspace word: batch positive count (left zeroed)
 };
 
 // exclusive prefix sum over the MN_T threads of the CTA; *total receives the block sum
@@ -399,7 +411,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 constexpr int MN_GC = 64;        // gt boxes staged in shared memory
 constexpr int MN_CAND = 512;     // boundary-bin candidates ranked directly (one per thread)
 
-template <int C, bool GRADS>
+template <int C, bool GRADS, bool FIN>
 __global__ void __launch_bounds__(MN_T)
 mine_kernel(const MineParams p)
 {
@@ -428,12 +440,58 @@ mine_kernel(const MineParams p)
     // ---- 1. keys: CE bits for negatives, 0 for positives (Losses.py:188-190); class bytes; gts ----
     if (t == 0) { s_nsel = 0u; s_ncand = 0u; s_max = 0u; }
     if (t < min(G, MN_GC)) {
-        const float4 bx = p.gt_xyxy[off0 + t];
+        const float4 bx = p.gt_xyxy[off0 + t];               // inputs of the step: may be read before the wait
         s_gbox[t] = bx;
         s_garea[t] = box_area(bx);
-        s_gbp[t] = p.best_prior[off0 + t];
     }
-    __syncthreads();
+    pdl_trigger();
+    pdl_wait();                                              // CE, class bytes, best priors, positive counts are ready
+    int npos_b;
+    if (FIN) {
+        // ---- 0. forced-match override of THIS image (Losses.py:164-167), fused here so that no separate finaliser
+        // kernel sits between the streaming kernel and this one.  The batch-global positive count, which only the
+        // gradient scale needs, is exchanged through a counter the CTAs of this (cooperative) grid wait on later.
+        __shared__ int s_fin_extra, s_fin_npos;
+        const int acc0 = ld_cg_s32(&p.npos_acc[b]);
+        if (t == 0) s_fin_extra = 0;
+        for (int g = t; g < G; g += MN_T) {
+            const int bp = (int)(0xffffffffu - (uint32_t)(ld_cg_u64(&p.best_key[off0 + g]) & 0xffffffffull));
+            p.best_key[off0 + g] = 0ull;                     // leave the workspace zeroed
+            p.best_prior_w[off0 + g] = bp;
+            if (g < MN_GC) s_gbp[g] = bp;
+        }
+        __syncthreads();
+        int extra = 0;
+        for (int g = t; g < G; g += MN_T) {
+            const int bp = g < MN_GC ? s_gbp[g] : p.best_prior_w[off0 + g];
+            bool winner = true;                              // T3: the highest gt index keeps the prior
+            for (int g2 = g + 1; g2 < G; ++g2) winner = winner && ((g2 < MN_GC ? s_gbp[g2] : p.best_prior_w[off0 + g2]) != bp);
+            if (winner) {
+                const int c_new = (int)p.gt_cls[off0 + g];
+                const int c_nat = (int)p.cls_rw[row0 + bp];
+                extra += (c_new != p.bg_class ? 1 : 0) - (c_nat != p.bg_class ? 1 : 0);
+                p.cls_rw[row0 + bp] = (uint8_t)c_new;        // read back below by this same CTA (after the barrier)
+            }
+        }
+        if (extra) atomicAdd(&s_fin_extra, extra);
+        __syncthreads();
+        if (t == 0) {
+            const int nb = acc0 + s_fin_extra;
+            s_fin_npos = nb;
+            p.npos_w[b] = nb;
+            p.npos_acc[b] = 0;
+            atomicAdd(p.total_acc, nb);
+            __threadfence();
+            atomicAdd(p.arrive, 1u);
+        }
+        __syncthreads();
+        npos_b = s_fin_npos;
+    } else {
+        if (t < min(G, MN_GC)) s_gbp[t] = p.best_prior[off0 + t];
+        __syncthreads();
+        npos_b = p.npos[b];
+    }
+    const int* bprior = FIN ? p.best_prior_w : p.best_prior;
     uint32_t kmax = 0u;
     const bool vec_ok = ((P & 3) == 0) && (((row0 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.ce) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.cls_u8) & 3) == 0);
@@ -475,7 +533,7 @@ mine_kernel(const MineParams p)
     kmax = s_max;
 
     // ---- 2. the k largest keys, ties to the lower prior index (T4): mark them with bit 31 ----
-    const long long kk = (long long)p.neg_ratio * (long long)p.npos[b];
+    const long long kk = (long long)p.neg_ratio * (long long)npos_b;
     const uint32_t k = (uint32_t)min((long long)P, max(0ll, kk));
     bool listed = false;                         // the row list was already built by the fast path
     if (k >= (uint32_t)P) {
@@ -618,7 +676,23 @@ mine_kernel(const MineParams p)
 
     // ---- 4. the selected rows only: conf gradient, and for positives the L1 term + loc gradient ----
     const uint32_t nsel = s_nsel;
-    const float nrm = (float)(*p.npos_norm);
+    int npos_total;
+    if (FIN) {
+        // every CTA of the grid is co-resident (cooperative launch) and published its count long ago (step 0);
+        // the bounded wait can only trip if the launch contract is violated, and then degrades instead of hanging
+        __shared__ int s_total;
+        if (t == 0) {
+            unsigned spins = 0;
+            while (ld_cg_s32(reinterpret_cast<const int*>(p.arrive)) < (int)gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
+            __threadfence();
+            s_total = ld_cg_s32(p.total_acc);
+        }
+        __syncthreads();
+        npos_total = s_total;
+    } else {
+        npos_total = *p.npos_norm;
+    }
+    const float nrm = (float)npos_total;
     const float gs_conf = __fdiv_rn(1.0f, nrm);
     const float gs_loc = __fdiv_rn(1.0f, __fmul_rn(4.0f, nrm));
     for (uint32_t idx = t; idx < nsel; idx += MN_T) {
@@ -665,7 +739,7 @@ mine_kernel(const MineParams p)
             for (int g = 0; g < G; ++g) {
                 float4 gb; float ga; int bp;
                 if (g < MN_GC) { gb = s_gbox[g]; ga = s_garea[g]; bp = s_gbp[g]; }
-                else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = p.best_prior[off0 + g]; }
+                else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = bprior[off0 + g]; }
                 if (bp == j) obj = g;
                 const float v = iou_sparse(gb, ga, pb, pa);
                 if (v > nb) { nb = v; ng = g; }
@@ -719,10 +793,15 @@ mine_kernel(const MineParams p)
             for (int w = 0; w < MN_W; ++w) { a += s_redd[0][w]; c += s_redd[1][w]; }
             p.sums[0] = a;
             p.sums[1] = c;
-            const double N = (double)(*p.npos_norm);
+            const double N = (double)npos_total;
             p.losses[0] = (float)(a / (4.0 * N));
             p.losses[1] = (float)(c / N);
             *p.done_counter = 0u;
+            if (FIN) {                   // every CTA has read the total (it did so before it reported done)
+                p.npos_w[p.B] = npos_total;
+                *p.arrive = 0u;
+                *p.total_acc = 0;
+            }
         }
     }
 }
@@ -785,21 +864,37 @@ static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, floa
     const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(grad_conf) && aligned16(grad_loc)))) ? 1 : 0;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS;
     const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
-    kce<<<grid_ce, CE_THREADS, smem_ce, st>>>(conf, ce, grad_conf, grad_loc, rows, use_tma, fm);
+    SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, conf, ce, grad_conf, grad_loc, rows, use_tma, fm));
     count_launch();
-    SSD_LAUNCH_CHECK();
     return 0;
 }
 
 template <int C, bool GRADS>
 static int launch_mine(const MineParams& prm, cudaStream_t st)
 {
-    auto kmn = mine_kernel<C, GRADS>;
+    auto kmn = mine_kernel<C, GRADS, false>;
     const size_t smem_mn = mine_smem_bytes(prm.P);
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
-    kmn<<<prm.B, MN_T, smem_mn, st>>>(prm);
+    SSD_CHECK_CUDA(launch_pdl(4, kmn, dim3(prm.B), dim3(MN_T), smem_mn, st, prm));
     count_launch();
-    SSD_LAUNCH_CHECK();
+    return 0;
+}
+
+// mine_kernel with the forced-match finaliser fused in needs every CTA co-resident (they exchange the batch positive
+// count through a counter): cooperative launch; returns 1 (not an error) when the grid does not fit, so the caller
+// falls back to match_finalize_kernel + the ordinary mining kernel.
+template <int C, bool GRADS>
+static int launch_mine_fin(MineParams prm, cudaStream_t st)
+{
+    auto kmn = mine_kernel<C, GRADS, true>;
+    const size_t smem_mn = mine_smem_bytes(prm.P);
+    SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
+    int per_sm = 0;
+    SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmn, MN_T, smem_mn));
+    if ((long long)per_sm * num_sms() < prm.B) return 1;
+    void* args[] = {&prm};
+    SSD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kmn, dim3(prm.B), dim3(MN_T), args, smem_mn, st));
+    count_launch();
     return 0;
 }
 
@@ -831,11 +926,12 @@ int ssdhead_ce_stream(const float* conf, int B, int P, int C, float* ce, float* 
 
 // ssdhead_ce_stream with the natural match fused in, followed by the per-image forced-match finaliser: produces
 // everything ssdhead_match produces for the loss (cls_u8, best_prior, npos) without a separate pass over the priors.
-int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+static int ce_match_stream_impl(const float* conf, const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
                             const float* pri_xyxy, int B, int P, int C, int sumG, float pos_iou,
                             float* ce, float* grad_loc, float* grad_conf,
                             uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
-                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
+                            bool run_finalizer)
 {
     if (B < 0 || P <= 0 || sumG < 0 || !conf || !gt_off || !pri_xyxy || !cls_u8 || !npos || !ws_loss || !ws_match) return SSDHEAD_E_BADARG;
     if (sumG > 0 && (!gt_xyxy || !gt_cls || !best_prior)) return SSDHEAD_E_BADARG;
@@ -865,10 +961,21 @@ int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float
     const int rc = grad_loc ? launch_ce_stream<21, true, true>(conf, ce_buf, grad_conf, grad_loc, rows, fm, st)
                             : launch_ce_stream<21, false, true>(conf, ce_buf, nullptr, nullptr, rows, fm, st);
     if (rc) return rc;
-    match_finalize_kernel<<<B, 64, 0, st>>>(gt_cls, gt_off, B, P, C - 1, best_prior, npos, cls_u8, best_key, npos_acc, image_counter);
+    if (!run_finalizer) return 0;
+    SSD_CHECK_CUDA(launch_pdl(2, match_finalize_kernel, dim3(B), dim3(64), 0, st, gt_cls, gt_off, B, P, C - 1, best_prior, npos, cls_u8,
+                              best_key, npos_acc, image_counter));
     count_launch();
-    SSD_LAUNCH_CHECK();
     return 0;
+}
+
+int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                            const float* pri_xyxy, int B, int P, int C, int sumG, float pos_iou,
+                            float* ce, float* grad_loc, float* grad_conf,
+                            uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    return ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce, grad_loc, grad_conf,
+                                cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, true);
 }
 
 int ssdhead_mine(const float* loc, const float* conf,
@@ -906,7 +1013,58 @@ int ssdhead_mine(const float* loc, const float* conf,
     prm.partials = (double*)((char*)ws + 16);
     prm.ce = ce ? ce : ws_ce(ws, B);
     prm.ce_tap = ce;
+    prm.cls_rw = nullptr; prm.best_prior_w = nullptr; prm.npos_w = nullptr; prm.best_key = nullptr; prm.npos_acc = nullptr;
+    prm.arrive = nullptr; prm.total_acc = nullptr;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
+    return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
+}
+
+// The whole training-head step of ONE GPU in two kernels: the streaming CE kernel with the fused natural match,
+// then the mining kernel with the forced-match finaliser fused in (cooperative launch).  When the batch does not fit
+// co-resident (B > 2 CTAs x SMs) it falls back to ssdhead_ce_match_stream + ssdhead_mine (three kernels).
+int ssdhead_multibox_step(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                          uint32_t* mined_mask, float* ce,
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    if (!loc || !pri_cxcywh || !sums || !losses || neg_ratio < 0) return SSDHEAD_E_BADARG;
+    if (!aligned16(loc) || !aligned16(pri_cxcywh)) return SSDHEAD_E_ALIGN;
+    int rc = ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce, grad_loc, grad_conf,
+                                  cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, false);
+    if (rc || B == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)ws_match;
+    unsigned long long* best_key = (unsigned long long*)w;            w += round_up((size_t)sumG * 8, 16);
+    w += round_up((size_t)B * 4, 16);
+    int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
+    unsigned int* image_counter = (unsigned int*)w;
+
+    MineParams prm;
+    prm.loc = loc; prm.conf = conf; prm.cls_u8 = cls_u8;
+    prm.gt_xyxy = (const float4*)gt_xyxy; prm.gt_cls = gt_cls; prm.gt_off = gt_off;
+    prm.pri_xyxy = (const float4*)pri_xyxy; prm.pri_cxcywh = (const float4*)pri_cxcywh;
+    prm.best_prior = best_prior; prm.npos = npos; prm.npos_norm = npos + B;
+    prm.B = B; prm.P = P; prm.neg_ratio = neg_ratio; prm.bg_class = C - 1; prm.pos_iou = pos_iou;
+    prm.sums = sums; prm.losses = losses; prm.grad_loc = grad_loc; prm.grad_conf = grad_conf;
+    prm.mined_mask = mined_mask;
+    prm.done_counter = (unsigned int*)ws_loss;
+    prm.partials = (double*)((char*)ws_loss + 16);
+    prm.ce = ce ? ce : ws_ce(ws_loss, B);
+    prm.ce_tap = ce;
+    prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
+    prm.best_key = best_key; prm.npos_acc = npos_acc;
+    prm.arrive = image_counter + 1; prm.total_acc = (int*)(image_counter + 2);
+    if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
+    rc = grad_loc ? launch_mine_fin<21, true>(prm, st) : launch_mine_fin<21, false>(prm, st);
+    if (rc != 1) return rc;
+    // does not fit co-resident: separate finaliser, ordinary mining kernel
+    SSD_CHECK_CUDA(launch_pdl(2, match_finalize_kernel, dim3(B), dim3(64), 0, st, gt_cls, gt_off, B, P, C - 1, best_prior, npos, cls_u8,
+                              best_key, npos_acc, image_counter));
+    count_launch();
     return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
 }
 

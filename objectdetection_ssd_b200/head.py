@@ -143,9 +143,22 @@ class MultiboxHead:
         ws = self._workspace(_lib.WS_LOSS, B, 0)
         cur = torch.cuda.current_stream(self.dev)
         m = match
+        if m is None and group is None:
+            # hot path, one GPU: two kernels (streaming CE + fused natural match; mining + fused forced-match finaliser)
+            m = self._match_outputs(gt, False)
+            wm = self._workspace(_lib.WS_MATCH, B, gt.sumG)
+            _lib.check(self.lib.ssdhead_multibox_step(
+                _ptr(loc), _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off),
+                _ptr(self.pri_xyxy), _ptr(self.pri_cxcywh), B, P, C, gt.sumG, int(neg_ratio), float(pos_iou),
+                _ptr(sums), _ptr(losses), _ptr(grad_loc), _ptr(grad_conf),
+                _ptr(m["cls_u8"]), _ptr(m["best_prior"]), _ptr(m["npos"]), _ptr(mined), _ptr(ce),
+                _ptr(ws), ws.numel(), _ptr(wm), wm.numel(), cur.cuda_stream), "ssdhead_multibox_step")
+            npos = m["npos"]
+            return dict(losses=losses, sums=sums, npos=npos, npos_norm=npos[B:B + 1], grad_loc=grad_loc,
+                        grad_conf=grad_conf, mined_mask=mined, ce=ce, best_prior=m["best_prior"], cls_u8=m["cls_u8"])
         if m is None:
-            # hot path: the natural match rides inside the HBM-bound CE streaming kernel (spare issue slots), a small
-            # finaliser applies the forced-match override; no separate pass over the priors
+            # sharded batch: the natural match rides inside the CE streaming kernel, a small finaliser applies the
+            # forced-match override; the positive count is all-reduced before the mining kernel
             m = self._match_outputs(gt, False)
             wm = self._workspace(_lib.WS_MATCH, B, gt.sumG)
             _lib.check(self.lib.ssdhead_ce_match_stream(
