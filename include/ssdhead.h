@@ -127,14 +127,17 @@ int ssdhead_ce_stream(const float* conf_dev, int B, int P, int C, float* ce_dev,
  * p of image b also finds the best gt of that prior and feeds the per-gt arg-max over priors; a small finaliser
  * kernel then applies the forced-match override.  Produces cls_u8 / best_prior / npos exactly as ssdhead_match does
  * (same IoU code, same tie rules), so no separate pass over the priors is needed.  `ws_match` is a
- * SSDHEAD_WS_MATCH workspace (zero-filled once; left zeroed).  B*P < 2^31. */
+ * SSDHEAD_WS_MATCH workspace (zero-filled once; left zeroed).  B*P < 2^31.
+ * run_finalizer: 1 = complete (streaming kernel + finaliser kernel).  0 = streaming kernel only: cls_u8 then holds
+ * the NATURAL classes and the workspace the un-finalised arg-max keys - the state ssdhead_multibox_step's fused
+ * mining kernel (or a profiler timing the dominant kernel alone, on a scratch workspace) continues from. */
 int ssdhead_ce_match_stream(const float* conf_dev, const float* gt_xyxy_dev, const float* gt_cls_dev,
                             const int32_t* gt_off_dev, const float* pri_xyxy_dev,
                             int B, int P, int C, int sumG, float pos_iou,
                             float* ce_dev, float* grad_loc_dev, float* grad_conf_dev,
                             uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
                             void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
-                            void* stream);
+                            int run_finalizer, void* stream);
 /* The whole training-head step of ONE GPU in two kernels: ssdhead_ce_match_stream's streaming kernel, then the
  * mining kernel with the forced-match finaliser fused in (cooperative launch: its CTAs exchange the batch positive
  * count through a counter they wait on, so all B CTAs must be co-resident).  Falls back by itself to the

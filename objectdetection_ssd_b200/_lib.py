@@ -35,7 +35,7 @@ SIGNATURES = {
                                    _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_ce_stream": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_ce_match_stream": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _sz, _vp, _sz, _vp]),
+                                     _vp, _sz, _vp, _sz, _i, _vp]),
     "ssdhead_multibox_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "ssdhead_mine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -173,7 +173,7 @@ int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
     // the natural match rides inside the CE streaming kernel; a small finaliser applies the forced-match override
     const int rc = ssdhead_ce_match_stream(conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
                                            nullptr, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
-                                           c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, st);
+                                           c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, 1, st);
     if (rc) return rc;
     if (npos_total_dev) *npos_total_dev = c->npos + B;
     return 0;

@@ -972,10 +972,12 @@ int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float
                             const float* pri_xyxy, int B, int P, int C, int sumG, float pos_iou,
                             float* ce, float* grad_loc, float* grad_conf,
                             uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
-                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+                            void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes,
+                            int run_finalizer, void* stream)
 {
     return ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce, grad_loc, grad_conf,
-                                cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, true);
+                                cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream,
+                                run_finalizer != 0);
 }
 
 int ssdhead_mine(const float* loc, const float* conf,

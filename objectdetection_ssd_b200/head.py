@@ -165,7 +165,7 @@ class MultiboxHead:
                 _ptr(conf), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off), _ptr(self.pri_xyxy),
                 B, P, C, gt.sumG, float(pos_iou), _ptr(ce), _ptr(grad_loc), _ptr(grad_conf),
                 _ptr(m["cls_u8"]), _ptr(m["best_prior"]), _ptr(m["npos"]),
-                _ptr(ws), ws.numel(), _ptr(wm), wm.numel(), cur.cuda_stream), "ssdhead_ce_match_stream")
+                _ptr(ws), ws.numel(), _ptr(wm), wm.numel(), 1, cur.cuda_stream), "ssdhead_ce_match_stream")
         else:
             # a match computed beforehand with ssdhead_match (e.g. with the debug taps)
             _lib.check(self.lib.ssdhead_ce_stream(
