@@ -393,6 +393,7 @@ detect_topk_kernel(const float4* __restrict__ boxes, const unsigned long long* _
     __shared__ int s_pref[33];
     __shared__ int s_m[33];
     __shared__ unsigned int s_tlow;
+    __shared__ int s_all_r;
     const int b = blockIdx.x, t = threadIdx.x;
     if (t < NF) s_m[t] = (int)kept_cnt[(size_t)b * NF + t];
     __syncthreads();
@@ -435,9 +436,23 @@ detect_topk_kernel(const float4* __restrict__ boxes, const unsigned long long* _
         // boxes of a class can qualify, and nothing scoring below the top_k-th score of any single class can either:
         // T_low = max over classes of that score prunes the merge to a few hundred keys.
         nout = top_k;
+        // two lower bounds on the top_k-th score of the union: (a) the top_k-th score of any single class;
+        // (b) with r = ceil(top_k / NF): if every class kept at least r boxes, the NF*r >= top_k boxes formed by the
+        //     top r of each class all score >= the smallest r-th score, so the top_k-th score of the union does too.
+        const int r = (top_k + NF - 1) / NF;
+        if (t == 0) s_all_r = 1;
+        __syncthreads();
+        unsigned rth = 0xffffffffu;
         if (t < NF) {
             const int kc = s_pref[t + 1] - s_pref[t];
-            if (kc >= top_k) atomicMax(&s_tlow, (unsigned)(cand[((size_t)b * NF + t) * capp + top_k - 1] >> 32));
+            const unsigned long long* seg = cand + ((size_t)b * NF + t) * capp;
+            if (kc >= top_k) atomicMax(&s_tlow, (unsigned)(seg[top_k - 1] >> 32));
+            if (kc >= r) rth = (unsigned)(seg[r - 1] >> 32); else s_all_r = 0;
+        }
+        if (t < 32) {
+            rth = __reduce_min_sync(FULL, rth);
+            __syncwarp();
+            if (t == 0 && s_all_r) atomicMax(&s_tlow, rth);
         }
         __syncthreads();
         const unsigned tlow = s_tlow;
