@@ -293,3 +293,51 @@ def test_mining_stage_isolated_is_bit_exact():
         torch.cuda.synchronize()
         assert torch.equal(H.unpack_mask(mined, P), ref["mined"]), f"seed {seed}: mined set differs from the oracle"
         assert abs(losses[1].item() - ref["conf_loss"].item()) <= 1e-6 * ref["conf_loss"].item()
+
+
+@pytest.mark.parametrize("counts", [(150, 3, 70), (129, 1), (65, 64, 33)])
+def test_many_gt_per_image_slow_paths(counts):
+    """Images with more gts than the shared-memory staging capacities (64 / 128) and the 32-gt shuffle chunks:
+    exercises the multi-chunk paths of match_kernel, the fused match, the finaliser(s) and mine_kernel."""
+    from objectdetection_ssd_b200 import synth
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    pri = H.priors()
+    P = pri.shape[0]
+    tb, tc = [], []
+    for i, n in enumerate(counts):
+        gb, gc = synth.make_gt(90 + i, 1, n, n)
+        tb.append(torch.from_numpy(gb[0]))
+        tc.append(torch.from_numpy(gc[0]))
+    B = len(counts)
+    loc, conf = synth.make_head(91, B, P)
+    loc, conf = torch.from_numpy(loc), torch.from_numpy(conf)
+    _check_match(_head(pri), pri, tb, tc)                              # standalone match kernel
+    out, ref = _check_loss(pri, loc, conf, tb, tc)                     # two-kernel step (fused match + fused finaliser)
+    assert torch.equal(out["cls_u8"].cpu().long(), ref["cls"])
+    assert torch.equal(out["best_prior"][:sum(counts)].cpu().long(), ref["best_prior"])
+    # three-kernel route (what a sharded batch uses): ce_match_stream + finaliser kernel + plain mining kernel
+    from objectdetection_ssd_b200 import _lib
+    head = MultiboxHead(pri, "cuda")
+    gt = PackedGT(tb, tc, head.dev)
+    lib = _lib.load()
+    m = head._match_outputs(gt, False)
+    ws = head._workspace(_lib.WS_LOSS, B, 0)
+    wm = head._workspace(_lib.WS_MATCH, B, gt.sumG)
+    st = torch.cuda.current_stream().cuda_stream
+    l, c = loc.cuda(), conf.cuda()
+    gl, gcf = torch.empty_like(l), torch.empty_like(c)
+    sums = torch.empty(2, dtype=torch.float64, device="cuda")
+    losses = torch.empty(2, device="cuda")
+    _lib.check(lib.ssdhead_ce_match_stream(c.data_ptr(), gt.boxes.data_ptr(), gt.classes.data_ptr(), gt.off.data_ptr(),
+                                           head.pri_xyxy.data_ptr(), B, P, 21, gt.sumG, 0.5, None, gl.data_ptr(), gcf.data_ptr(),
+                                           m["cls_u8"].data_ptr(), m["best_prior"].data_ptr(), m["npos"].data_ptr(),
+                                           ws.data_ptr(), ws.numel(), wm.data_ptr(), wm.numel(), 1, st), "ce_match_stream")
+    _lib.check(lib.ssdhead_mine(l.data_ptr(), c.data_ptr(), gt.boxes.data_ptr(), gt.classes.data_ptr(), gt.off.data_ptr(),
+                                head.pri_xyxy.data_ptr(), head.pri_cxcywh.data_ptr(), m["best_prior"].data_ptr(),
+                                m["npos"].data_ptr(), m["npos"][B:].data_ptr(), m["cls_u8"].data_ptr(), B, P, 21, 3, 0.5,
+                                sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), None, None,
+                                ws.data_ptr(), ws.numel(), st), "mine")
+    torch.cuda.synchronize()
+    assert torch.equal(m["cls_u8"], out["cls_u8"]) and torch.equal(m["npos"], out["npos"])
+    assert torch.equal(gcf, out["grad_conf"]) and torch.equal(gl, out["grad_loc"])
+    assert torch.equal(losses, out["losses"])
