@@ -198,7 +198,10 @@ def workload_config(args, world):
         return {"workload": "SSD300-VGG16 VOC head, 8732 priors, 21 classes: match + hard-negative-mined CE + L1 loss, "
                             "forward and gradients (north_star target size: batch 256 per GPU)",
                 "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_priors": 8732, "num_classes": 21,
-                "gt_per_image": "U{1..10}", "parallelism": f"image-sharded x{world}, NCCL all-reduce of Npos and loss sums",
+                "gt_per_image": "U{1..10}", "parallelism": (f"image-sharded x{world}; Npos and the loss sums cross GPUs "
+                                + ("through NVLink peer-memory stores inside the mining kernel (--collective peer)"
+                                   if getattr(args, "collective", "peer") == "peer" else "through two NCCL all-reduces (--collective nccl)")
+                                if world > 1 else "single GPU"),
                 "l2": "inputs rotate through >= 2 x 126 MB of distinct device buffers (larger than L2)"}
     return {"workload": "SSD300 inference post-processing: decode + conf 0.01 threshold + per-class NMS (iou 0.45) + "
                         "global top-200; background-logit bias +6 (~1.1k candidates/class)",
@@ -254,12 +257,21 @@ def time_train(args, rank, world, dev, sampler):
     st = stream.cuda_stream
     sumG = int(off[-1])
     npos_norm = torch.zeros(1, dtype=torch.int32, device=dev)
+    collective = "none"
     if world > 1:
         import torch.distributed as dist
+        collective = args.collective
+        if collective == "peer":
+            # one-off: exchange the CUDA IPC handles of the ranks' exchange buffers; afterwards the step is the same
+            # two kernels as on one GPU, the mining kernel trading Npos and the loss sums with its peers over NVLink
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.xchg_export())
+            ctx.xchg_import(handles, rank)
+            dist.barrier()
 
     def step(i):
         l, c = sets[i % nset]
-        if world == 1:
+        if world == 1 or collective == "peer":
             ctx.loss_dev(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
                          sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
         else:
@@ -287,6 +299,8 @@ def time_train(args, rank, world, dev, sampler):
     launches = _lib.launch_count() - n0
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     loss_val = losses.tolist()
+    if collective == "peer" and ctx.xchg_error():
+        raise SystemExit("bench.py: a wait for a peer rank expired inside the sharded step (results invalid)")
 
     # ---- the dominant kernel alone, CUDA events on its launch stream: the streaming CE kernel with the fused natural
     # match (ssdhead_ce_match_stream with run_finalizer = 0, on a scratch match workspace) ----
@@ -335,7 +349,7 @@ def time_train(args, rank, world, dev, sampler):
     ctx.close()
     return dict(ms_total=ms, launches=launches, kern_ms=kern_ms, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, losses=loss_val,
                 kernel="ce_stream_kernel<21,true,true>", kernel_bytes=CE_STREAM_BYTES * B, algo=ALGO_BYTES["train"],
-                e2e_steps=en)
+                e2e_steps=en, collective=collective)
 
 
 def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
@@ -490,6 +504,10 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "detect"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 256 train, 64 detect)")
     ap.add_argument("--no-others", action="store_true", help="skip the short secondary-configuration runs")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how Npos and the loss sums cross GPUs - 'peer' = stores into peer memory over NVLink "
+                         "from inside the mining kernel (2 kernels/step, no NCCL call), 'nccl' = two NCCL all-reduces "
+                         "around the mining kernel (3 kernels/step)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 256 if args.workload == "train" else 64

@@ -153,6 +153,24 @@ int ssdhead_multibox_step(const float* loc_dev, const float* conf_dev,
                           uint32_t* mined_mask_dev, float* ce_dev,
                           void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
                           void* stream);
+/* ssdhead_multibox_step for a batch SHARDED BY IMAGE over R GPUs (one process per GPU): the same two kernels; the
+ * mining kernel exchanges the positive count (before it scales any gradient) and the two loss sums with its peers by
+ * storing into their exchange buffers over NVLink peer memory - no NCCL call and no extra kernel in the step.
+ * `peers_dev`: device table of R pointers to the ranks' exchange buffers (ssdhead_xchg_bytes() each, zero-filled
+ * once, mapped into this process with cudaIpcOpenMemHandle; entry `rank` is xchg_local_dev).  `seq` >= 1 is a step
+ * counter every rank advances in lock step.  sums/losses come back GLOBAL, npos[B] is this rank's own count,
+ * *err_flag_dev is set if a (10 s bounded) wait for a peer expired.  B must fit co-resident (else E_UNSUPPORTED:
+ * use ssdhead_ce_match_stream + an all-reduce + ssdhead_mine). */
+int ssdhead_multibox_step_sharded(const float* loc_dev, const float* conf_dev,
+                          const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                          const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                          uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                          void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                          int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev,
+                          int32_t* err_flag_dev, void* stream);
+size_t ssdhead_xchg_bytes(void);
 int ssdhead_mine(const float* loc_dev, const float* conf_dev,
                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                  const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
@@ -244,6 +262,13 @@ int ssdhead_ctx_multibox_loss_end(ssdhead_ctx* ctx, const float* loc_dev, const 
                                   int B, int neg_ratio, float pos_iou, const int32_t* npos_norm_dev,
                                   double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
                                   void* stream);
+/* Sharded batches without NCCL: every rank exports the IPC handle of its exchange buffer (64 bytes), the handles are
+ * gathered by the caller (e.g. torch.distributed.all_gather_object) and imported; from then on
+ * ssdhead_ctx_multibox_loss_dev runs ssdhead_multibox_step_sharded and returns GLOBAL losses.  All ranks must call it
+ * in lock step.  ssdhead_ctx_xchg_error returns 1 if a wait for a peer ever expired. */
+int ssdhead_ctx_xchg_export(ssdhead_ctx* ctx, void* handle64_out);
+int ssdhead_ctx_xchg_import(ssdhead_ctx* ctx, const void* handles /*[R][64]*/, int R, int rank);
+int ssdhead_ctx_xchg_error(ssdhead_ctx* ctx);
 /* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair.
  * Copies, kernels and copies back are pipelined in image chunks on the context's streams; pass
  * page-locked buffers (ssdhead_host_alloc) so the copies are asynchronous.  Blocks until done. */

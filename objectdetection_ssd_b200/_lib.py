@@ -38,6 +38,12 @@ SIGNATURES = {
                                      _vp, _sz, _vp, _sz, _i, _vp]),
     "ssdhead_multibox_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "ssdhead_multibox_step_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
+    "ssdhead_xchg_bytes": (_sz, []),
+    "ssdhead_ctx_xchg_export": (_i, [_vp, _vp]),
+    "ssdhead_ctx_xchg_import": (_i, [_vp, _vp, _i, _i]),
+    "ssdhead_ctx_xchg_error": (_i, [_vp]),
     "ssdhead_mine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                           _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_finish_loss": (_i, [_vp, _vp, _vp, _vp]),

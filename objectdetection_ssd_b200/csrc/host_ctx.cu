@@ -34,6 +34,13 @@ __global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nch
 
 struct ssdhead_ctx {
     int device, maxB, P, C, max_sumG, top_k, last_detect_B;
+    // cross-GPU exchange (sharded batches)
+    int xchg_R, xchg_rank;
+    unsigned int xchg_seq;
+    void* xchg_local;
+    void** xchg_peers_dev;
+    void* xchg_opened[16];
+    int* err_flag;
     cudaStream_t s_main, s_aux, s_h2d, s_d2h;
     cudaEvent_t ev_fork, ev_join, ev_gt, ev_done;
     std::vector<cudaEvent_t> ev_in, ev_out;            // per chunk
@@ -80,6 +87,10 @@ void ssdhead_ctx_destroy(ssdhead_ctx* c)
                     c->ws_match, c->ws_loss, c->ws_detect, c->det_boxes, c->det_prob, c->det_cls, c->det_prior, c->det_cnt};
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->h_losses) cudaFreeHost(c->h_losses);
+    for (int q = 0; q < 16; ++q) if (c->xchg_opened[q]) cudaIpcCloseMemHandle(c->xchg_opened[q]);
+    if (c->xchg_local) cudaFree(c->xchg_local);
+    if (c->xchg_peers_dev) cudaFree(c->xchg_peers_dev);
+    if (c->err_flag) cudaFree(c->err_flag);
     cudaStream_t st[] = {c->s_main, c->s_aux, c->s_h2d, c->s_d2h};
     for (cudaStream_t s : st) if (s) cudaStreamDestroy(s);
     cudaEvent_t ev[] = {c->ev_fork, c->ev_join, c->ev_gt, c->ev_done};
@@ -152,6 +163,12 @@ int ssdhead_ctx_create(ssdhead_ctx** out, int device, int maxB, int P, int C, in
         CTX_CUDA(cudaMalloc(&c->det_prior, (size_t)maxB * top_k * 4));
         CTX_CUDA(cudaMalloc(&c->det_cnt, (size_t)maxB * 4));
         CTX_CUDA(cudaHostAlloc(&c->h_losses, 64, cudaHostAllocDefault));
+        CTX_CUDA(cudaMalloc(&c->xchg_local, ssdhead_xchg_bytes()));
+        CTX_CUDA(cudaMemset(c->xchg_local, 0, ssdhead_xchg_bytes()));
+        CTX_CUDA(cudaMalloc(&c->xchg_peers_dev, 16 * sizeof(void*)));
+        CTX_CUDA(cudaMalloc(&c->err_flag, sizeof(int)));
+        CTX_CUDA(cudaMemset(c->err_flag, 0, sizeof(int)));
+        c->xchg_R = 1;
     }
     *out = c;
     return 0;
@@ -202,9 +219,50 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
 {
     if (!c) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    if (c->xchg_R > 1)
+        return ssdhead_multibox_step_sharded(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
+                                             neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
+                                             c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes,
+                                             c->xchg_R, c->xchg_rank, ++c->xchg_seq, c->xchg_peers_dev, c->xchg_local, c->err_flag, stream);
     return ssdhead_multibox_step(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
                                  neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
                                  nullptr, nullptr, c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, stream);
+}
+
+int ssdhead_ctx_xchg_export(ssdhead_ctx* c, void* handle64_out)
+{
+    if (!c || !handle64_out) return SSDHEAD_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SSD_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    SSD_CHECK_CUDA(cudaIpcGetMemHandle(&h, c->xchg_local));
+    std::memcpy(handle64_out, &h, 64);
+    return 0;
+}
+
+int ssdhead_ctx_xchg_import(ssdhead_ctx* c, const void* handles, int R, int rank)
+{
+    if (!c || !handles || R < 1 || R > 16 || rank < 0 || rank >= R) return SSDHEAD_E_BADARG;
+    SSD_CHECK_CUDA(cudaSetDevice(c->device));
+    void* table[16] = {};
+    for (int q = 0; q < R; ++q) {
+        if (q == rank) { table[q] = c->xchg_local; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 64 * q, 64);
+        SSD_CHECK_CUDA(cudaIpcOpenMemHandle(&table[q], h, cudaIpcMemLazyEnablePeerAccess));
+        c->xchg_opened[q] = table[q];
+    }
+    SSD_CHECK_CUDA(cudaMemcpy(c->xchg_peers_dev, table, sizeof(table), cudaMemcpyHostToDevice));
+    c->xchg_R = R; c->xchg_rank = rank; c->xchg_seq = 0;
+    return 0;
+}
+
+int ssdhead_ctx_xchg_error(ssdhead_ctx* c)
+{
+    if (!c) return SSDHEAD_E_BADARG;
+    int e = 0;
+    if (cudaMemcpy(&e, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return e;
 }
 
 // ssd() on HOST buffers (pass page-locked memory, e.g. ssdhead_host_alloc, for asynchronous copies).

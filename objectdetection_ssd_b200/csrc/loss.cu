@@ -386,7 +386,18 @@ struct MineParams {
     int* npos_acc;                  //                  natural positives per image (left zeroed)
     unsigned int* arrive;           // workspace word: CTAs that published their count (left zeroed)
     int* total_acc;                 // workspace word: batch positive count (left zeroed)
+    // cross-GPU exchange of the positive count and the loss sums over NVLink peer memory (xchg_R > 1):
+    // every rank owns an exchange buffer of XCHG_WORDS 64-bit words that its PEERS write into (and it spins on).
+    int xchg_R, xchg_rank;
+    unsigned int xchg_seq;          // step sequence number (>= 1); slots are double-buffered by its parity
+    unsigned long long* const* xchg_peers;   // [R] device table: peer-mapped exchange buffers, indexed by rank
+    unsigned long long* xchg_local;          // this rank's buffer
+    int* err_flag;                  // set to 1 if a bounded wait expired
 };
+
+constexpr int XCHG_MAX_R = 16;
+constexpr int XCHG_WORDS = 2 * 4 * XCHG_MAX_R;     // parity x {npos, sum_l1, sum_ce, sums_flag} x rank
+__device__ __forceinline__ int xchg_slot(unsigned seq, int what, int rank) { return ((int)(seq & 1u) * 4 + what) * XCHG_MAX_R + rank; }
 
 // exclusive prefix sum over the MN_T threads of the CTA; *total receives the block sum
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[MN_W+1]*/, uint32_t* total)
@@ -482,7 +493,14 @@ mine_kernel(const MineParams p)
             p.npos_acc[b] = 0;
             atomicAdd(p.total_acc, nb);
             __threadfence();
-            atomicAdd(p.arrive, 1u);
+            const unsigned arrived = atomicAdd(p.arrive, 1u);
+            if (p.xchg_R > 1 && arrived == gridDim.x - 1u) {
+                // last image of this GPU: its positive count is complete -> one 64-bit store (seq << 32 | count) into
+                // the exchange buffer of every rank (own included) over NVLink
+                __threadfence();
+                const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)ld_cg_s32(p.total_acc);
+                for (int q = 0; q < p.xchg_R; ++q) st_release_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
+            }
         }
         __syncthreads();
         npos_b = s_fin_npos;
@@ -683,9 +701,22 @@ mine_kernel(const MineParams p)
         __shared__ int s_total;
         if (t == 0) {
             unsigned spins = 0;
-            while (ld_cg_s32(reinterpret_cast<const int*>(p.arrive)) < (int)gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
-            __threadfence();
-            s_total = ld_cg_s32(p.total_acc);
+            if (p.xchg_R > 1) {
+                // sharded batch: the counts of all ranks, written into MY exchange buffer by their last CTAs
+                int tot = 0;
+                for (int q = 0; q < p.xchg_R; ++q) {
+                    unsigned long long w;
+                    while ((unsigned)((w = ld_acquire_sys_u64(p.xchg_local + xchg_slot(p.xchg_seq, 0, q))) >> 32) != p.xchg_seq &&
+                           ++spins < (1u << 27)) __nanosleep(64);
+                    tot += (int)(unsigned)w;
+                }
+                if (spins >= (1u << 27)) *p.err_flag = 1;
+                s_total = tot;
+            } else {
+                while (ld_cg_s32(reinterpret_cast<const int*>(p.arrive)) < (int)gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
+                __threadfence();
+                s_total = ld_cg_s32(p.total_acc);
+            }
         }
         __syncthreads();
         npos_total = s_total;
@@ -791,6 +822,24 @@ mine_kernel(const MineParams p)
         if (t == 0) {
             a = 0.0; c = 0.0;
             for (int w = 0; w < MN_W; ++w) { a += s_redd[0][w]; c += s_redd[1][w]; }
+            if (FIN && p.xchg_R > 1) {
+                // all-reduce of the two loss sums through the same peer buffers: values first, then the flag; the
+                // global sums are accumulated in rank order on every rank -> identical bits everywhere
+                for (int q = 0; q < p.xchg_R; ++q) {
+                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 1, p.xchg_rank), (unsigned long long)__double_as_longlong(a));
+                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 2, p.xchg_rank), (unsigned long long)__double_as_longlong(c));
+                }
+                __threadfence_system();
+                for (int q = 0; q < p.xchg_R; ++q) st_release_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 3, p.xchg_rank), (unsigned long long)p.xchg_seq);
+                unsigned spins = 0;
+                a = 0.0; c = 0.0;
+                for (int q = 0; q < p.xchg_R; ++q) {
+                    while ((unsigned)ld_acquire_sys_u64(p.xchg_local + xchg_slot(p.xchg_seq, 3, q)) != p.xchg_seq && ++spins < (1u << 27)) __nanosleep(64);
+                    a += __longlong_as_double((long long)ld_relaxed_sys_u64(p.xchg_local + xchg_slot(p.xchg_seq, 1, q)));
+                    c += __longlong_as_double((long long)ld_relaxed_sys_u64(p.xchg_local + xchg_slot(p.xchg_seq, 2, q)));
+                }
+                if (spins >= (1u << 27)) *p.err_flag = 1;
+            }
             p.sums[0] = a;
             p.sums[1] = c;
             const double N = (double)npos_total;
@@ -798,7 +847,7 @@ mine_kernel(const MineParams p)
             p.losses[1] = (float)(c / N);
             *p.done_counter = 0u;
             if (FIN) {                   // every CTA has read the total (it did so before it reported done)
-                p.npos_w[p.B] = npos_total;
+                p.npos_w[p.B] = (p.xchg_R > 1) ? ld_cg_s32(p.total_acc) : npos_total;    // this rank's own count
                 *p.arrive = 0u;
                 *p.total_acc = 0;
             }
@@ -980,6 +1029,54 @@ int ssdhead_ce_match_stream(const float* conf, const float* gt_xyxy, const float
                                 run_finalizer != 0);
 }
 
+static int multibox_step_impl(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                          uint32_t* mined_mask, float* ce,
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
+                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag);
+
+int ssdhead_multibox_step(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                          uint32_t* mined_mask, float* ce,
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    return multibox_step_impl(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, B, P, C, sumG, neg_ratio, pos_iou,
+                              sums, losses, grad_loc, grad_conf, cls_u8, best_prior, npos, mined_mask, ce,
+                              ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, 0, 0, 0u, nullptr, nullptr, nullptr);
+}
+
+// The same two kernels for a batch sharded by image over R GPUs: the mining kernel exchanges the positive count (before
+// it scales any gradient) and the two loss sums with its peers by storing into their exchange buffers over NVLink -
+// no NCCL call, no extra kernel.  `peers_dev` is a device table of R peer-mapped exchange buffers (XCHG words each,
+// zero-filled once), `seq` a step counter starting at 1 that every rank advances in lock step.
+int ssdhead_multibox_step_sharded(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes,
+                          int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev, int32_t* err_flag_dev,
+                          void* stream)
+{
+    if (R < 1 || R > XCHG_MAX_R || rank < 0 || rank >= R || seq == 0u) return SSDHEAD_E_BADARG;
+    if (R > 1 && (!peers_dev || !xchg_local_dev || !err_flag_dev)) return SSDHEAD_E_BADARG;
+    return multibox_step_impl(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, B, P, C, sumG, neg_ratio, pos_iou,
+                              sums, losses, grad_loc, grad_conf, cls_u8, best_prior, npos, nullptr, nullptr,
+                              ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, R, rank, seq, peers_dev, xchg_local_dev,
+                              err_flag_dev);
+}
+
+size_t ssdhead_xchg_bytes(void) { return (size_t)XCHG_WORDS * 8; }
+
 int ssdhead_mine(const float* loc, const float* conf,
                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
                  const float* pri_xyxy, const float* pri_cxcywh,
@@ -1017,6 +1114,7 @@ int ssdhead_mine(const float* loc, const float* conf,
     prm.ce_tap = ce;
     prm.cls_rw = nullptr; prm.best_prior_w = nullptr; prm.npos_w = nullptr; prm.best_key = nullptr; prm.npos_acc = nullptr;
     prm.arrive = nullptr; prm.total_acc = nullptr;
+    prm.xchg_R = 0; prm.xchg_rank = 0; prm.xchg_seq = 0; prm.xchg_peers = nullptr; prm.xchg_local = nullptr; prm.err_flag = nullptr;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
     return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
 }
@@ -1024,14 +1122,15 @@ int ssdhead_mine(const float* loc, const float* conf,
 // The whole training-head step of ONE GPU in two kernels: the streaming CE kernel with the fused natural match,
 // then the mining kernel with the forced-match finaliser fused in (cooperative launch).  When the batch does not fit
 // co-resident (B > 2 CTAs x SMs) it falls back to ssdhead_ce_match_stream + ssdhead_mine (three kernels).
-int ssdhead_multibox_step(const float* loc, const float* conf,
+static int multibox_step_impl(const float* loc, const float* conf,
                           const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
                           const float* pri_xyxy, const float* pri_cxcywh,
                           int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
                           double* sums, float* losses, float* grad_loc, float* grad_conf,
                           uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
                           uint32_t* mined_mask, float* ce,
-                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
+                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag)
 {
     if (!loc || !pri_cxcywh || !sums || !losses || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!aligned16(loc) || !aligned16(pri_cxcywh)) return SSDHEAD_E_ALIGN;
@@ -1060,9 +1159,12 @@ int ssdhead_multibox_step(const float* loc, const float* conf,
     prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
     prm.best_key = best_key; prm.npos_acc = npos_acc;
     prm.arrive = image_counter + 1; prm.total_acc = (int*)(image_counter + 2);
+    prm.xchg_R = R; prm.xchg_rank = rank; prm.xchg_seq = seq;
+    prm.xchg_peers = (unsigned long long* const*)peers_dev; prm.xchg_local = (unsigned long long*)xchg_local; prm.err_flag = err_flag;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
     rc = grad_loc ? launch_mine_fin<21, true>(prm, st) : launch_mine_fin<21, false>(prm, st);
     if (rc != 1) return rc;
+    if (R > 1) return SSDHEAD_E_UNSUPPORTED;       // the peer exchange needs the co-resident grid: use the NCCL route
     // does not fit co-resident: separate finaliser, ordinary mining kernel
     SSD_CHECK_CUDA(launch_pdl(2, match_finalize_kernel, dim3(B), dim3(64), 0, st, gt_cls, gt_off, B, P, C - 1, best_prior, npos, cls_u8,
                               best_key, npos_acc, image_counter));

@@ -107,5 +107,22 @@ class SSDHeadContext:
             self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(neg_ratio), float(pos_iou),
             npos_norm_ptr, sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_end")
 
+    # ------------------------------------------------------------------ sharded batches over NVLink peer memory
+    def xchg_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange buffer (gather them across ranks, then ``xchg_import``)."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.ssdhead_ctx_xchg_export(self._h, buf), "ssdhead_ctx_xchg_export")
+        return buf.raw
+
+    def xchg_import(self, handles, rank: int) -> None:
+        """Map every rank's exchange buffer; afterwards ``loss_dev`` runs the sharded two-kernel step (global
+        normalisation, no NCCL call).  All ranks must then call ``loss_dev`` in lock step."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _lib.check(self.lib.ssdhead_ctx_xchg_import(self._h, blob, len(handles), int(rank)), "ssdhead_ctx_xchg_import")
+
+    def xchg_error(self) -> bool:
+        return bool(self.lib.ssdhead_ctx_xchg_error(self._h))
+
     def finish_loss(self, sums_ptr, npos_norm_ptr, losses_ptr, stream):
         _lib.check(self.lib.ssdhead_finish_loss(sums_ptr, npos_norm_ptr, losses_ptr, stream), "ssdhead_finish_loss")
