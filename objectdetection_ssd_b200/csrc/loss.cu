@@ -499,7 +499,8 @@ mine_kernel(const MineParams p)
                 // the exchange buffer of every rank (own included) over NVLink
                 __threadfence();
                 const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)ld_cg_s32(p.total_acc);
-                for (int q = 0; q < p.xchg_R; ++q) st_release_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
+                for (int q = 0; q < p.xchg_R; ++q)          // the word validates itself (seq in the high half): relaxed, pipelined stores
+                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
             }
         }
         __syncthreads();
@@ -830,7 +831,8 @@ mine_kernel(const MineParams p)
                     st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 2, p.xchg_rank), (unsigned long long)__double_as_longlong(c));
                 }
                 __threadfence_system();
-                for (int q = 0; q < p.xchg_R; ++q) st_release_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 3, p.xchg_rank), (unsigned long long)p.xchg_seq);
+                for (int q = 0; q < p.xchg_R; ++q)          // one system fence above orders all value stores before these flags
+                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 3, p.xchg_rank), (unsigned long long)p.xchg_seq);
                 unsigned spins = 0;
                 a = 0.0; c = 0.0;
                 for (int q = 0; q < p.xchg_R; ++q) {
