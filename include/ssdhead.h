@@ -229,6 +229,20 @@ int ssdhead_detect_from_scores(const float* boxes_cxcywh_dev, const float* probs
                                float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
                                int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* ---- evaluation: get_map(), Util.py:783-885 (VOC 11-point interpolated AP; consumer of the detect output) -------
+ * Detections and ground truth are packed image-major with int32 offsets [num_images+1] (det_off, gt_off).  Per class:
+ * detections ranked by descending score (ties -> lower detection index); walking that order, a detection is a true
+ * positive iff its best-IoU gt of the same image and class (ties -> first gt) has IoU > iou_thr and is unclaimed
+ * (Util.py:855-868); AP = mean over `recall_levels[11]` of the max precision at recall >= level; precision in fp64,
+ * recall = cumTP * float32(1/#gt) as the reference's numpy/torch mix evaluates Util.py:872 (a class without detections
+ * or without gt scores 0).  ap_out: double [num_fg]. */
+size_t ssdhead_voc_ap_workspace_bytes(int N, int M, int num_fg);
+int ssdhead_voc_ap(const float* det_boxes_xyxy_dev, const int32_t* det_cls_dev, const float* det_score_dev,
+                   const int32_t* det_off_dev, int N,
+                   const float* gt_boxes_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev, int M,
+                   int num_images, int num_fg, float iou_thr, const double* recall_levels_dev /*[11]*/,
+                   double* ap_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- host-buffer front end (pinned staging + streams owned by the context) -----------
  * The same path for callers whose tensors live in host memory (what the reference's CPU
  * path sees).  Copies are pipelined against the kernels in image chunks. */

@@ -154,6 +154,46 @@ def map_prior_to_bb(jacc, classes, threshold=0.5):
     return cls.to(dtype=torch.as_tensor(classes).dtype), obj      # classes[obj] keeps the dtype of `classes`
 
 
+def get_map(det_boxes, det_classes, det_scores, gt_boxes, gt_classes):
+    """VOC 11-point interpolated average precision per class (Util.py:783-885), on the GPU.
+
+    Arguments as in the reference: per-image lists of tensors (detections: boxes [n,4], classes [n], scores [n];
+    ground truth: boxes [m,4], classes [m]).  Returns ``{class_id: AP}`` for the 20 foreground classes (numpy
+    float64).  Equal scores rank by the lower detection index (the reference's sort leaves ties open)."""
+    dev = _cuda_device()
+    n_img = len(det_boxes)
+    if n_img == 0 or len(gt_boxes) != n_img:
+        raise ValueError("get_map: detections and ground truth must be per-image lists of the same, non-zero length")
+
+    def pack(lists, width, dtype):
+        parts = [torch.as_tensor(x).reshape(-1, width) if width else torch.as_tensor(x).reshape(-1) for x in lists]
+        off = [0]
+        for p_ in parts:
+            off.append(off[-1] + int(p_.shape[0]))
+        shape = (0, width) if width else (0,)
+        cat = torch.cat(parts) if off[-1] else torch.zeros(shape)
+        return cat.to(device=dev, dtype=dtype).contiguous(), off
+
+    db, doff = pack(det_boxes, 4, torch.float32)
+    dc, _ = pack(det_classes, 0, torch.int32)
+    ds, _ = pack(det_scores, 0, torch.float32)
+    gb, goff = pack(gt_boxes, 4, torch.float32)
+    gc, _ = pack(gt_classes, 0, torch.float32)
+    N, M = doff[-1], goff[-1]
+    d_off = torch.tensor(doff, dtype=torch.int32, device=dev)
+    g_off = torch.tensor(goff, dtype=torch.int32, device=dev)
+    levels = torch.arange(0, 1.1, 0.1).to(device=dev, dtype=torch.float64)      # the float32 values of Util.py:875
+    ap = torch.zeros(20, dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    ws = torch.empty(int(lib.ssdhead_voc_ap_workspace_bytes(N, M, 20)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.ssdhead_voc_ap(db.data_ptr() if N else None, dc.data_ptr() if N else None, ds.data_ptr() if N else None,
+                                  d_off.data_ptr(), N, gb.data_ptr() if M else None, gc.data_ptr() if M else None,
+                                  g_off.data_ptr(), M, n_img, 20, 0.5, levels.data_ptr(), ap.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream(dev)), "ssdhead_voc_ap")
+    out = ap.cpu().numpy()
+    return {c: out[c] for c in range(20)}
+
+
 def subsampling(x, step):
     """Strided sub-sampling used by Model.py for the fc6/fc7 surgery (Util.py:555-560); plain indexing."""
     for d, s in enumerate(step):

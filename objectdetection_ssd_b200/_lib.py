@@ -50,6 +50,8 @@ SIGNATURES = {
     "ssdhead_scale_grads": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "ssdhead_detect": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_detect_from_scores": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_voc_ap_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ssdhead_voc_ap": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_ctx_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp]),
     "ssdhead_ctx_destroy": (None, [_vp]),
     "ssdhead_host_alloc": (_vp, [_sz]),

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libssdhead.so")
-SOURCES = ["api.cu", "match.cu", "loss.cu", "detect.cu", "host_ctx.cu"]
+SOURCES = ["api.cu", "match.cu", "loss.cu", "detect.cu", "evalmap.cu", "host_ctx.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -5,17 +5,19 @@
 //                        one thread per prior does softmax (or takes given probabilities), decodes the box to
 //                        corner form once, and appends (prob, prior) keys to the candidate list of every
 //                        foreground class whose prob >= min_score (one warp-aggregated atomic per class).
-//   detect_nms_kernel    one CTA per (class, image): bitonic sort of the 64-bit keys (prob bits << 32 | ~prior:
-//                        descending prob, ties -> lower prior, T5), then greedy NMS in blocks of 64 sorted
-//                        candidates: a block is first tested against the boxes kept so far (kept boxes live in
-//                        shared memory), then resolved internally with a 64x64 suppression bit mask.  The IoU
-//                        test avoids the division unless the ratio is within 2^-20 of the threshold, where the
-//                        reference's exact `inter/union >= thr` is evaluated (bit-exact keep lists).
-//                        Only the first top_k kept boxes of a class can reach the global top-k (kept boxes are
-//                        in descending score order), so the sweep stops there: the result is unchanged and the
-//                        O(n^2) tail of the reference's loop is never executed.
+//   detect_nms_kernel    one CTA per (class, image).  The sweep stops once top_k boxes are kept (kept boxes come out
+//                        in descending score order, so only the first top_k of a class can reach the global top-k:
+//                        the result is unchanged and the O(n^2) tail of the reference's loop is never executed), so
+//                        the candidate list is consumed in SLICES of descending score found with a histogram over
+//                        linear probability bins; each slice is bitonic-sorted on the 64-bit keys (prob bits << 32 |
+//                        ~prior: descending prob, ties -> lower prior, T5) and swept in blocks of 64: a block is first
+//                        tested against the boxes kept so far (kept boxes live in shared memory), then resolved
+//                        internally with a 64x64 suppression bit mask.  The IoU test avoids the division unless the
+//                        ratio is within 2^-20 of the threshold, where the reference's exact `inter/union >= thr` is
+//                        evaluated (bit-exact keep lists).
 //   detect_topk_kernel   one CTA per image: class-major concatenation (Losses.py:71-73) or, if more than top_k
-//                        survive, the top_k by descending prob with ties to the earlier class-major position (T7).
+//                        survive, the top_k by descending prob with ties to the earlier class-major position (T7);
+//                        two lower bounds on the top_k-th score prune the 20 sorted lists before the merge sort.
 #include <algorithm>
 #include "common.cuh"
 

@@ -10,16 +10,27 @@
 //                      TMA bulk copies (mbarrier full/empty pipeline) and, from a zeroed tile in
 //                      shared memory, bulk-stores the zero background of grad_conf / grad_loc.
 //                      Consumers do thread-per-row log-softmax out of shared memory (row stride 21
-//                      words: bank-conflict free) and write one CE value per prior.  conf is read
-//                      exactly once; nothing is re-read; the tile grid is flat over B*P rows so
-//                      every bulk copy is 16-byte aligned whatever P is.
-//   mine_kernel        one CTA per image: CE row + class bytes -> keys in shared memory, exact
-//                      radix select (11/11/10 bits) of the k = 3*npos-th largest background CE,
-//                      ties to the lower prior index (T4; positives rank with value 0,
-//                      Losses.py:190), then thread-per-row over the ~4*npos selected rows only:
-//                      re-read that conf row, write (softmax - onehot)/N into grad_conf, and for
-//                      positives the L1 term and sign/(4N) into grad_loc.  Loss partials are reduced
-//                      in fp64 in a fixed order by the last CTA -> run-to-run deterministic.
+//                      words: bank-conflict free) and write one CE value per prior, scored against
+//                      the BACKGROUND class (~99 % of the rows; positives are re-scored by
+//                      mine_kernel).  With MATCH = true the same thread also computes the natural
+//                      match of its prior (best gt, T1) and feeds the per-gt arg-max over priors (T2):
+//                      the kernel is HBM-bound, the match rides in its spare issue slots.  conf is
+//                      read exactly once; the tile grid is flat over B*P rows so every bulk copy is
+//                      16-byte aligned whatever P is.
+//   mine_kernel        one CTA per image: (FIN) forced-match override of the image from the arg-max
+//                      keys (T3); CE row + class bytes -> keys in shared memory; exact selection of
+//                      the k = 3*npos largest background CE (linear-bin histogram + direct ranking of
+//                      the boundary bin; radix select 11/11/10 bits when ties crowd it), ties to the
+//                      lower prior index (T4; positives rank with value 0, Losses.py:190); then
+//                      thread-per-row over the ~4*npos selected rows only: re-read that conf row, write
+//                      (softmax - onehot)/N into grad_conf, and for positives the L1 term and sign/(4N)
+//                      into grad_loc.  N is the batch-global positive count: with FIN the CTAs of the
+//                      (cooperative) grid exchange it through a counter, and - for a batch sharded over
+//                      several GPUs - with their peers through stores into NVLink peer memory, as they
+//                      do the two loss sums.  Loss partials are reduced in fp64 in a fixed order by the
+//                      last CTA -> run-to-run deterministic.
+//   match_finalize_kernel   the forced-match override as a separate small kernel (the NCCL route of a
+//                      sharded batch, or when the batch does not fit a co-resident grid).
 //
 // HBM traffic per image: conf in once (733 KB) + CE out/in (2 x 35 KB, L2-resident between the two
 // kernels) + dense gradients out once (873 KB) + ~4*npos sparse rows: the algorithmic minimum.

@@ -345,3 +345,51 @@ def detect_image(loc: torch.Tensor, conf: torch.Tensor, pri_cxcywh: torch.Tensor
     boxes = decode(loc, pri_cxcywh)
     probs = F.softmax(conf, dim=1)
     return detect_from_scores(boxes, probs, min_score, iou_thr, top_k, num_fg)
+
+
+# --------------------------------------------------------------------------- evaluation
+def voc_ap(det_boxes, det_classes, det_scores, gt_boxes, gt_classes, num_fg: int = 20, iou_thr: float = 0.5):
+    """11-point interpolated VOC average precision per class (``get_map``, Util.py:783-885).
+
+    Inputs are per-image lists of tensors.  Per class: detections ranked by descending score (stable: ties -> lower
+    detection index, rule M1; the reference's sort leaves ties open); in that order a detection is a true positive
+    iff the gt of the same image and class with the highest IoU (first one on ties, M2) has IoU > iou_thr and has
+    not been claimed yet (Util.py:855-868).  Precision in float64; recall = cumTP * float32(1 / #gt) (see below);
+    recall levels = the float32 values of ``torch.arange(0, 1.1, 0.1)`` (Util.py:875).  Returns float64 [num_fg]."""
+    det_img = torch.cat([torch.full((len(b),), i, dtype=torch.int64) for i, b in enumerate(det_boxes)])
+    db = torch.cat([b.reshape(-1, 4) for b in det_boxes]).float()
+    dc = torch.cat([c.reshape(-1) for c in det_classes]).long()
+    ds = torch.cat([s.reshape(-1) for s in det_scores]).float()
+    gt_img = torch.cat([torch.full((len(b),), i, dtype=torch.int64) for i, b in enumerate(gt_boxes)])
+    gb = torch.cat([b.reshape(-1, 4) for b in gt_boxes]).float()
+    gc = torch.cat([c.reshape(-1) for c in gt_classes]).long()
+    claimed = np.zeros(gb.shape[0], dtype=bool)
+    levels = torch.arange(0, 1.1, 0.1).double().numpy()
+    ap = np.zeros(num_fg, dtype=np.float64)
+    for c in range(num_fg):
+        idx = (dc == c).nonzero().flatten()
+        if idx.numel() == 0:
+            continue
+        order = torch.sort(ds[idx], descending=True, stable=True).indices
+        idx = idx[order]
+        nobj = int((gc == c).sum())
+        tp = np.zeros(idx.numel(), dtype=np.float64)
+        for r, d in enumerate(idx.tolist()):
+            g = ((gt_img == det_img[d]) & (gc == c)).nonzero().flatten()
+            if g.numel() == 0:
+                continue
+            iou = iou_matrix(db[d:d + 1], gb[g])[0]
+            ov, j = iou.max(dim=0)
+            gi = int(g[j])
+            if float(ov) > iou_thr and not claimed[gi]:
+                claimed[gi] = True
+                tp[r] = 1.0
+        ctp = tp.cumsum()
+        precision = ctp / np.arange(1, len(tp) + 1, dtype=np.float64)
+        # Util.py:872 divides a numpy array by a 0-dim int64 TENSOR: torch evaluates that as reciprocal(tensor) * array,
+        # and the reciprocal of an integer tensor is float32 - so recall = cumTP * float32(1/#gt), a hair above k/#gt.
+        with np.errstate(divide="ignore", invalid="ignore"):
+            recall = ctp * np.float64(np.float32(1.0) / np.float32(nobj))
+        vals = [precision[recall >= lv].max() if (recall >= lv).any() else 0.0 for lv in levels]
+        ap[c] = float(np.mean(vals))
+    return ap
