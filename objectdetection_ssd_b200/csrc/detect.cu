@@ -95,7 +95,7 @@ detect_score_kernel(const float* __restrict__ loc, const float* __restrict__ con
             for (int q = 1; q < C; ++q) m = fmaxf(m, x[q]);
             float s = 0.0f;
 #pragma unroll
-            for (int q = 0; q < C; ++q) { e[q] = expf(__fsub_rn(x[q], m)); s = __fadd_rn(s, e[q]); }
+            for (int q = 0; q < C; ++q) { e[q] = __expf(__fsub_rn(x[q], m)); s = __fadd_rn(s, e[q]); }   // ex2.approx: rel. error ~2e-7
             const float inv = __fdiv_rn(1.0f, s);
 #pragma unroll
             for (int q = 0; q < NF; ++q) prob[q] = __fmul_rn(e[q], inv);
@@ -291,10 +291,15 @@ detect_nms_kernel(const float4* __restrict__ boxes, unsigned long long* __restri
     // is therefore consumed in SLICES of descending score: a histogram over linear probability bins (monotone in
     // the key) finds bin ranges holding about 2*top_k candidates; each slice is compacted into shared memory,
     // bitonic-sorted (descending prob, ties -> lower prior, T5) and swept, continuing with the same kept set.
-    const int slice_target = max(2 * top_k, 256);
+    const int slice_target = max(top_k + top_k / 2, 192);
+    // bins in the LOG domain, anchored at probability 1: the float's exponent and top 8 mantissa bits give 256 bins
+    // per octave, 8 octaves (2^-8 .. 1) in 2048 bins - a relative resolution of 0.4 % everywhere, so a slice lands
+    // close to its target even where candidates crowd just above min_score; monotone in the key; smaller
+    // probabilities share bin 0
     auto bin_of = [](unsigned long long key) {
-        const float p = __uint_as_float((unsigned)(key >> 32));
-        return min(NMS_BINS - 1, max(0, (int)__fmul_rn(p, (float)(NMS_BINS - 1))));
+        const int top = (int)(0x3f800000u >> 15);                     // bits of 1.0f
+        const int b = NMS_BINS - 1 - (top - (int)((unsigned)(key >> 32) >> 15));
+        return min(NMS_BINS - 1, max(0, b));
     };
     if (n <= slice_target * 2 && n <= SORT_SMEM) {
         // short list: one slice = everything
