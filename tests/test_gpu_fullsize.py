@@ -87,6 +87,14 @@ def test_train_head_batch256_properties():
     _loss_properties(pri, loc, conf, tb, tc, check_images=[0, 100, 255])
 
 
+def test_train_head_batch300_exceeds_coresident_grid():
+    """B = 300 > 2 CTAs x 148 SMs: the cooperative two-kernel step does not fit and ssdhead_multibox_step falls back
+    to the three-kernel route (stream, finaliser, mining) by itself; same properties must hold."""
+    pri = H.priors()
+    loc, conf, tb, tc = H.train_inputs(75, 300, pri.shape[0])
+    _loss_properties(pri, loc, conf, tb, tc, check_images=[0, 299])
+
+
 def test_train_head_stress_24564_priors_100_gt():
     pri = H.priors("ssd512")
     loc, conf, tb, tc = H.train_inputs(72, 32, pri.shape[0], min_gt=100, max_gt=100)
