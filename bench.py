@@ -261,13 +261,26 @@ def time_train(args, rank, world, dev, sampler):
     if world > 1:
         import torch.distributed as dist
         collective = args.collective
+        if collective == "peer" and B > 2 * torch.cuda.get_device_properties(dev).multi_processor_count:
+            collective = "nccl"          # the in-kernel exchange needs one co-resident CTA per image (B <= 2 x SMs)
         if collective == "peer":
             # one-off: exchange the CUDA IPC handles of the ranks' exchange buffers; afterwards the step is the same
             # two kernels as on one GPU, the mining kernel trading Npos and the loss sums with its peers over NVLink
             handles = [None] * world
             dist.all_gather_object(handles, ctx.xchg_export())
-            ctx.xchg_import(handles, rank)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                ctx.xchg_import(handles, rank)
+            except RuntimeError as e:                      # no peer access between these GPUs: every rank falls back
+                print(f"bench.py: rank {rank}: peer-memory import failed ({e}); using --collective nccl", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                ctx.close()
+                ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)   # a context without the exchange
+                collective = "nccl"
             dist.barrier()
+        args.collective = collective      # what actually ran (reported in config.parallelism)
 
     def step(i):
         l, c = sets[i % nset]
