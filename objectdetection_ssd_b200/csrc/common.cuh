@@ -146,7 +146,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
 {
-    static const int mask = getenv("SSDHEAD_PDL") ? atoi(getenv("SSDHEAD_PDL")) : 5;   // measured: CE + mine (5) best; chaining finaliser + mine (6, 7) is slower
+    static const int mask = getenv("SSDHEAD_PDL") ? atoi(getenv("SSDHEAD_PDL")) : 13;   // 1 CE stream, 2 finaliser, 4 mine, 8 detect; measured: CE + mine best, chaining the finaliser (2) is slower
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
