@@ -78,6 +78,14 @@ __device__ __forceinline__ float4 decode_box(const float4 g, const float4 p) {
                        __fmul_rn(expf(__fdiv_rn(g.w, 5.0f)), p.w));
 }
 
+// exp(d) through one ex2.approx.ftz (no denormal pre-scaling: results below 2^-126 flush to zero, which no caller can
+// tell from a denormal).  Same value as __expf(d) everywhere else; relative error <= (2 + 1.16|d|) ulp.
+__device__ __forceinline__ float fast_exp_ftz(float d) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(d, 1.4426950408889634f)));
+    return r;
+}
+
 // Order-preserving map float -> uint32 (total order of the reals; -0 and +0 collapse).
 __device__ __forceinline__ uint32_t float_order_key(float f) {
     f = __fadd_rn(f, 0.0f);                      // -0.0 -> +0.0

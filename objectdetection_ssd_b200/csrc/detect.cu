@@ -31,8 +31,18 @@
 
 namespace ssdhead {
 
+#ifdef SSDHEAD_PHASE_TIMES      // developer build: SM clock at the phase boundaries of the first image's sweep CTA
+__device__ long long g_phase[16];
+#define PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase[i] = clock64(); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
+
 constexpr int SC_T = 256;          // score kernel: threads = rows per tile
-constexpr int NT = 512;            // nms kernel threads
+#ifndef SSDHEAD_NMS_THREADS
+#define SSDHEAD_NMS_THREADS 512
+#endif
+constexpr int NT = SSDHEAD_NMS_THREADS;   // nms kernel threads
 constexpr int NPART = NT / 64;     // threads per candidate in a block of 64
 constexpr int CBINS = 256;         // coarse log-probability rank bins of an image (0 = [1, ..), 32 per octave)
 constexpr int FBINS = 2048;        // bins of the in-slice counting sort
@@ -43,30 +53,36 @@ static_assert(SC_T == CBINS, "one thread per coarse bin in the score kernel");
 static_assert(FBINS % NT == 0 && CBINS <= NT, "scan ownership");
 
 struct DetectWs {
-    unsigned long long* cand;      // [B][capI] candidate keys of an image, unordered
+    unsigned long long* cand;      // [B][capI] candidate keys of an image: one chunk per score tile, each chunk ordered
+                                   //           by coarse rank bin (highest probabilities first)
     unsigned long long* scr_a;     // [B][capI] slice buffers for slices that do not fit shared memory
     unsigned long long* scr_b;     // [B][capI]
-    unsigned int* cand_cnt;        // [B]         zero on entry, zero on exit
-    unsigned int* chist;           // [B][CBINS]  zero on entry, zero on exit
-    unsigned int* overflow;        // [B]         zero on entry, zero on exit
+    unsigned short* dir;           // [B][T][CBINS] keys per coarse rank bin of every chunk (rewritten by every call)
+    unsigned int* dir_base;        // [B][T]    start of the chunk in the image's list
+    unsigned int* cand_cnt;        // [B]       zero on entry, zero on exit
+    unsigned int* overflow;        // [B]       zero on entry, zero on exit
 };
 
 static inline int detect_cap_image(int P, int C, int n) { return (C - 1) * (n > 0 ? std::min(n, P) : P); }
+static inline int detect_tiles(int P) { return (P + SC_T - 1) / SC_T; }
 
 static size_t detect_ws_layout(int B, int P, int C, int n, DetectWs* w, void* base)
 {
     const size_t capI = (size_t)detect_cap_image(P, C, n);
+    const size_t T = (size_t)detect_tiles(P);
     size_t off = 0;
     char* b = (char*)base;
     auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return b ? (void*)(b + o) : nullptr; };
     void* p0 = take((size_t)B * capI * 8);
     void* p1 = take((size_t)B * capI * 8);
     void* p2 = take((size_t)B * capI * 8);
-    void* p3 = take((size_t)B * 4);
-    void* p4 = take((size_t)B * CBINS * 4);
+    void* p3 = take((size_t)B * T * CBINS * 2);
+    void* p4 = take((size_t)B * T * 4);
     void* p5 = take((size_t)B * 4);
+    void* p6 = take((size_t)B * 4);
     if (w) { w->cand = (unsigned long long*)p0; w->scr_a = (unsigned long long*)p1; w->scr_b = (unsigned long long*)p2;
-             w->cand_cnt = (unsigned int*)p3; w->chist = (unsigned int*)p4; w->overflow = (unsigned int*)p5; }
+             w->dir = (unsigned short*)p3; w->dir_base = (unsigned int*)p4;
+             w->cand_cnt = (unsigned int*)p5; w->overflow = (unsigned int*)p6; }
     return off;
 }
 
@@ -95,14 +111,21 @@ template <int C, bool FROM_SCORES>
 __global__ void __launch_bounds__(SC_T)
 detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int capI,
                     unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
-                    unsigned int* __restrict__ chist, unsigned int* __restrict__ overflow)
+                    unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
+                    unsigned int* __restrict__ overflow)
 {
     constexpr int NF = C - 1;
+    constexpr int NW = SC_T / 32;
     static_assert(NF <= 32, "class mask is one 32-bit word");
     __shared__ __align__(128) float s_conf[SC_T * C];
-    __shared__ unsigned int s_ch[CBINS];
+    __shared__ unsigned int s_ch[CBINS];            // keys per coarse rank bin, then their exclusive prefix sums
+    __shared__ unsigned int s_fill[CBINS];
+    __shared__ unsigned short s_stq[SC_T * NF];     // per warp: (lane << 5 | class) of its candidates, compact
+    __shared__ unsigned int s_wtot[NW];
+    __shared__ unsigned int s_wsum[NW];
+    __shared__ unsigned int s_base;
     __shared__ __align__(8) uint64_t s_bar;
-    const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31;
+    const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int r0 = tile * SC_T;
     const int nrows = min(SC_T, P - r0);
     const float* src = conf + ((size_t)b * P + r0) * C;
@@ -111,8 +134,9 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
 
     if (bulk && t == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
     s_ch[t] = 0u;
+    s_fill[t] = 0u;
     pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
-    pdl_wait();                          // the previous call's sweep may still be reading the lists we append to
+    pdl_wait();                          // the previous call's sweep may still be reading the lists we overwrite
     __syncthreads();
     if (bulk) {
         if (t == 0) { mbar_expect_tx(&s_bar, bytes); bulk_g2s(s_conf, src, bytes, &s_bar); }
@@ -122,30 +146,35 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
         __syncthreads();
     }
 
-    const bool valid = t < nrows;
-    const int row = r0 + t;
-    const float* x = s_conf + t * C;
+    // thread per prior: class probabilities, written back over the row's logits; bit q of cmask <=> prob[q] >= min_score
+    float* x = s_conf + t * C;
     unsigned cmask = 0u;
-    float m = 0.0f, inv = 1.0f;
-    if (valid) {
+    if (t < nrows) {
+        float p[NF];
         if (FROM_SCORES) {
 #pragma unroll
-            for (int q = 0; q < NF; ++q) cmask |= (x[q] >= min_score ? 1u : 0u) << q;
+            for (int q = 0; q < NF; ++q) p[q] = x[q];
         } else {
             // softmax: exp(x - max) * (1 / sum)  (Losses.py:25)
             float e[C];
-            m = x[0];
 #pragma unroll
-            for (int q = 1; q < C; ++q) m = fmaxf(m, x[q]);
+            for (int q = 0; q < C; ++q) e[q] = x[q];
+            float m = e[0];
+#pragma unroll
+            for (int q = 1; q < C; ++q) m = fmaxf(m, e[q]);
             float s = 0.0f;
 #pragma unroll
-            for (int q = 0; q < C; ++q) { e[q] = __expf(__fsub_rn(x[q], m)); s = __fadd_rn(s, e[q]); }   // ex2.approx: rel. error ~2e-7
-            inv = __fdiv_rn(1.0f, s);
+            for (int q = 0; q < C; ++q) { e[q] = fast_exp_ftz(__fsub_rn(e[q], m)); s = __fadd_rn(s, e[q]); }   // rel. error ~2e-7
+            const float inv = __fdiv_rn(1.0f, s);
 #pragma unroll
-            for (int q = 0; q < NF; ++q) cmask |= (__fmul_rn(e[q], inv) >= min_score ? 1u : 0u) << q;   // Losses.py:32
+            for (int q = 0; q < NF; ++q) { p[q] = __fmul_rn(e[q], inv); x[q] = p[q]; }
         }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) cmask |= (p[q] >= min_score ? 1u : 0u) << q;                              // Losses.py:32
     }
-    // one atomic per warp reserves the slots of all its candidates in the image's list
+    // Rows with a weak background logit pass in many classes at once (heavy tail), so per-thread emission would run
+    // at the pace of the warp's busiest lane.  Each lane only lists its candidates as (lane, class) descriptors,
+    // compacted across the warp; the warp then handles 32 candidates at a time.
     const unsigned ncand = (unsigned)__popc(cmask);
     unsigned incl = ncand;
 #pragma unroll
@@ -153,29 +182,65 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
         const unsigned o = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += o;
     }
-    unsigned wbase = 0u;
-    if (lane == 31 && incl) wbase = atomicAdd(&cand_cnt[b], incl);
-    wbase = __shfl_sync(FULL, wbase, 31);
-    unsigned slot = wbase + incl - ncand;
-    unsigned long long* seg = cand + (size_t)b * capI;
-    bool over = false;
-    while (cmask) {
-        const int q = __ffs(cmask) - 1;
-        cmask &= cmask - 1u;
-        // the same operations on the same inputs as above: the same bits
-        const float p = FROM_SCORES ? x[q] : __fmul_rn(__expf(__fsub_rn(x[q], m)), inv);
-        if (slot < (unsigned)capI) {
-            seg[slot] = make_key(p, q, row);
-            atomicAdd(&s_ch[coarse_rank(__float_as_uint(p))], 1u);
-        } else {
-            over = true;
+    const unsigned wtotal = __shfl_sync(FULL, incl, 31);
+    if (lane == 0) s_wtot[warp] = wtotal;
+    unsigned short* st_q = s_stq + warp * (32 * NF);
+    {
+        unsigned o = incl - ncand;
+        unsigned mm = cmask;
+        while (mm) {
+            const int q = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            st_q[o++] = (unsigned short)((lane << 5) | q);
         }
-        ++slot;
     }
-    if (over) atomicOr(&overflow[b], 1u);
     __syncthreads();
+    // the CTA's keys form one chunk of the image's list: reserve it (the atomic's latency hides behind the histogram)
+    unsigned total = 0u, chunk = 0u;
+    if (t == 0) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) total += s_wtot[w];
+        if (total) chunk = atomicAdd(&cand_cnt[b], total);
+    }
+    const float* wrow = s_conf + warp * (32 * C);
+    for (unsigned j = lane; j < wtotal; j += 32) {
+        const unsigned lq = st_q[j];
+        const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
+        atomicAdd(&s_ch[coarse_rank(__float_as_uint(pj))], 1u);
+    }
+    __syncthreads();
+    // exclusive prefix sums over the 256 rank bins: the chunk is written ordered by bin, highest probabilities first,
+    // and its per-bin counts go to the image's directory - the sweep kernel then reads only the keys of a score slice
     const unsigned h = s_ch[t];
-    if (h) atomicAdd(&chist[(size_t)b * CBINS + t], h);
+    unsigned hin = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(FULL, hin, d);
+        if (lane >= d) hin += o;
+    }
+    if (lane == 31) s_wsum[warp] = hin;
+    if (t == 0) {
+        const bool fits = chunk + total <= (unsigned)capI;
+        s_base = fits ? chunk : 0xffffffffu;
+        dir_base[(size_t)b * gridDim.x + tile] = fits ? chunk : 0u;
+        if (!fits) atomicOr(&overflow[b], 1u);                   // the whole chunk is dropped; out_cnt[b] becomes -1
+    }
+    __syncthreads();
+    unsigned wb = 0u;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) if (w < warp) wb += s_wsum[w];
+    s_ch[t] = wb + hin - h;
+    const unsigned base = s_base;
+    dir[((size_t)b * gridDim.x + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)h : (unsigned short)0;
+    __syncthreads();
+    if (base == 0xffffffffu) return;
+    unsigned long long* seg = cand + (size_t)b * capI + base;
+    for (unsigned j = lane; j < wtotal; j += 32) {
+        const unsigned lq = st_q[j];
+        const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
+        const int rb = coarse_rank(__float_as_uint(pj));
+        seg[s_ch[rb] + atomicAdd(&s_fill[rb], 1u)] = make_key(pj, (int)(lq & 31u), r0 + warp * 32 + (int)(lq >> 5));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -221,6 +286,26 @@ struct Kept {                      // kept boxes in sweep order + per-class inde
     int cap;
 };
 
+// exclusive prefix sum of one value per thread over the CTA (two barriers; s_wsum is reusable afterwards)
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned int* s_wsum, unsigned& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0u;
+    total = 0u;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const unsigned x = s_wsum[w]; if (w < warp) wbase += x; total += x; }
+    __syncthreads();
+    return wbase + incl - v;
+}
+
 // exclusive prefix sums of s_cnt[0..FBINS) into s_S[0..FBINS], counters reset to zero (thread t owns FBINS/NT bins)
 __device__ __forceinline__ void scan_bins(unsigned int* s_cnt, unsigned int* s_S, unsigned int* s_wsum)
 {
@@ -247,12 +332,30 @@ __device__ __forceinline__ void scan_bins(unsigned int* s_cnt, unsigned int* s_S
     __syncthreads();
 }
 
+// Linear map of a key range onto FBINS bins, bin 0 = largest keys (keys outside the range are clamped: still monotone).
+struct BinMap {
+    unsigned long long kmax;
+    int shift;
+    __device__ __forceinline__ BinMap(unsigned long long kmin_, unsigned long long kmax_) : kmax(kmax_) {
+        const unsigned long long range = kmax_ - kmin_;
+        shift = range ? max(0, 64 - __clzll((long long)range) - 11) : 0;                      // (range >> shift) < FBINS
+    }
+    __device__ __forceinline__ int operator()(unsigned long long k) const {
+        return k >= kmax ? 0 : (int)min((kmax - k) >> shift, (unsigned long long)(FBINS - 1));
+    }
+};
+
 // Sorts X[0,n) in descending key order (keys are distinct); Y is scratch of the same size.  X/Y may be shared or
 // global memory.  Adaptive counting sort: FBINS linear bins between the segment's min and max key, keys scattered
 // bin-grouped into Y, ranked inside their bin back into X; a bin with more than CROWD keys becomes a segment of the
 // next level (its own min/max spread its keys again), so ties in the probability cost one more level, not n^2.
+// `pre`: the caller already knows bounds [kmin0, kmax0] of the keys and has counted them into s_cnt with
+// BinMap(kmin0, kmax0) (the slice filter does this on the fly), so the first level starts at the prefix sums.
+// place(pos, key) is called once per key when its final position is known.
+template <typename Place>
 __device__ void sort_desc(unsigned long long* X, unsigned long long* Y, int n,
-                          unsigned int* s_S, unsigned int* s_cnt, SortShared& ss)
+                          unsigned int* s_S, unsigned int* s_cnt, SortShared& ss,
+                          bool pre, unsigned long long kmin0, unsigned long long kmax0, Place place)
 {
     const int t = threadIdx.x;
     if (t == 0) { ss.seg[0][0] = make_int2(0, n); ss.nseg[0] = 1; ss.nseg[1] = 0; }
@@ -263,10 +366,12 @@ __device__ void sort_desc(unsigned long long* X, unsigned long long* Y, int n,
         if (ns == 0) break;
         for (int si = 0; si < ns; ++si) {
             const int a = ss.seg[cur][si].x, m = ss.seg[cur][si].y - a;
-            if (t == 0) { ss.kmin = ~0ull; ss.kmax = 0ull; }
-            for (int i = t; i < FBINS; i += NT) s_cnt[i] = 0u;
-            __syncthreads();
-            {
+            unsigned long long kmin = kmin0, kmax = kmax0;
+            const bool counted = pre && level == 0;
+            if (!counted) {
+                if (t == 0) { ss.kmin = ~0ull; ss.kmax = 0ull; }
+                for (int i = t; i < FBINS; i += NT) s_cnt[i] = 0u;
+                __syncthreads();
                 unsigned long long lo = ~0ull, hi = 0ull;
                 for (int i = t; i < m; i += NT) { const unsigned long long k = X[a + i]; lo = min(lo, k); hi = max(hi, k); }
 #pragma unroll
@@ -275,14 +380,19 @@ __device__ void sort_desc(unsigned long long* X, unsigned long long* Y, int n,
                     hi = max(hi, __shfl_xor_sync(FULL, hi, d));
                 }
                 if ((t & 31) == 0 && lo <= hi) { atomicMin(&ss.kmin, lo); atomicMax(&ss.kmax, hi); }
+                __syncthreads();
+                kmin = ss.kmin; kmax = ss.kmax;
+                if (kmax == kmin) {                              // one key (or equal keys): nothing to order
+                    for (int i = t; i < m; i += NT) place(a + i, X[a + i]);
+                    __syncthreads();
+                    continue;
+                }
             }
-            __syncthreads();
-            const unsigned long long kmax = ss.kmax, range = kmax - ss.kmin;
-            if (range == 0ull) { __syncthreads(); continue; }  // one key (or equal keys): nothing to order
-            const int shift = max(0, 64 - __clzll((long long)range) - 11);       // (range >> shift) < FBINS
-            auto bin_of = [&](unsigned long long k) { return (int)((kmax - k) >> shift); };   // bin 0 = largest keys
-            for (int i = t; i < m; i += NT) atomicAdd(&s_cnt[bin_of(X[a + i])], 1u);
-            __syncthreads();
+            const BinMap bin_of(kmin, kmax);
+            if (!counted) {
+                for (int i = t; i < m; i += NT) atomicAdd(&s_cnt[bin_of(X[a + i])], 1u);
+                __syncthreads();
+            }
             scan_bins(s_cnt, s_S, ss.wsum);
             for (int i = t; i < m; i += NT) {
                 const unsigned long long k = X[a + i];
@@ -309,6 +419,7 @@ __device__ void sort_desc(unsigned long long* X, unsigned long long* Y, int n,
                 int r = 0;
                 for (int j = lo; j < hi; ++j) r += (Y[a + j] > k) ? 1 : 0;
                 X[a + lo + r] = k;
+                place(a + lo + r, k);
             }
             __syncthreads();
         }
@@ -341,6 +452,7 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
     }
     if (t < 2) s.supp[t] = 0u;
     __syncthreads();
+    unsigned long long bits = 0ull;
     {
         const int cnd = t & 63, part = t >> 6;
         if (cnd < m) {
@@ -359,7 +471,6 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
             }
             // (b) inside the block: row cnd tests the later same-class columns of its part
             constexpr int CW = 64 / NPART;
-            unsigned long long bits = 0ull;
 #pragma unroll
             for (int q = 0; q < CW; ++q) {
                 const int col = part * CW + q;
@@ -370,27 +481,35 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
             if (bits) atomicOr(&s.mask[cnd], bits);
         }
     }
-    __syncthreads();
-    if (t < 32) {
-        // (c) serial resolve: a box that is still alive suppresses the later boxes it overlaps.  The 64 mask rows are
-        // pulled into registers first (two per lane) so the dependent chain is pure ALU + shuffles.
-        const unsigned long long m_lo = s.mask[t], m_hi = s.mask[t + 32];
-        unsigned long long alive = (m == 64 ? ~0ull : ((1ull << m) - 1ull)) &
-                                   ~((unsigned long long)s.supp[0] | ((unsigned long long)s.supp[1] << 32));
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const unsigned long long mk = __shfl_sync(FULL, m_lo, i);
-            alive &= ((alive >> i) & 1ull) ? ~mk : ~0ull;
+    const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+    unsigned long long alive;
+    if (__syncthreads_or(bits != 0ull)) {
+        if (t < 32) {
+            // (c) serial resolve: a box that is still alive suppresses the later boxes it overlaps.  The 64 mask rows
+            // are pulled into registers first (two per lane); the dependent chain is ALU + shuffles.
+            const unsigned long long m_lo = s.mask[t], m_hi = s.mask[t + 32];
+            unsigned long long al = valid & ~((unsigned long long)s.supp[0] | ((unsigned long long)s.supp[1] << 32));
+            unsigned nz_lo = __ballot_sync(FULL, m_lo != 0ull), nz_hi = __ballot_sync(FULL, m_hi != 0ull);
+            while (nz_lo) {                                   // only rows that overlap somebody, in sweep order
+                const int i = __ffs(nz_lo) - 1;
+                nz_lo &= nz_lo - 1u;
+                const unsigned long long mk = __shfl_sync(FULL, m_lo, i);
+                if ((al >> i) & 1ull) al &= ~mk;
+            }
+            while (nz_hi) {
+                const int i = __ffs(nz_hi) - 1;
+                nz_hi &= nz_hi - 1u;
+                const unsigned long long mk = __shfl_sync(FULL, m_hi, i);
+                if ((al >> (i + 32)) & 1ull) al &= ~mk;
+            }
+            if (t == 0) s.alive = al;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const unsigned long long mk = __shfl_sync(FULL, m_hi, i);
-            alive &= ((alive >> (i + 32)) & 1ull) ? ~mk : ~0ull;
-        }
-        if (t == 0) s.alive = alive;
+        __syncthreads();
+        alive = s.alive;
+    } else {
+        // no overlapping same-class pair inside the block (the common case): nothing to resolve
+        alive = valid & ~((unsigned long long)s.supp[0] | ((unsigned long long)s.supp[1] << 32));
     }
-    __syncthreads();
-    const unsigned long long alive = s.alive;
     if (t < m && ((alive >> t) & 1ull)) {
         const int pos = K + __popcll(alive & ((1ull << t) - 1ull));
         if (pos < kp.cap) {
@@ -403,7 +522,7 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
     return K + __popcll(alive);
 }
 
-static size_t nms_smem_bytes(int NF, int top_k)
+static size_t nms_smem_bytes(int NF, int top_k, int T)
 {
     const size_t kcap = (size_t)top_k + 65;
     size_t off = 0;
@@ -415,6 +534,7 @@ static size_t nms_smem_bytes(int NF, int top_k)
     off += (size_t)FBINS * 4;          // counters
     off += kcap * 4;                   // kept areas
     off += 32 * 4;                     // per-class kept counts
+    off += (size_t)T * 4 * 4;          // per-chunk base, start, length, offset of the current slice
     off += (size_t)NF * kcap * 2;      // per-class index lists
     return (off + 15) & ~(size_t)15;
 }
@@ -423,9 +543,10 @@ template <bool FROM_SCORES>
 __global__ void __launch_bounds__(NT)
 detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
                   unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
-                  unsigned long long* __restrict__ scr_b, unsigned int* __restrict__ cand_cnt,
-                  unsigned int* __restrict__ chist, unsigned int* __restrict__ overflow,
-                  const float* __restrict__ img_wh, int P, int NF, int capI, int top_k, float iou_thr,
+                  unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
+                  const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
+                  unsigned int* __restrict__ overflow,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
@@ -441,43 +562,58 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(sp);               sp += (size_t)FBINS * 4;
     float* s_karea = reinterpret_cast<float*>(sp);                           sp += (size_t)kcap * 4;
     int* s_kcnt = reinterpret_cast<int*>(sp);                                sp += 32 * 4;
+    unsigned int* s_cbase = reinterpret_cast<unsigned int*>(sp);             sp += (size_t)T * 4;
+    unsigned int* s_cstart = reinterpret_cast<unsigned int*>(sp);            sp += (size_t)T * 4;
+    unsigned int* s_clen = reinterpret_cast<unsigned int*>(sp);              sp += (size_t)T * 4;
+    unsigned int* s_coff = reinterpret_cast<unsigned int*>(sp);              sp += (size_t)T * 4;
     unsigned short* s_kidx = reinterpret_cast<unsigned short*>(sp);
+    // the image's directory (T x 256 counts) is kept in the box buffer, which is idle while a slice is gathered
+    bool dir_cached = (size_t)T * CBINS * 2 <= (size_t)SL * 16;       // until the first slice's boxes overwrite it
+    unsigned short* s_dir = reinterpret_cast<unsigned short*>(s_box);
     __shared__ NmsBlock s;
     __shared__ SortShared ss;
     __shared__ unsigned int s_CS[CBINS + 1];
+    __shared__ unsigned int s_col[CBINS];
     __shared__ int s_rc1;
-    __shared__ unsigned int s_fill;
 
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    pdl_wait();                                              // the score kernel's lists and histogram are complete
-    const int n = (int)min(cand_cnt[b], (unsigned)capI);
+    if (t < CBINS) s_col[t] = 0u;
+    if (t < 32) s_kcnt[t] = 0;
+    __syncthreads();
+    pdl_wait();                                              // the score kernel's lists and directory are complete
+    PHASE(0);
     const unsigned long long* seg = cand + (size_t)b * capI;
+    const unsigned short* gdir = dir + (size_t)b * T * CBINS;
     const size_t bP = (size_t)b * P;
     float4* ob = out_boxes + (size_t)b * top_k;
     float* op = out_prob + (size_t)b * top_k;
     int* oc = out_cls + (size_t)b * top_k;
     int* oi = out_prior ? out_prior + (size_t)b * top_k : nullptr;
 
-    // coarse histogram -> prefix sums CS[r] = number of keys in rank bins < r (bin 0 = highest probabilities)
+    // column sums of the directory = the image's coarse histogram -> prefix sums CS[r] = number of keys in rank bins
+    // < r (bin 0 = highest probabilities)
     {
-        unsigned c = 0u;
-        if (t < CBINS && n > 0) { c = chist[(size_t)b * CBINS + t]; chist[(size_t)b * CBINS + t] = 0u; }
-        unsigned incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += o;
+        constexpr int G = NT / CBINS;                        // thread groups sharing the chunks of a column
+        const int col = t % CBINS, g = t / CBINS;
+        unsigned sum = 0u;
+#pragma unroll 4
+        for (int c = g; c < T; c += G) {
+            const unsigned short v = gdir[(size_t)c * CBINS + col];
+            if (dir_cached) s_dir[c * CBINS + col] = v;
+            sum += v;
         }
-        if (lane == 31) ss.wsum[warp] = incl;
-        if (t < 32) s_kcnt[t] = 0;
+        if (g < G && sum) atomicAdd(&s_col[col], sum);
+        for (int c = t; c < T; c += NT) s_cbase[c] = dir_base[(size_t)b * T + c];
         __syncthreads();
-        unsigned wbase = 0u;
-        for (int w = 0; w < warp; ++w) wbase += ss.wsum[w];
-        if (t < CBINS) s_CS[t] = wbase + incl - c;
-        if (t == CBINS - 1) s_CS[CBINS] = wbase + incl;
+        unsigned total;
+        const unsigned c = t < CBINS ? s_col[t] : 0u;
+        const unsigned ex = block_excl_scan(c, ss.wsum, total);
+        if (t < CBINS) s_CS[t] = ex;
+        if (t == 0) s_CS[CBINS] = total;
         __syncthreads();
     }
 
+    PHASE(1);
     const float thr_lo = __fmul_rn(iou_thr, 1.0f - 9.5367431640625e-07f);   // thr * (1 - 2^-20)
     const float thr_hi = __fmul_rn(iou_thr, 1.0f + 9.5367431640625e-07f);
     const Kept kp = {s_kbox, s_kkey, s_karea, s_kidx, s_kcnt, kcap};
@@ -493,7 +629,7 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
     int target = max(top_k + top_k / 2 + 1, 96);
     while (K <= top_k && rc0 < CBINS && s_CS[CBINS] - s_CS[rc0] > 0u) {
         // slice = rank bins [rc0, rc1): the fewest bins holding at least `target` keys, or all that is left
-        if (t == 0) { s_rc1 = CBINS; s_fill = 0u; }
+        if (t == 0) s_rc1 = CBINS;
         __syncthreads();
         if (t < CBINS) {
             const int rc = t + 1;
@@ -505,38 +641,71 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
         const bool in_smem = cnt <= SL;
         unsigned long long* X = in_smem ? s_buf_a : scr_a + (size_t)b * capI;
         unsigned long long* Y = in_smem ? s_buf_b : scr_b + (size_t)b * capI;
-        if (rc0 == 0 && rc1 == CBINS) {
-            for (int i = t; i < n; i += NT) X[i] = seg[i];
-        } else {
-            for (int i0 = 0; i0 < n; i0 += NT * 4) {
-                unsigned long long k4[4];
+        // key bounds of the slice from its coarse bins (the open-ended last bin has none: the sort measures them)
+        const bool pre = rc1 < CBINS;
+        const unsigned top18 = 0x3f800000u >> 18;
+        const unsigned long long kmax0 = rc0 == 0 ? (0x3f800000ull << 32 | 0xffffffffull)
+                                                  : ((unsigned long long)((top18 - rc0 + 1) << 18) << 32) - 1ull;
+        const unsigned long long kmin0 = pre ? (unsigned long long)((top18 - (rc1 - 1)) << 18) << 32 : 0ull;
+        const BinMap bin0(kmin0, kmax0);
+        if (pre) for (int i = t; i < FBINS; i += NT) s_cnt[i] = 0u;
+        // where the slice sits in every chunk: chunks are ordered by rank bin, so it is one contiguous piece per chunk
+        for (int c = warp; c < T; c += NT / 32) {
+            const uint4 v = dir_cached ? *reinterpret_cast<const uint4*>(s_dir + c * CBINS + lane * 8)
+                                       : __ldg(reinterpret_cast<const uint4*>(gdir + (size_t)c * CBINS + lane * 8));
+            const unsigned w8[4] = {v.x, v.y, v.z, v.w};
+            unsigned before = 0u, inside = 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT + t; k4[u] = i < n ? seg[i] : 0ull; }
+            for (int k = 0; k < 8; ++k) {
+                const int r = lane * 8 + k;
+                const unsigned cntk = (w8[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                before += r < rc0 ? cntk : 0u;
+                inside += (r >= rc0 && r < rc1) ? cntk : 0u;
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * NT + t;
-                    if (i < n) {
-                        const int r = coarse_rank((unsigned)(k4[u] >> 32));
-                        if (r >= rc0 && r < rc1) X[atomicAdd(&s_fill, 1u)] = k4[u];
-                    }
-                }
+            for (int d = 16; d > 0; d >>= 1) {
+                before += __shfl_xor_sync(FULL, before, d);
+                inside += __shfl_xor_sync(FULL, inside, d);
+            }
+            if (lane == 0) { s_cstart[c] = before; s_clen[c] = inside; }
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < T; c0 += NT) {                    // T <= NT: one round
+            unsigned total;
+            const int c = c0 + t;
+            const unsigned ex = block_excl_scan(c < T ? s_clen[c] : 0u, ss.wsum, total);
+            if (c < T) s_coff[c] = ex;
+        }
+        __syncthreads();
+        for (int c = warp; c < T; c += NT / 32) {
+            const unsigned long long* src = seg + s_cbase[c] + s_cstart[c];
+            const int len = (int)s_clen[c], off = (int)s_coff[c];
+            for (int i = lane; i < len; i += 32) {
+                const unsigned long long k = ld_cg_u64(src + i);
+                X[off + i] = k;
+                if (pre) atomicAdd(&s_cnt[bin0(k)], 1u);
             }
         }
         __syncthreads();
-        sort_desc(X, Y, cnt, s_S, s_cnt, ss);
+        PHASE(2);
         if (in_smem) {
-            for (int i = t; i < cnt; i += NT) s_box[i] = load_box(X[i]);
-            __syncthreads();
+            // boxes are decoded as soon as a key's final position is known
+            sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [&](int pos, unsigned long long key) { s_box[pos] = load_box(key); });
+            PHASE(3);
+            PHASE(4);
             for (int base = 0; base < cnt && K <= top_k; base += 64)
                 K = nms_block(s, X, base, min(64, cnt - base), [&](int i, unsigned long long) { return s_box[i]; },
                               kp, K, iou_thr, thr_lo, thr_hi);
         } else {
+            sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [](int, unsigned long long) {});
             for (int base = 0; base < cnt && K <= top_k; base += 64)
                 K = nms_block(s, X, base, min(64, cnt - base), [&](int, unsigned long long key) { return load_box(key); },
                               kp, K, iou_thr, thr_lo, thr_hi);
         }
         rc0 = rc1;
+        dir_cached = false;
         if (target < (1 << 28)) target *= 2;
+        PHASE(5);
     }
 
     float sx = 1.0f, sy = 1.0f;
@@ -571,6 +740,7 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
         overflow[b] = 0u;
         cand_cnt[b] = 0u;
     }
+    PHASE(6);
 }
 
 template <bool FROM_SCORES>
@@ -586,7 +756,9 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (B > 65535 || P >= (1 << 24) || top_k > 60000) return SSDHEAD_E_UNSUPPORTED;
     if (!aligned16(loc) || (!FROM_SCORES && !aligned16(pri_cxcywh)) || !aligned16(out_boxes) || !aligned16(ws)) return SSDHEAD_E_ALIGN;
     const int NF = C - 1;
-    const size_t smem_nms = nms_smem_bytes(NF, top_k);
+    const int T = detect_tiles(P);
+    if (T > NT) return SSDHEAD_E_UNSUPPORTED;                                 // P <= 131072
+    const size_t smem_nms = nms_smem_bytes(NF, top_k, T);
     if (smem_nms > 200 * 1024) return SSDHEAD_E_UNSUPPORTED;                 // top_k <= ~1400 for 20 classes
     DetectWs w;
     const size_t need = detect_ws_layout(B, P, C, n_cap, &w, ws);
@@ -595,13 +767,13 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
 
     dim3 g1((P + SC_T - 1) / SC_T, B);
     SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
-                              conf, P, min_score, capI, w.cand, w.cand_cnt, w.chist, w.overflow));
+                              conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
     count_launch();
 
     SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
     SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
-                              (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.cand_cnt, w.chist,
-                              w.overflow, img_wh, P, NF, capI, top_k, iou_thr,
+                              (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
+                              w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
                               (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     count_launch();
     return 0;
@@ -630,5 +802,9 @@ int ssdhead_detect_from_scores(const float* boxes_cxcywh, const float* probs, in
     return run_detect<true>(boxes_cxcywh, probs, nullptr, B, P, C, min_score, iou_thr, top_k, img_wh,
                             out_boxes, out_prob, out_cls, out_prior, out_cnt, ws, ws_bytes, max_candidates, (cudaStream_t)stream);
 }
+
+#ifdef SSDHEAD_PHASE_TIMES
+int ssdhead_debug_phases(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, g_phase, sizeof(long long) * 16); }
+#endif
 
 }  // extern "C"
