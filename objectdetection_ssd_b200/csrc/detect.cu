@@ -260,6 +260,35 @@ __device__ __forceinline__ bool iou_ge(const float4 a, const float aa, const flo
     return __fdiv_rn(inter, uni) >= thr;
 }
 
+// The same predicate with a cheap filter in front.  In real arithmetic inter/union >= thr <=> inter >= T (aa + ab) with
+// T = thr / (1 + thr); the fp32 evaluation of either side is off by less than 2^-21 relative (no cancellation: inter <=
+// union), so outside a 2^-18 band around T (aa + ab) the answer is certain and inside it the reference's own expression
+// decides.  t_lo/t_hi = T (1 -+ 2^-18), or -inf/+inf when thr is not inside (0, 1) (always the exact path); NaNs fail
+// both comparisons and reach the exact path too.
+struct IouThr { float thr, thr_lo, thr_hi, t_lo, t_hi; };
+__device__ __forceinline__ IouThr make_iou_thr(float thr) {
+    IouThr r;
+    r.thr = thr;
+    r.thr_lo = __fmul_rn(thr, 1.0f - 9.5367431640625e-07f);   // thr * (1 - 2^-20)
+    r.thr_hi = __fmul_rn(thr, 1.0f + 9.5367431640625e-07f);
+    const bool ok = thr > 0.0f && thr < 1.0f;
+    const float T = __fdiv_rn(thr, __fadd_rn(1.0f, thr));
+    r.t_lo = ok ? __fmul_rn(T, 1.0f - 3.814697265625e-06f) : __int_as_float(0xff800000);
+    r.t_hi = ok ? __fmul_rn(T, 1.0f + 3.814697265625e-06f) : __int_as_float(0x7f800000);
+    return r;
+}
+__device__ __forceinline__ bool iou_ge_fast(const float4 a, const float aa, const float4 b, const float ab, const IouThr& q)
+{
+    const float dx = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float dy = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = __fmul_rn(dx, dy);
+    const float sum = __fadd_rn(aa, ab);
+    bool res = inter > __fmul_rn(sum, q.t_hi);
+    if (!res && !(inter < __fmul_rn(sum, q.t_lo)))            // rare: inside the band (or NaN)
+        res = __fdiv_rn(inter, __fsub_rn(sum, inter)) >= q.thr;
+    return res;
+}
+
 struct NmsBlock {                  // one block of up to 64 sorted candidates
     float4 cbox[64];
     unsigned long long ckey[64];
@@ -522,6 +551,137 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
     return K + __popcll(alive);
 }
 
+// Sweep of one sorted slice held in shared memory (keys X[0,cnt), boxes s_box[0,cnt), cnt <= SL).  Suppression only
+// acts inside a class, so the greedy NMS of a class (Losses.py:44-55) runs inside ONE warp, all classes side by side and
+// without a block-wide barrier: (1) a stable partition of the slice positions by class (match_any inside chunks of 32 +
+// per-class prefix sums over the chunks), (2) per class, 32 candidates at a time in lanes: tested against the boxes of
+// the class kept earlier (previous slices, previous rounds), then resolved in score order - only boxes that are still
+// alive are broadcast with shuffles, (3) the kept flags are compacted in slice (= global score) order onto the kept
+// list.  `scratch` is at least 16 KB of shared memory that is free during the sweep.  Returns the new kept count.
+__device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, const float4* s_box, int cnt, int NF, unsigned char* scratch,
+                                    unsigned int* s_wsum, const Kept kp, int K, const IouThr q)
+{
+    constexpr int NW = NT / 32;
+    constexpr int NFP = 32;                                    // row stride of the per-chunk class counts
+    unsigned short* s_order = reinterpret_cast<unsigned short*>(scratch);              // [SL] positions, grouped by class
+    unsigned char* s_keep = scratch + SL * 2;                                          // [SL]
+    unsigned short* s_cc = reinterpret_cast<unsigned short*>(scratch + SL * 3);        // [SL/32][NFP]
+    int* s_cstart = reinterpret_cast<int*>(scratch + SL * 3 + (SL / 32) * NFP * 2);    // [NFP + 1]
+    unsigned int* my_rows = reinterpret_cast<unsigned int*>(s_cstart + NFP + 4) + (threadIdx.x >> 5) * 32;   // [NW][32]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nchunk = (cnt + 31) >> 5;
+    PHASE(8);
+
+    for (int i = t; i < nchunk * NFP; i += NT) s_cc[i] = 0;
+    for (int i = t; i < cnt; i += NT) s_keep[i] = 0;
+    __syncthreads();
+    for (int ch = warp; ch < nchunk; ch += NW) {
+        const int i = ch * 32 + lane;
+        const int c = i < cnt ? key_cls(X[i]) : NFP - 1;       // padding lanes form their own group
+        const unsigned peers = __match_any_sync(FULL, c);
+        if (lane == __ffs(peers) - 1) s_cc[ch * NFP + c] = (unsigned short)__popc(peers);
+    }
+    __syncthreads();
+    if (t < NFP) {
+        int run = 0;
+        for (int ch = 0; ch < nchunk; ++ch) { const int v = s_cc[ch * NFP + t]; s_cc[ch * NFP + t] = (unsigned short)run; run += v; }
+        // class starts: exclusive prefix over the classes (one warp)
+        int incl = t < NF ? run : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        s_cstart[t + 1] = incl;
+        if (t == 0) s_cstart[0] = 0;
+    }
+    __syncthreads();
+    for (int ch = warp; ch < nchunk; ch += NW) {
+        const int i = ch * 32 + lane;
+        const int c = i < cnt ? key_cls(X[i]) : NFP - 1;
+        const unsigned peers = __match_any_sync(FULL, c);
+        if (i < cnt) s_order[s_cstart[c] + s_cc[ch * NFP + c] + __popc(peers & lt)] = (unsigned short)i;
+    }
+    __syncthreads();
+    PHASE(9);
+
+    for (int c = warp; c < NF; c += NW) {
+        const int n_c = s_cstart[c + 1] - s_cstart[c];
+        unsigned short* L = s_order + s_cstart[c];
+        const int kc0 = kp.cnt[c];
+        const unsigned short* il = kp.idx + (size_t)c * kp.cap;
+        int m_c = 0;                                           // kept in this slice so far: their positions are L[0, m_c)
+        for (int r0 = 0; r0 < n_c; r0 += 32) {
+            const int j = r0 + lane;
+            const bool v = j < n_c;
+            const int pos = v ? (int)L[j] : 0;
+            const float4 bx = v ? s_box[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ar = box_area(bx);
+            bool sup = false;
+            for (int k = 0; k < kc0; ++k) {
+                const int id = il[k];
+                sup = sup || iou_ge_fast(kp.box[id], kp.area[id], bx, ar, q);
+            }
+            for (int k = 0; k < m_c; ++k) {
+                const float4 b2 = s_box[L[k]];
+                sup = sup || iou_ge_fast(b2, box_area(b2), bx, ar, q);
+            }
+            // all pairs of the round along the diagonals (independent iterations, they pipeline): lane i ends up with
+            // the later lanes its box overlaps; then only rows that overlap somebody are walked in score order
+            const int nr = min(32, n_c - r0);
+            my_rows[lane] = 0u;
+            __syncwarp();
+#pragma unroll 4
+            for (int d = 1; d < nr; ++d) {                    // lane j against lane j - d
+                const int pi = __shfl_up_sync(FULL, pos, d);
+                if (lane >= d && v) {
+                    const float4 bi = s_box[pi];
+                    if (iou_ge_fast(bi, box_area(bi), bx, ar, q)) atomicOr(&my_rows[lane - d], 1u << lane);
+                }
+            }
+            __syncwarp();
+            const unsigned row = my_rows[lane];
+            unsigned alive = __ballot_sync(FULL, v && !sup);
+            unsigned todo = __ballot_sync(FULL, row != 0u);
+            while (todo) {
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const unsigned r = __shfl_sync(FULL, row, i);
+                if ((alive >> i) & 1u) alive &= ~r;
+            }
+            __syncwarp();
+            if ((alive >> lane) & 1u) { L[m_c + __popc(alive & lt)] = (unsigned short)pos; s_keep[pos] = 1; }
+            m_c += __popc(alive);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    PHASE(10);
+
+    // kept flags -> kept list, in slice order
+    const int per = (cnt + NT - 1) / NT;
+    const int lo = min(cnt, t * per), hi = min(cnt, lo + per);
+    unsigned local = 0u;
+    for (int i = lo; i < hi; ++i) local += s_keep[i];
+    unsigned total;
+    int g = K + (int)block_excl_scan(local, s_wsum, total);
+    for (int i = lo; i < hi; ++i) {
+        if (!s_keep[i]) continue;
+        if (g < kp.cap) {
+            const unsigned long long key = X[i];
+            const float4 bx = s_box[i];
+            kp.box[g] = bx; kp.area[g] = box_area(bx); kp.key[g] = key;
+            const int c = key_cls(key);
+            kp.idx[(size_t)c * kp.cap + atomicAdd(&kp.cnt[c], 1)] = (unsigned short)g;
+        }
+        ++g;
+    }
+    __syncthreads();
+    PHASE(11);
+    return K + (int)total;
+}
+
 static size_t nms_smem_bytes(int NF, int top_k, int T)
 {
     const size_t kcap = (size_t)top_k + 65;
@@ -540,7 +700,7 @@ static size_t nms_smem_bytes(int NF, int top_k, int T)
 }
 
 template <bool FROM_SCORES>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
                   unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
@@ -693,9 +853,7 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [&](int pos, unsigned long long key) { s_box[pos] = load_box(key); });
             PHASE(3);
             PHASE(4);
-            for (int base = 0; base < cnt && K <= top_k; base += 64)
-                K = nms_block(s, X, base, min(64, cnt - base), [&](int i, unsigned long long) { return s_box[i]; },
-                              kp, K, iou_thr, thr_lo, thr_hi);
+            K = sweep_slice_by_class(X, s_box, cnt, NF, reinterpret_cast<unsigned char*>(Y), ss.wsum, kp, K, make_iou_thr(iou_thr));
         } else {
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [](int, unsigned long long) {});
             for (int base = 0; base < cnt && K <= top_k; base += 64)

@@ -21,5 +21,7 @@ for it in range(4):
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 16)()
     rc = lib.ssdhead_debug_phases(buf)
-    ph = list(buf)[:7]
-    print(it, " ".join(f"{names[i + 1]}={(ph[i + 1] - ph[i]) / 1965.0:.2f}us" for i in range(6)), f"total={(ph[6] - ph[0]) / 1965.0:.2f}us")
+    full = list(buf)
+    ph = full[:7]
+    print(it, " ".join(f"{names[i + 1]}={(ph[i + 1] - ph[i]) / 1965.0:.2f}us" for i in range(6)), f"total={(ph[6] - ph[0]) / 1965.0:.2f}us",
+          "| sweep: partition=%.2f classes=%.2f compact=%.2f" % tuple((full[i + 1] - full[i]) / 1965.0 for i in (8, 9, 10)))
