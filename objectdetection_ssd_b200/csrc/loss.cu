@@ -39,10 +39,17 @@
 
 namespace ssdhead {
 
+#ifdef SSDHEAD_PHASE_TIMES      // developer build: SM clock at the phase boundaries of the first image's mining CTA
+__device__ long long g_phase_loss[16];
+#define LPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_loss[i] = clock64(); } while (0)
+#else
+#define LPHASE(i) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // per-row cross entropy, -(x_c - max - log(sum exp(x - max))): the order ATen's log_softmax uses
 // ------------------------------------------------------------------------------------------------
-// FAST = true (streaming kernel only): exp through one ex2.approx per element (d <= 0; relative error
+// FAST = true (streaming kernel only): exp through one ex2.approx.ftz per element (d <= 0; relative error
 // <= (2 + 1.16|d|) ulp, i.e. an absolute error of ~2e-7 on log(sum)); the gradient and positive-row paths use expf.
 template <int C, bool FAST = false>
 __device__ __forceinline__ float row_cross_entropy(const float* __restrict__ row, int c)
@@ -57,7 +64,7 @@ __device__ __forceinline__ float row_cross_entropy(const float* __restrict__ row
 #pragma unroll
     for (int q = 0; q < C; ++q) {
         const float d = __fsub_rn(x[q], m);
-        s = __fadd_rn(s, FAST ? __expf(d) : expf(d));
+        s = __fadd_rn(s, FAST ? fast_exp_ftz(d) : expf(d));
         if (q == c) xc = d;
     }
     const float ce = __fsub_rn(logf(s), xc);
@@ -395,8 +402,7 @@ struct MineParams {
     int* npos_w;                 // [B+1] out
     unsigned long long* best_key;   // match workspace: per-gt arg-max keys (left zeroed)
     int* npos_acc;                  //                  natural positives per image (left zeroed)
-    unsigned int* arrive;           // workspace word: CTAs that published their count (left zeroed)
-    int* total_acc;                 // workspace word: batch positive count (left zeroed)
+    unsigned long long* arrive_total;  // workspace word: CTAs that published (high half) | batch positive count (low), left zeroed
     // cross-GPU exchange of the positive count and the loss sums over NVLink peer memory (xchg_R > 1):
     // every rank owns an exchange buffer of XCHG_WORDS 64-bit words that its PEERS write into (and it spins on).
     int xchg_R, xchg_rank;
@@ -434,7 +440,7 @@ constexpr int MN_GC = 64;        // gt boxes staged in shared memory
 constexpr int MN_CAND = 512;     // boundary-bin candidates ranked directly (one per thread)
 
 template <int C, bool GRADS, bool FIN>
-__global__ void __launch_bounds__(MN_T)
+__global__ void __launch_bounds__(MN_T, 2)    // two CTAs per SM: B = 256 images stay co-resident (cooperative launch)
 mine_kernel(const MineParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -468,6 +474,7 @@ mine_kernel(const MineParams p)
     }
     pdl_trigger();
     pdl_wait();                                              // CE, class bytes, best priors, positive counts are ready
+    LPHASE(0);
     int npos_b;
     if (FIN) {
         // ---- 0. forced-match override of THIS image (Losses.py:164-167), fused here so that no separate finaliser
@@ -502,14 +509,13 @@ mine_kernel(const MineParams p)
             s_fin_npos = nb;
             p.npos_w[b] = nb;
             p.npos_acc[b] = 0;
-            atomicAdd(p.total_acc, nb);
-            __threadfence();
-            const unsigned arrived = atomicAdd(p.arrive, 1u);
-            if (p.xchg_R > 1 && arrived == gridDim.x - 1u) {
+            // one 64-bit atomic carries both the arrival (high word) and the image's positives (low word): whoever sees
+            // gridDim.x arrivals sees the complete batch count in the same word - no fence between two atomics
+            const unsigned long long before = atomicAdd(p.arrive_total, (1ull << 32) | (unsigned long long)(unsigned)nb);
+            if (p.xchg_R > 1 && (unsigned)(before >> 32) == gridDim.x - 1u) {
                 // last image of this GPU: its positive count is complete -> one 64-bit store (seq << 32 | count) into
                 // the exchange buffer of every rank (own included) over NVLink
-                __threadfence();
-                const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)ld_cg_s32(p.total_acc);
+                const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)((unsigned)before + (unsigned)nb);
                 for (int q = 0; q < p.xchg_R; ++q)          // the word validates itself (seq in the high half): relaxed, pipelined stores
                     st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
             }
@@ -522,6 +528,7 @@ mine_kernel(const MineParams p)
         npos_b = p.npos[b];
     }
     const int* bprior = FIN ? p.best_prior_w : p.best_prior;
+    LPHASE(1);
     uint32_t kmax = 0u;
     const bool vec_ok = ((P & 3) == 0) && (((row0 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.ce) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.cls_u8) & 3) == 0);
@@ -561,6 +568,7 @@ mine_kernel(const MineParams p)
     if (lane == 0) atomicMax(&s_max, kmax);
     __syncthreads();
     kmax = s_max;
+    LPHASE(2);
 
     // ---- 2. the k largest keys, ties to the lower prior index (T4): mark them with bit 31 ----
     const long long kk = (long long)p.neg_ratio * (long long)npos_b;
@@ -705,6 +713,7 @@ mine_kernel(const MineParams p)
     __syncthreads();
 
     // ---- 4. the selected rows only: conf gradient, and for positives the L1 term + loc gradient ----
+    LPHASE(3);
     const uint32_t nsel = s_nsel;
     int npos_total;
     if (FIN) {
@@ -725,9 +734,9 @@ mine_kernel(const MineParams p)
                 if (spins >= (1u << 27)) *p.err_flag = 1;
                 s_total = tot;
             } else {
-                while (ld_cg_s32(reinterpret_cast<const int*>(p.arrive)) < (int)gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
-                __threadfence();
-                s_total = ld_cg_s32(p.total_acc);
+                unsigned long long w;
+                while ((unsigned)((w = ld_cg_u64(p.arrive_total)) >> 32) < gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
+                s_total = (int)(unsigned)w;
             }
         }
         __syncthreads();
@@ -735,19 +744,50 @@ mine_kernel(const MineParams p)
     } else {
         npos_total = *p.npos_norm;
     }
+    LPHASE(4);
     const float nrm = (float)npos_total;
     const float gs_conf = __fdiv_rn(1.0f, nrm);
     const float gs_loc = __fdiv_rn(1.0f, __fmul_rn(4.0f, nrm));
-    for (uint32_t idx = t; idx < nsel; idx += MN_T) {
-        const int j = (int)s_list[idx];
-        const int c = (int)s_cls[j];
+    // The rows are scattered over the image, 84 bytes each: a thread-per-row access touches 32 rows per instruction
+    // (32 sectors for 128 useful bytes).  With gradients the warp therefore moves its 32 rows through shared memory:
+    // flat, coalesced loads of the 32 x 21 logits, thread-per-row arithmetic in place, flat coalesced stores - about
+    // seven times fewer L2 transactions on the latency chain every CTA of the step waits for.  The staging area is the
+    // key + histogram region, dead since the selection.
+    const bool staged = GRADS && (size_t)P * 4 + (size_t)MN_BINS * 4 >= (size_t)MN_W * 32 * C * 4;
+    float* wstage = reinterpret_cast<float*>(smem_raw) + warp * (32 * C);
+    for (uint32_t base = 0; base < nsel; base += MN_T) {
+        const uint32_t idx = base + t;
+        const bool valid = idx < nsel;
+        const uint32_t wbase = base + (uint32_t)warp * 32u;
+        const int nrw = wbase < nsel ? (int)min(32u, nsel - wbase) : 0;
+        const int j = valid ? (int)s_list[idx] : 0;
+        if (staged) {
+            // element e = lane + 32 i of the warp's 32 x C block belongs to row e / C, whose index lane e / C holds;
+            // all loads are issued before the first shared-memory store (which the compiler must assume may alias)
+            float v[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int e = lane + 32 * i, r = e / C, q = e - r * C;
+                const int jr = __shfl_sync(FULL, j, r);
+                v[i] = r < nrw ? __ldg(p.conf + (row0 + jr) * C + q) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) wstage[lane + 32 * i] = v[i];
+            __syncwarp();
+        }
+        const int c = valid ? (int)s_cls[j] : p.bg_class;
         const bool pos = c != p.bg_class;
         float x[C];
         float4 pb, pc, l;
-        if (GRADS || pos) {
-            const float* row = p.conf + (row0 + j) * C;
+        if (valid && (GRADS || pos)) {
+            if (staged) {
 #pragma unroll
-            for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
+                for (int q = 0; q < C; ++q) x[q] = wstage[lane * C + q];
+            } else {
+                const float* row = p.conf + (row0 + j) * C;
+#pragma unroll
+                for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
+            }
         }
         if (pos) {                                   // issue every independent load before the first use
             pb = p.pri_xyxy[j];
@@ -761,7 +801,7 @@ mine_kernel(const MineParams p)
             acc_ce += (double)ce;
             if (p.ce_tap) p.ce_tap[row0 + j] = ce;
         }
-        if (GRADS) {
+        if (GRADS && valid) {
             float m = x[0];
 #pragma unroll
             for (int q = 1; q < C; ++q) m = fmaxf(m, x[q]);
@@ -769,10 +809,29 @@ mine_kernel(const MineParams p)
 #pragma unroll
             for (int q = 0; q < C; ++q) { x[q] = expf(__fsub_rn(x[q], m)); s = __fadd_rn(s, x[q]); }
             const float inv = __fdiv_rn(1.0f, s);
-            float* grow = p.grad_conf + (row0 + j) * C;
+            if (staged) {
 #pragma unroll
-            for (int q = 0; q < C; ++q)
-                grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
+                for (int q = 0; q < C; ++q)
+                    wstage[lane * C + q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
+            } else {
+                float* grow = p.grad_conf + (row0 + j) * C;
+#pragma unroll
+                for (int q = 0; q < C; ++q)
+                    grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
+            }
+        }
+        if (staged) {
+            __syncwarp();
+            float v[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) v[i] = wstage[lane + 32 * i];
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int e = lane + 32 * i, r = e / C, q = e - r * C;
+                const int jr = __shfl_sync(FULL, j, r);
+                if (r < nrw) p.grad_conf[(row0 + jr) * C + q] = v[i];
+            }
+            __syncwarp();
         }
         if (pos) {
             // which gt: the forced one (T3: highest index wins) or the natural argmax (T1)
@@ -804,6 +863,7 @@ mine_kernel(const MineParams p)
         }
     }
 
+    LPHASE(5);
     // ---- 5. loss sums: per-image partial -> the last CTA reduces all partials in a fixed order ----
     acc_l1 = warp_sum(acc_l1);
     acc_ce = warp_sum(acc_ce);
@@ -822,6 +882,7 @@ mine_kernel(const MineParams p)
         s_is_last = (done == gridDim.x - 1u) ? 1 : 0;
     }
     __syncthreads();
+    LPHASE(6);
     if (s_is_last) {
         __threadfence();
         double a = 0.0, c = 0.0;
@@ -863,9 +924,8 @@ mine_kernel(const MineParams p)
             p.losses[1] = (float)(c / N);
             *p.done_counter = 0u;
             if (FIN) {                   // every CTA has read the total (it did so before it reported done)
-                p.npos_w[p.B] = (p.xchg_R > 1) ? ld_cg_s32(p.total_acc) : npos_total;    // this rank's own count
-                *p.arrive = 0u;
-                *p.total_acc = 0;
+                p.npos_w[p.B] = (p.xchg_R > 1) ? (int)(unsigned)ld_cg_u64(p.arrive_total) : npos_total;    // this rank's own count
+                *p.arrive_total = 0ull;
             }
         }
     }
@@ -1129,7 +1189,7 @@ int ssdhead_mine(const float* loc, const float* conf,
     prm.ce = ce ? ce : ws_ce(ws, B);
     prm.ce_tap = ce;
     prm.cls_rw = nullptr; prm.best_prior_w = nullptr; prm.npos_w = nullptr; prm.best_key = nullptr; prm.npos_acc = nullptr;
-    prm.arrive = nullptr; prm.total_acc = nullptr;
+    prm.arrive_total = nullptr;
     prm.xchg_R = 0; prm.xchg_rank = 0; prm.xchg_seq = 0; prm.xchg_peers = nullptr; prm.xchg_local = nullptr; prm.err_flag = nullptr;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
     return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
@@ -1174,7 +1234,7 @@ static int multibox_step_impl(const float* loc, const float* conf,
     prm.ce_tap = ce;
     prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
     prm.best_key = best_key; prm.npos_acc = npos_acc;
-    prm.arrive = image_counter + 1; prm.total_acc = (int*)(image_counter + 2);
+    prm.arrive_total = (unsigned long long*)(image_counter + 2);   // 8-byte aligned word of the 16-byte tail
     prm.xchg_R = R; prm.xchg_rank = rank; prm.xchg_seq = seq;
     prm.xchg_peers = (unsigned long long* const*)peers_dev; prm.xchg_local = (unsigned long long*)xchg_local; prm.err_flag = err_flag;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
@@ -1224,5 +1284,9 @@ int ssdhead_scale_grads(float* grad_loc, size_t n_loc, float* grad_conf, size_t 
     SSD_LAUNCH_CHECK();
     return 0;
 }
+
+#ifdef SSDHEAD_PHASE_TIMES
+int ssdhead_debug_phases_loss(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, ssdhead::g_phase_loss, sizeof(long long) * 16); }
+#endif
 
 }  // extern "C"

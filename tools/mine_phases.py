@@ -1,0 +1,32 @@
+"""Developer tool: SM-clock phase times of the first image's mining CTA (mine_kernel).
+
+Needs a developer build:  SSDHEAD_NVCC_EXTRA=-DSSDHEAD_PHASE_TIMES python -m objectdetection_ssd_b200.build --force
+"""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from objectdetection_ssd_b200 import synth, priors as PR, _lib
+from objectdetection_ssd_b200.ctx import SSDHeadContext
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+pri = PR.make_priors(); P = pri.shape[0]
+ctx = SSDHeadContext(pri.numpy(), max_batch=B)
+gb, gc = synth.make_gt(1, B); gx, gcl, off = synth.pack_gt(gb, gc)
+loc, conf = synth.make_head(1, B, P)
+d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+tgx, tgc, toff = d(gx), d(gcl), d(off)
+sets = [(d(loc) + i, d(conf) + 0.01 * i) for i in range(3)]
+sums = torch.empty(2, dtype=torch.float64, device="cuda"); losses = torch.empty(2, device="cuda")
+gl = torch.empty_like(sets[0][0]); gcf = torch.empty_like(sets[0][1])
+st = torch.cuda.current_stream().cuda_stream
+lib = _lib.load()
+names = ["finalise", "keys", "select+list", "wait total", "grad rows", "publish"]
+for it in range(5):
+    l, c = sets[it % 3]
+    ctx.loss_dev(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
+                 sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 16)()
+    lib.ssdhead_debug_phases_loss(buf)
+    ph = list(buf)[:7]
+    print(it, " ".join(f"{names[i]}={(ph[i + 1] - ph[i]) / 1965.0:.2f}us" for i in range(6)), f"total={(ph[6] - ph[0]) / 1965.0:.2f}us")
