@@ -136,3 +136,64 @@ def test_detect_end_to_end_close():
         assert torch.allclose(gp[j], rp[h], rtol=1e-5, atol=1e-8)
         assert torch.allclose(gb[j], rb[h], rtol=1e-5, atol=1e-6)
     assert mism <= 2 * B, f"{mism} detections differ (expected only ulp-level threshold flips)"
+
+
+def _clustered_inputs(seed, B, pri, classes, jitter=0.02, frac=0.5):
+    """Boxes = the priors with a small jitter (neighbouring priors overlap heavily -> strong suppression);
+    probabilities only in ``classes`` for a random ``frac`` of the priors."""
+    g = torch.Generator().manual_seed(seed)
+    P = pri.shape[0]
+    boxes = pri.unsqueeze(0).repeat(B, 1, 1).clone()
+    boxes[..., :2] += jitter * torch.randn(B, P, 2, generator=g)
+    boxes[..., 2:] *= torch.exp(jitter * torch.randn(B, P, 2, generator=g))
+    probs = torch.zeros(B, P, 21)
+    for c in classes:
+        on = torch.rand(B, P, generator=g) < frac
+        probs[..., c] = torch.where(on, 0.05 + 0.9 * torch.rand(B, P, generator=g), torch.zeros(()))
+    probs[..., 20] = 1.0 - probs[..., :20].sum(-1).clamp(max=1.0)
+    return boxes.contiguous(), probs.contiguous()
+
+
+def test_detect_heavy_suppression_runs_through_every_slice():
+    """Two classes, ~4.4k overlapping candidates each: the sweep needs many slices (the later ones larger than the
+    shared-memory slice buffer -> global-memory path) and ends with fewer than top_k boxes (class-major output)."""
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    boxes, probs = _clustered_inputs(41, 2, pri, classes=(2, 11))
+    ref = _oracle_stage(boxes, probs, 0.05, 0.45, 200)
+    out = detect_from_scores(_head(pri), boxes, probs, 0.05, 0.45, 200)
+    torch.cuda.synchronize()
+    _check_exact(out, ref, 200)
+    # the same candidates with a top_k small enough to stop early, and one large enough to need the whole list
+    for tk in (1, 37, 600):
+        out = detect_from_scores(_head(pri), boxes, probs, 0.05, 0.45, tk)
+        torch.cuda.synchronize()
+        _check_exact(out, _oracle_stage(boxes, probs, 0.05, 0.45, tk), tk)
+
+
+def test_detect_quantised_scores_tie_across_classes_and_priors():
+    """Probabilities rounded to multiples of 1/32: thousands of exact ties inside and across classes (T5, T7) and
+    crowded sort bins."""
+    from objectdetection_ssd_b200.head import detect_from_scores
+    pri = H.priors()
+    loc, conf = H.detect_inputs(42, 2, pri.shape[0], bg_bias=3.0)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(2)])
+    probs = torch.round(F.softmax(conf, dim=2) * 32) / 32
+    out = detect_from_scores(_head(pri), boxes, probs, 1 / 32, 0.45, 200)
+    torch.cuda.synchronize()
+    _check_exact(out, _oracle_stage(boxes, probs, 1 / 32, 0.45, 200), 200)
+
+
+def test_detect_unaligned_prior_count_takes_the_plain_load_path():
+    """P = 1001: image rows are not 16-byte aligned, so the score kernel cannot use its bulk copy."""
+    from objectdetection_ssd_b200.head import detect_from_scores, detect
+    pri = H.priors()[:1001].contiguous()
+    loc, conf = H.detect_inputs(43, 3, 1001, bg_bias=3.0)
+    boxes = torch.stack([O.decode(loc[i], pri) for i in range(3)])
+    probs = F.softmax(conf, dim=2)
+    out = detect_from_scores(_head(pri), boxes, probs, 0.02, 0.45, 50)
+    torch.cuda.synchronize()
+    _check_exact(out, _oracle_stage(boxes, probs, 0.02, 0.45, 50), 50)
+    out2 = detect(_head(pri), loc, conf, 0.02, 0.45, 50)             # own softmax + decode on the same odd shape
+    torch.cuda.synchronize()
+    assert (out2["cnt"].cpu() == out["cnt"].cpu()).all()
