@@ -243,6 +243,19 @@ int ssdhead_voc_ap(const float* det_boxes_xyxy_dev, const int32_t* det_cls_dev, 
                    int num_images, int num_fg, float iou_thr, const double* recall_levels_dev /*[11]*/,
                    double* ap_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* ---- gt collate: Dataset.py:24-36 (difficult filter, standardisation) + train_function.py:62-63 (B small copies)
+ * + Losses.py:129-130 (cat, cumsum) in one HOST pass ------------------------------------------------------------
+ * B ragged host arrays -> the packed gt layout every entry point above takes: boxes [sumG,4], classes [sumG] fp32,
+ * offsets int32 [B+1].  counts[i] boxes of image i are read from boxes[i] (xyxy, [counts[i],4]) and classes[i];
+ * `difficult` (nullable, or null per image) drops boxes whose flag is non-zero unless keep_difficult != 0
+ * (Dataset.py:28-30); `img_wh` (nullable, [B,2] = w,h) divides pixel boxes by (w,h,w,h) in fp32 (Dataset.py:35-36).
+ * The outputs are host buffers with room for `capacity` boxes (page-locked memory from ssdhead_host_alloc makes the
+ * single copy to the device asynchronous).  Returns sumG >= 0, SSDHEAD_E_WORKSPACE if `capacity` is too small, or
+ * SSDHEAD_E_STATE if an image is left without a box (the reference fails on such a batch, Losses.py:153). */
+int ssdhead_pack_gt(const float* const* boxes_host, const float* const* classes_host, const uint8_t* const* difficult_host,
+                    const int32_t* counts, int B, int keep_difficult, const float* img_wh_host,
+                    float* out_xyxy_host, float* out_cls_host, int32_t* out_off_host, int capacity);
+
 /* ---- host-buffer front end (pinned staging + streams owned by the context) -----------
  * The same path for callers whose tensors live in host memory (what the reference's CPU
  * path sees).  Copies are pipelined against the kernels in image chunks. */

@@ -14,6 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libssdhead.so")
 
 WS_MATCH, WS_LOSS, WS_DETECT, WS_NMS = 0, 1, 2, 3
+E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN, E_STATE = -1, -2, -3, -4, -5
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -61,6 +62,7 @@ SIGNATURES = {
     "ssdhead_ctx_multibox_loss_end": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "ssdhead_ctx_detect_host": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ssdhead_pack_gt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
 }
 
 _lib = None

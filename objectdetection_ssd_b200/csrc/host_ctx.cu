@@ -70,6 +70,38 @@ static const int kMaxChunks = 16;
 
 extern "C" {
 
+// gt collate on the host (Dataset.py:24-36, train_function.py:62-63, Losses.py:129-130): see ssdhead.h
+int ssdhead_pack_gt(const float* const* boxes, const float* const* classes, const uint8_t* const* difficult,
+                    const int32_t* counts, int B, int keep_difficult, const float* img_wh,
+                    float* out_xyxy, float* out_cls, int32_t* out_off, int capacity)
+{
+    if (B < 0 || capacity < 0 || !out_off || (B > 0 && (!boxes || !classes || !counts))) return SSDHEAD_E_BADARG;
+    int n = 0;
+    out_off[0] = 0;
+    for (int i = 0; i < B; ++i) {
+        if (counts[i] < 0 || (counts[i] > 0 && (!boxes[i] || !classes[i]))) return SSDHEAD_E_BADARG;
+        const uint8_t* dif = (difficult && !keep_difficult) ? difficult[i] : nullptr;
+        const int before = n;
+        for (int g = 0; g < counts[i]; ++g) {
+            if (dif && dif[g]) continue;                                        // Dataset.py:28-30
+            if (n >= capacity || !out_xyxy || !out_cls) return SSDHEAD_E_WORKSPACE;
+            const float* bx = boxes[i] + 4 * (size_t)g;
+            float* o = out_xyxy + 4 * (size_t)n;
+            if (img_wh) {                                                       // Dataset.py:35-36: bboxes / [w, h, w, h]
+                const float w = img_wh[2 * i], h = img_wh[2 * i + 1];
+                o[0] = bx[0] / w; o[1] = bx[1] / h; o[2] = bx[2] / w; o[3] = bx[3] / h;
+            } else {
+                o[0] = bx[0]; o[1] = bx[1]; o[2] = bx[2]; o[3] = bx[3];
+            }
+            out_cls[n] = classes[i][g];
+            ++n;
+        }
+        if (n == before) return SSDHEAD_E_STATE;                                // an image without objects (Losses.py:153)
+        out_off[i + 1] = n;
+    }
+    return n;
+}
+
 void* ssdhead_host_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -1017,6 +1017,28 @@ static int launch_mine_fin(MineParams prm, cudaStream_t st)
     int per_sm = 0;
     SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmn, MN_T, smem_mn));
     if ((long long)per_sm * num_sms() < prm.B) return 1;
+    // cooperative (co-residency guaranteed) AND programmatic stream serialization (the grid may become resident while
+    // the streaming kernel drains; it waits in pdl_wait()).  Runtimes that refuse the combination get the plain
+    // cooperative launch.
+    static int combo = getenv("SSDHEAD_COOP_PDL") ? atoi(getenv("SSDHEAD_COOP_PDL")) : 1;
+    if (combo) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(prm.B);
+        cfg.blockDim = dim3(MN_T);
+        cfg.dynamicSmemBytes = smem_mn;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kmn, prm);
+        if (e == cudaSuccess) { count_launch(); return 0; }
+        (void)cudaGetLastError();
+        combo = 0;
+    }
     void* args[] = {&prm};
     SSD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kmn, dim3(prm.B), dim3(MN_T), args, smem_mn, st));
     count_launch();

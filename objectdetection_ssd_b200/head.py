@@ -57,6 +57,16 @@ class PackedGT:
         for n in counts:
             off.append(off[-1] + n)
         self.off_host = off
+        on_host = all(b.device.type == "cpu" for b in boxes) and all(c.device.type == "cpu" for c in classes)
+        if on_host and torch.cuda.is_available():
+            # host lists (what a DataLoader hands over): one native pass into page-locked memory, one copy per array
+            from .collate import collate_gt
+            self._staging = collate_gt(boxes, classes)           # keeps the pinned block alive until the copies ran
+            hb, hc, ho = self._staging
+            self.boxes = torch.from_numpy(hb).to(dev, non_blocking=True)
+            self.classes = torch.from_numpy(hc).to(dev, non_blocking=True)
+            self.off = torch.from_numpy(ho).to(dev, non_blocking=True)
+            return
         self.boxes = torch.cat([b.reshape(-1, 4) for b in boxes]).to(device=dev, dtype=torch.float32).contiguous()
         self.classes = torch.cat([c.reshape(-1) for c in classes]).to(device=dev, dtype=torch.float32).contiguous()
         self.off = torch.tensor(off, dtype=torch.int32).pin_memory().to(dev, non_blocking=True) \

@@ -393,3 +393,28 @@ def voc_ap(det_boxes, det_classes, det_scores, gt_boxes, gt_classes, num_fg: int
         vals = [precision[recall >= lv].max() if (recall >= lv).any() else 0.0 for lv in levels]
         ap[c] = float(np.mean(vals))
     return ap
+
+
+# --------------------------------------------------------------------------- gt collate
+def collate_gt(boxes, classes, difficult=None, keep_difficult=True, img_wh=None):
+    """The reference's gt handling between the dataset and the loss, restated with its own torch ops:
+    ``Dataset.py:28-30`` (drop difficult boxes), ``Dataset.py:35-36`` (``bboxes / FloatTensor([w, h, w, h])``),
+    ``Losses.py:129-130`` (``torch.cat`` + cumulative offsets).  Returns (boxes [sumG,4], classes [sumG] float32,
+    offsets int32 [B+1]); an image left without a box raises IndexError (``Losses.py:153`` fails on it)."""
+    out_b, out_c, off = [], [], [0]
+    for i, (b, c) in enumerate(zip(boxes, classes)):
+        b = torch.as_tensor(b, dtype=torch.float32).reshape(-1, 4)
+        c = torch.as_tensor(c, dtype=torch.float32).reshape(-1)
+        if difficult is not None and not keep_difficult:
+            keep = torch.as_tensor(difficult[i]).reshape(-1) == 0
+            b, c = b[keep], c[keep]
+        if img_wh is not None:
+            w, h = float(img_wh[i][0]), float(img_wh[i][1])
+            b = b / torch.FloatTensor([w, h, w, h]).unsqueeze(0)
+        if b.shape[0] == 0:
+            raise IndexError(f"image {i} has no ground-truth box")
+        out_b.append(b)
+        out_c.append(c)
+        off.append(off[-1] + b.shape[0])
+    return torch.cat(out_b), torch.cat(out_c), torch.tensor(off, dtype=torch.int32)
+

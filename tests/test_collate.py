@@ -1,0 +1,70 @@
+"""CPU: the native gt collate (ssdhead_pack_gt) against the oracle's restatement of
+Dataset.py:28-36 + Losses.py:129-130 - bit-exact (plain fp32 copies and divisions)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ssd_oracle as O
+
+
+def _ragged(seed, B, lo=1, hi=12, pixels=False):
+    g = np.random.default_rng(seed)
+    boxes, classes, diff, wh = [], [], [], []
+    for _ in range(B):
+        n = int(g.integers(lo, hi + 1))
+        w, h = float(g.integers(200, 640)), float(g.integers(200, 640))
+        xy = g.uniform(0, 0.7, (n, 2)).astype(np.float32)
+        sz = g.uniform(0.05, 0.3, (n, 2)).astype(np.float32)
+        b = np.concatenate([xy, xy + sz], 1)
+        if pixels:
+            b = (b * np.array([w, h, w, h], np.float32)).round()
+        boxes.append(torch.from_numpy(b.astype(np.float32)))
+        classes.append(torch.from_numpy(g.integers(0, 20, n).astype(np.float32)))
+        d = (g.uniform(size=n) < 0.3).astype(np.uint8)
+        d[int(g.integers(0, n))] = 0                      # at least one easy box per image
+        diff.append(torch.from_numpy(d))
+        wh.append((w, h))
+    return boxes, classes, diff, np.array(wh, np.float32)
+
+
+@pytest.mark.parametrize("keep_difficult,pixels", [(True, False), (False, False), (False, True), (True, True)])
+def test_collate_matches_the_reference_ops(keep_difficult, pixels):
+    from objectdetection_ssd_b200.collate import collate_gt
+    boxes, classes, diff, wh = _ragged(5, 33, pixels=pixels)
+    rb, rc, ro = O.collate_gt(boxes, classes, diff, keep_difficult, wh if pixels else None)
+    gb, gc, go = collate_gt(boxes, classes, diff, keep_difficult, wh if pixels else None)
+    assert np.array_equal(go, ro.numpy())
+    assert np.array_equal(gb.view(np.uint32), rb.numpy().view(np.uint32))           # same bits, incl. the fp32 division
+    assert np.array_equal(gc, rc.numpy())
+
+
+def test_collate_accepts_numpy_lists_and_int_classes():
+    from objectdetection_ssd_b200.collate import collate_gt
+    boxes, classes, _, _ = _ragged(6, 4)
+    gb, gc, go = collate_gt([b.numpy() for b in boxes], [c.numpy().astype(np.int64) for c in classes])
+    rb, rc, ro = O.collate_gt(boxes, classes)
+    assert np.array_equal(gb, rb.numpy()) and np.array_equal(gc, rc.numpy()) and np.array_equal(go, ro.numpy())
+
+
+def test_collate_image_without_boxes_raises_like_the_reference():
+    from objectdetection_ssd_b200.collate import collate_gt
+    boxes, classes, diff, _ = _ragged(7, 3)
+    boxes[1] = torch.zeros(0, 4)
+    classes[1] = torch.zeros(0)
+    with pytest.raises(IndexError):
+        collate_gt(boxes, classes)
+    boxes, classes, diff, _ = _ragged(8, 3)
+    diff[2][:] = 1                                        # every box of image 2 is difficult
+    with pytest.raises(IndexError):
+        collate_gt(boxes, classes, diff, keep_difficult=False)
+    assert collate_gt(boxes, classes, diff, keep_difficult=True)[2][-1] == sum(b.shape[0] for b in boxes)
+
+
+def test_collate_feeds_the_packed_layout_of_synth():
+    from objectdetection_ssd_b200 import synth
+    from objectdetection_ssd_b200.collate import collate_gt
+    gb, gc = synth.make_gt(3, 16)
+    a = synth.pack_gt(gb, gc)
+    b = collate_gt(gb, gc, pinned=False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
