@@ -203,6 +203,7 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
         if (total) chunk = atomicAdd(&cand_cnt[b], total);
     }
     const float* wrow = s_conf + warp * (32 * C);
+#pragma unroll 1                         // ~3 trips: an unrolled body only adds a preamble
     for (unsigned j = lane; j < wtotal; j += 32) {
         const unsigned lq = st_q[j];
         const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
@@ -235,6 +236,7 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
     __syncthreads();
     if (base == 0xffffffffu) return;
     unsigned long long* seg = cand + (size_t)b * capI + base;
+#pragma unroll 1
     for (unsigned j = lane; j < wtotal; j += 32) {
         const unsigned lq = st_q[j];
         const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
