@@ -53,7 +53,8 @@ const char* ssdhead_error_string(int code);
 uint64_t    ssdhead_launch_count(void);
 
 /* Bytes of device workspace an entry point needs.  `n` = total gt count (MATCH),
- * max candidates per (image,class) the caller wants to allow (DETECT/NMS; 0 = P). */
+ * max candidates per (image,class) the caller wants to allow (DETECT/NMS; 0 = P: three key buffers of
+ * B * (C-1) * P * 8 bytes - 4.2 MB per SSD300 image - plus a small directory). */
 size_t ssdhead_workspace_bytes(int which, int B, int P, int C, int n);
 
 /* ---- box format / offsets: Util.py:93-96, 57-63, 98-102, 86-91 ------------------- */
@@ -207,13 +208,16 @@ int ssdhead_scale_grads(float* grad_loc_dev, size_t n_loc, float* grad_conf_dev,
  * class-major, and if more than top_k survive take the global top_k by descending prob
  * (ties -> earlier class-major position, T7).  Boxes are corner form, NOT clamped; fractional,
  * or multiplied by the image size when `img_wh_dev` [B,2] (w,h) is given (Losses.py:87-89).
- * `max_candidates` caps the candidate list of one (image, class) to bound the workspace
- * (0 = P = no cap, the reference's behaviour); if a list overflows, out_cnt[b] = -1.
- * Only the first top_k boxes kept in a class can reach the global top-k, so the NMS sweep of
- * a class stops once it has kept top_k boxes - the output is identical to the full sweep.
+ * `max_candidates` bounds the workspace: an image's candidate list holds (C-1) * max_candidates keys
+ * (0 = P per class = every candidate, the reference's behaviour); if it overflows, out_cnt[b] = -1.
+ * The per-class sweeps are run as ONE sweep per image in descending (prob, lower class, lower prior)
+ * order with suppression tested inside a class only - the same keep/suppress decisions, the kept boxes
+ * already in the order of the final global top-k - which stops once top_k + 1 boxes are kept: the
+ * output is identical to the reference's full per-class sweeps.
  * Outputs: out_boxes [B,top_k,4], out_prob [B,top_k], out_cls int32 [B,top_k],
  *          out_prior int32 [B,top_k] (prior id of each detection; nullable), out_cnt int32 [B].
- * Three kernels (score/decode/threshold; per-(image,class) sort + NMS; per-image top-k).
+ * Two kernels (softmax/threshold/candidate keys; per-image slice sort + class-parallel NMS + output).
+ * P <= 131072, top_k <= ~1400.  Probabilities given to the _from_scores twin must be >= 0.
  * The workspace must be zero-filled before its FIRST use; every call leaves its counters zeroed. */
 int ssdhead_detect(const float* loc_dev, const float* conf_dev, const float* pri_cxcywh_dev,
                    int B, int P, int C, float min_score, float iou_thr, int top_k,
