@@ -247,6 +247,40 @@ int ssdhead_voc_ap(const float* det_boxes_xyxy_dev, const int32_t* det_cls_dev, 
                    int num_images, int num_fg, float iou_thr, const double* recall_levels_dev /*[11]*/,
                    double* ap_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* ---- head outputs per pyramid level: Model.py:212-235 without the permute/cat round trip -----
+ * The reference permutes each of its 12 conv outputs to NHWC, copies it (`.contiguous()`) and concatenates the six
+ * levels into loc [B,8732,4] / conf [B,8732,21].  An NHWC (channels_last) conv output [B,H,W,A*21] already IS the row
+ * layout [B, n_l, 21] of its level (n_l = H*W*A priors, cell-major then anchor - the prior order of Util.py:105-137),
+ * so these entry points read the level tensors in place and write the gradients per level in the same layout:
+ * no concatenated tensor exists in either direction.  count[l] priors per image in level l (sum = P), conf[l]
+ * [B, count[l], C], loc[l] [B, count[l], 4], grads likewise (all or none), every pointer 16-byte aligned. */
+#define SSDHEAD_MAX_LEVELS 8
+typedef struct ssdhead_levels {
+    int32_t      num_levels;
+    int32_t      count[SSDHEAD_MAX_LEVELS];
+    const float* conf[SSDHEAD_MAX_LEVELS];
+    const float* loc[SSDHEAD_MAX_LEVELS];
+    float*       grad_conf[SSDHEAD_MAX_LEVELS];
+    float*       grad_loc[SSDHEAD_MAX_LEVELS];
+} ssdhead_levels;
+
+/* ssdhead_multibox_step on per-level tensors: same two kernels, same outputs (the class map, best priors and counts
+ * keep the global [B,P] prior indexing), results bit-identical to the concatenated call. */
+int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
+                                 const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                 const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                                 double* sums_dev, float* losses_dev,
+                                 uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                                 void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                                 void* stream);
+/* ssdhead_detect on per-level tensors (grad pointers unused). */
+int ssdhead_detect_levels(const ssdhead_levels* levels, const float* pri_cxcywh_dev,
+                          int B, int P, int C, float min_score, float iou_thr, int top_k,
+                          const float* img_wh_dev, int max_candidates,
+                          float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
+                          int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- gt collate: Dataset.py:24-36 (difficult filter, standardisation) + train_function.py:62-63 (B small copies)
  * + Losses.py:129-130 (cat, cumsum) in one HOST pass ------------------------------------------------------------
  * B ragged host arrays -> the packed gt layout every entry point above takes: boxes [sumG,4], classes [sumG] fp32,

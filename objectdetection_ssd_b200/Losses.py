@@ -22,7 +22,8 @@ from . import Util as _U
 from .Util import (class_to_label, label_to_class, create_priors_ssd300, xywh_to_xyxy, xyxy_to_xywh,       # noqa: F401
                    gcxgcy_to_cxcy, get_offsets_coords, find_intersection, get_jaccard_tensor1,
                    get_jaccard_tensor11, map_prior_to_bb, subsampling)
-from .head import MultiboxHead, PackedGT, multibox_loss, detect as _detect
+from .head import (MultiboxHead, PackedGT, multibox_loss, detect as _detect, multibox_loss_levels,
+                   detect_levels as _detect_levels)
 from .priors import cxcywh_to_xyxy_host
 
 ancs_xywh = create_priors_ssd300()
@@ -89,6 +90,34 @@ def ssd_old(outputs, tr_classes, tr_bboxs):
         lbb = lbb + lbb_
         lc = lc + lc_
     return lbb / bs, lc / bs
+
+
+def head_levels(loc_maps, conf_maps, num_classes=21):
+    """The twelve conv outputs of the head (``Model.py:212-233``: per level a loc map [B, A*4, H, W] and a conf map
+    [B, A*21, H, W]) as per-level row tensors [B, H*W*A, 4] / [B, H*W*A, 21].  ``permute(0, 2, 3, 1)`` is what the
+    reference does; for a channels_last (NHWC) conv output it is a pure view, so neither the ``.contiguous()`` copy nor
+    the ``torch.cat`` of Model.py:234-235 ever happens."""
+    locs = [m.permute(0, 2, 3, 1).reshape(m.shape[0], -1, 4) for m in loc_maps]
+    confs = [m.permute(0, 2, 3, 1).reshape(m.shape[0], -1, num_classes) for m in conf_maps]
+    return locs, confs
+
+
+def ssd_levels(outputs, tr_classes, tr_bboxs):
+    """``ssd`` on per-level head tensors: ``outputs`` = (list of loc [B, n_l, 4], list of conf
+    [B, n_l, 21]) - e.g. from ``head_levels`` - in the prior order of ``create_priors_ssd300``.  Same value and
+    gradients as ``ssd(torch.cat(...))``, bit for bit, without ever building the concatenated tensors."""
+    locs, confs = outputs
+    head = _head(_dev_of(confs[0]))
+    _last.clear()
+    _last.update(head=head, boxes=[b.detach() for b in tr_bboxs], classes=[c.detach() for c in tr_classes])
+    return multibox_loss_levels(head, list(locs), list(confs), list(tr_bboxs), list(tr_classes))
+
+
+def inference_batch_levels(loc_levels, conf_levels, top_k=200, min_score=0.2, iou_threshold=0.45, img_wh=None,
+                           max_candidates=0):
+    """``inference_batch`` on per-level head tensors."""
+    return _detect_levels(_head(_dev_of(conf_levels[0])), list(loc_levels), list(conf_levels), min_score, iou_threshold,
+                          top_k, img_wh, max_candidates)
 
 
 def inference_batch(loc, conf, top_k=200, min_score=0.2, iou_threshold=0.45, img_wh=None, max_candidates=0):

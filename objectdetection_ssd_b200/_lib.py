@@ -63,7 +63,19 @@ SIGNATURES = {
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "ssdhead_ctx_detect_host": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_pack_gt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
+    "ssdhead_multibox_step_levels": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _sz, _vp, _sz, _vp]),
+    "ssdhead_detect_levels": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
+
+MAX_LEVELS = 8
+
+
+class Levels(C.Structure):
+    """``ssdhead_levels`` of include/ssdhead.h: per-pyramid-level head tensors."""
+    _fields_ = [("num_levels", C.c_int32), ("count", C.c_int32 * MAX_LEVELS),
+                ("conf", C.c_void_p * MAX_LEVELS), ("loc", C.c_void_p * MAX_LEVELS),
+                ("grad_conf", C.c_void_p * MAX_LEVELS), ("grad_loc", C.c_void_p * MAX_LEVELS)]
 
 _lib = None
 

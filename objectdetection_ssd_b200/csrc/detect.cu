@@ -69,7 +69,7 @@ static inline int detect_tiles(int P) { return (P + SC_T - 1) / SC_T; }
 static size_t detect_ws_layout(int B, int P, int C, int n, DetectWs* w, void* base)
 {
     const size_t capI = (size_t)detect_cap_image(P, C, n);
-    const size_t T = (size_t)detect_tiles(P);
+    const size_t T = (size_t)detect_tiles(P) + SSDHEAD_MAX_LEVELS;   // per-level calls: at most one partial tile more per level
     size_t off = 0;
     char* b = (char*)base;
     auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return b ? (void*)(b + o) : nullptr; };
@@ -106,13 +106,25 @@ __device__ __forceinline__ int coarse_rank(unsigned pbits) {
     return min(CBINS - 1, max(0, d));
 }
 
+// Head outputs given per pyramid level (ssdhead_detect_levels; see ssdhead.h): level l holds cnt[l] priors per image,
+// priors start[l] .. start[l+1]-1 of the global order; an image's score tiles tile0[l] .. tile0[l+1]-1 belong to level l.
+constexpr int MAX_LEVELS = SSDHEAD_MAX_LEVELS;
+struct DetLevels {
+    int n;
+    int cnt[MAX_LEVELS];
+    int start[MAX_LEVELS + 1];
+    int tile0[MAX_LEVELS + 1];
+    const float* conf[MAX_LEVELS];
+    const float* loc[MAX_LEVELS];
+};
+
 // ------------------------------------------------------------------------------------------------
-template <int C, bool FROM_SCORES>
-__global__ void __launch_bounds__(SC_T)
-detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int capI,
-                    unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
-                    unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
-                    unsigned int* __restrict__ overflow)
+template <int C, bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_score_body(const float* __restrict__ conf, int P, float min_score, int capI,
+                  unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
+                  unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
+                  unsigned int* __restrict__ overflow, const DetLevels* __restrict__ dl)
 {
     constexpr int NF = C - 1;
     constexpr int NW = SC_T / 32;
@@ -126,9 +138,18 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
     __shared__ unsigned int s_base;
     __shared__ __align__(8) uint64_t s_bar;
     const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int r0 = tile * SC_T;
-    const int nrows = min(SC_T, P - r0);
+    int r0 = tile * SC_T;                                   // first prior of the tile (global order)
+    int nrows = min(SC_T, P - r0);
     const float* src = conf + ((size_t)b * P + r0) * C;
+    if (LEVELS) {
+        int l = 0;
+#pragma unroll
+        for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && tile >= dl->tile0[q]) l = q;
+        const int off = (tile - dl->tile0[l]) * SC_T;
+        nrows = min(SC_T, dl->cnt[l] - off);
+        r0 = dl->start[l] + off;
+        src = dl->conf[l] + ((size_t)b * dl->cnt[l] + off) * C;
+    }
     const uint32_t bytes = (uint32_t)nrows * C * 4u;
     const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0;
 
@@ -243,6 +264,26 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
         const int rb = coarse_rank(__float_as_uint(pj));
         seg[s_ch[rb] + atomicAdd(&s_fill[rb], 1u)] = make_key(pj, (int)(lq & 31u), r0 + warp * 32 + (int)(lq >> 5));
     }
+}
+
+template <int C, bool FROM_SCORES>
+__global__ void __launch_bounds__(SC_T)
+detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int capI,
+                    unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
+                    unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
+                    unsigned int* __restrict__ overflow)
+{
+    detect_score_body<C, FROM_SCORES, false>(conf, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, nullptr);
+}
+
+template <int C>
+__global__ void __launch_bounds__(SC_T)
+detect_score_levels_kernel(int P, float min_score, int capI,
+                           unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
+                           unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
+                           unsigned int* __restrict__ overflow, const DetLevels dl)
+{
+    detect_score_body<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,9 +742,9 @@ static size_t nms_smem_bytes(int NF, int top_k, int T)
     return (off + 15) & ~(size_t)15;
 }
 
-template <bool FROM_SCORES>
-__global__ void __launch_bounds__(NT, 2)
-detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
+template <bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
                   unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
@@ -781,7 +822,15 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
     const Kept kp = {s_kbox, s_kkey, s_karea, s_kidx, s_kcnt, kcap};
     auto load_box = [&](unsigned long long key) {
         const unsigned prior = key_prior(key);
-        float4 v = loc_or_boxes[bP + prior];
+        float4 v;
+        if (LEVELS) {
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && (int)prior >= dl->start[q]) l = q;
+            v = reinterpret_cast<const float4*>(dl->loc[l])[(size_t)b * dl->cnt[l] + (prior - (unsigned)dl->start[l])];
+        } else {
+            v = loc_or_boxes[bP + prior];
+        }
         if (!FROM_SCORES) v = decode_box(v, pri_cxcywh[prior]);             // Losses.py:23
         return cxcywh_to_xyxy(v);                                           // Losses.py:41,71
     };
@@ -904,19 +953,48 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
 }
 
 template <bool FROM_SCORES>
+__global__ void __launch_bounds__(NT, 2)
+detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
+                  unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
+                  unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
+                  const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
+                  unsigned int* __restrict__ overflow,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                  float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
+                  int* __restrict__ out_prior, int* __restrict__ out_cnt)
+{
+    detect_nms_body<FROM_SCORES, false>(nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
+                                        img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+
+__global__ void __launch_bounds__(NT, 2)
+detect_nms_levels_kernel(const DetLevels dl, const float4* __restrict__ pri_cxcywh,
+                         unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
+                         unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
+                         const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
+                         unsigned int* __restrict__ overflow,
+                         const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                         float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
+                         int* __restrict__ out_prior, int* __restrict__ out_cnt)
+{
+    detect_nms_body<false, true>(&dl, nullptr, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
+                                 img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+
+template <bool FROM_SCORES>
 static int run_detect(const float* loc, const float* conf, const float* pri_cxcywh, int B, int P, int C,
                       float min_score, float iou_thr, int top_k, const float* img_wh,
                       float* out_boxes, float* out_prob, int32_t* out_cls, int32_t* out_prior, int32_t* out_cnt,
-                      void* ws, size_t ws_bytes, int n_cap, cudaStream_t st)
+                      void* ws, size_t ws_bytes, int n_cap, cudaStream_t st, const DetLevels* dl = nullptr)
 {
     if (B < 0 || P <= 0 || top_k <= 0 || n_cap < 0) return SSDHEAD_E_BADARG;
-    if (!loc || !conf || (!FROM_SCORES && !pri_cxcywh) || !out_boxes || !out_prob || !out_cls || !out_cnt || !ws) return SSDHEAD_E_BADARG;
+    if ((!dl && (!loc || !conf)) || (!FROM_SCORES && !pri_cxcywh) || !out_boxes || !out_prob || !out_cls || !out_cnt || !ws) return SSDHEAD_E_BADARG;
     if (C != 21) return SSDHEAD_E_UNSUPPORTED;
     if (B == 0) return 0;
     if (B > 65535 || P >= (1 << 24) || top_k > 60000) return SSDHEAD_E_UNSUPPORTED;
-    if (!aligned16(loc) || (!FROM_SCORES && !aligned16(pri_cxcywh)) || !aligned16(out_boxes) || !aligned16(ws)) return SSDHEAD_E_ALIGN;
+    if ((!dl && !aligned16(loc)) || (!FROM_SCORES && !aligned16(pri_cxcywh)) || !aligned16(out_boxes) || !aligned16(ws)) return SSDHEAD_E_ALIGN;
     const int NF = C - 1;
-    const int T = detect_tiles(P);
+    const int T = dl ? dl->tile0[dl->n] : detect_tiles(P);
     if (T > NT) return SSDHEAD_E_UNSUPPORTED;                                 // P <= 131072
     const size_t smem_nms = nms_smem_bytes(NF, top_k, T);
     if (smem_nms > 200 * 1024) return SSDHEAD_E_UNSUPPORTED;                 // top_k <= ~1400 for 20 classes
@@ -925,16 +1003,29 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     const int capI = detect_cap_image(P, C, n_cap);
 
-    dim3 g1((P + SC_T - 1) / SC_T, B);
-    SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
-                              conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
+    dim3 g1(T, B);
+    if (dl) {
+        SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
+                                  P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, *dl));
+    } else {
+        SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
+                                  conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
+    }
     count_launch();
 
-    SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
-    SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
-                              (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                              w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
-                              (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
+    if (dl) {
+        SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
+        SSD_CHECK_CUDA(launch_pdl(8, detect_nms_levels_kernel, dim3(B), dim3(NT), smem_nms, st,
+                                  *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
+    } else {
+        SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
+        SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
+                                  (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
+    }
     count_launch();
     return 0;
 }
@@ -961,6 +1052,32 @@ int ssdhead_detect_from_scores(const float* boxes_cxcywh, const float* probs, in
 {
     return run_detect<true>(boxes_cxcywh, probs, nullptr, B, P, C, min_score, iou_thr, top_k, img_wh,
                             out_boxes, out_prob, out_cls, out_prior, out_cnt, ws, ws_bytes, max_candidates, (cudaStream_t)stream);
+}
+
+int ssdhead_detect_levels(const ssdhead_levels* levels, const float* pri_cxcywh,
+                          int B, int P, int C, float min_score, float iou_thr, int top_k,
+                          const float* img_wh, int max_candidates,
+                          float* out_boxes, float* out_prob, int32_t* out_cls, int32_t* out_prior, int32_t* out_cnt,
+                          void* ws, size_t ws_bytes, void* stream)
+{
+    if (!levels || levels->num_levels < 1 || levels->num_levels > MAX_LEVELS) return SSDHEAD_E_BADARG;
+    DetLevels dl = {};
+    dl.n = levels->num_levels;
+    int sum = 0, t0 = 0;
+    for (int l = 0; l < dl.n; ++l) {
+        const int n = levels->count[l];
+        if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
+        if (!aligned16(levels->conf[l]) || !aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;
+        dl.cnt[l] = n; dl.start[l] = sum; dl.tile0[l] = t0;
+        dl.conf[l] = levels->conf[l]; dl.loc[l] = levels->loc[l];
+        sum += n;
+        t0 += (n + SC_T - 1) / SC_T;
+    }
+    for (int l = dl.n; l <= MAX_LEVELS; ++l) { dl.start[l] = sum; dl.tile0[l] = t0; }
+    if (sum != P) return SSDHEAD_E_BADARG;
+    return run_detect<false>(nullptr, nullptr, pri_cxcywh, B, P, C, min_score, iou_thr, top_k, img_wh,
+                             out_boxes, out_prob, out_cls, out_prior, out_cnt, ws, ws_bytes, max_candidates,
+                             (cudaStream_t)stream, &dl);
 }
 
 #ifdef SSDHEAD_PHASE_TIMES

@@ -279,11 +279,41 @@ constexpr int CE_ROWS = 256;                      // rows per tile = consumer th
 constexpr int CE_STAGES = 4;
 constexpr int CE_THREADS = CE_ROWS + 32;          // + one producer warp
 
-template <int C, bool ZERO_FILL, bool MATCH>
-__global__ void __launch_bounds__(CE_THREADS, 2)
-ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
-                 float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma,
-                 const FusedMatch fm)
+// Head outputs given PER PYRAMID LEVEL: the reference permutes every conv output to NHWC and
+// concatenates the six levels into [B,8732,4] / [B,8732,21] (Model.py:212-235) - a full extra HBM round trip.  An
+// NHWC conv output already IS the row layout [B, n_l, 21] of its level, so the kernels can read the level tensors in
+// place: level l holds n_l = cnt[l] priors per image, its rows are flat [B * n_l], priors start[l] .. start[l+1]-1 of the
+// global order.  The streaming kernel walks one virtual tile space: tile0[l] .. tile0[l+1]-1 are the full 256-row tiles
+// of level l (tiles straddle images inside a level exactly as they do in the concatenated layout).
+constexpr int MAX_LEVELS = SSDHEAD_MAX_LEVELS;
+struct LevelTab {
+    int n;
+    int cnt[MAX_LEVELS];
+    int start[MAX_LEVELS + 1];
+    long long tile0[MAX_LEVELS + 1];
+    const float* conf[MAX_LEVELS];
+    const float* loc[MAX_LEVELS];
+    float* gconf[MAX_LEVELS];
+    float* gloc[MAX_LEVELS];
+};
+__device__ __forceinline__ int level_of_tile(const LevelTab& lv, long long vt) {
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < MAX_LEVELS; ++q) if (q < lv.n && vt >= lv.tile0[q]) l = q;
+    return l;
+}
+__device__ __forceinline__ int level_of_prior(const LevelTab& lv, int j) {
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < MAX_LEVELS; ++q) if (q < lv.n && j >= lv.start[q]) l = q;
+    return l;
+}
+
+template <int C, bool ZERO_FILL, bool MATCH, bool LEVELS>
+__device__ __forceinline__ void
+ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
+               float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma,
+               const FusedMatch& fm, const LevelTab* __restrict__ lvp)
 {
     constexpr uint32_t TILE_BYTES = CE_ROWS * C * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -292,7 +322,8 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
     float* zero_tile = reinterpret_cast<float*>(smem_raw + (size_t)CE_STAGES * TILE_BYTES);
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const long long full_tiles = use_tma ? total_rows / CE_ROWS : 0;
+    const long long full_tiles = LEVELS ? lvp->tile0[lvp->n] : (use_tma ? total_rows / CE_ROWS : 0);
+    const int P = fm.P;
 
     if (t == 0) {
 #pragma unroll
@@ -316,10 +347,19 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
             for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
                 mbar_wait(&s_empty[s], ph ^ 1u);
                 mbar_expect_tx(&s_full[s], TILE_BYTES);
-                bulk_g2s(smem_raw + (size_t)s * TILE_BYTES, conf + (size_t)tile * CE_ROWS * C, TILE_BYTES, &s_full[s]);
+                const float* src = conf + (size_t)tile * CE_ROWS * C;
+                float* gc = grad_conf + (size_t)tile * CE_ROWS * C;
+                float* gl = grad_loc + (size_t)tile * CE_ROWS * 4;
+                if (LEVELS) {
+                    const int l = level_of_tile(*lvp, tile);
+                    const size_t r0 = (size_t)(tile - lvp->tile0[l]) * CE_ROWS;
+                    src = lvp->conf[l] + r0 * C;
+                    if (ZERO_FILL) { gc = lvp->gconf[l] + r0 * C; gl = lvp->gloc[l] + r0 * 4; }
+                }
+                bulk_g2s(smem_raw + (size_t)s * TILE_BYTES, src, TILE_BYTES, &s_full[s]);
                 if (ZERO_FILL) {
-                    bulk_s2g(grad_conf + (size_t)tile * CE_ROWS * C, zero_tile, TILE_BYTES);
-                    bulk_s2g(grad_loc + (size_t)tile * CE_ROWS * 4, zero_tile, CE_ROWS * 16);
+                    bulk_s2g(gc, zero_tile, TILE_BYTES);
+                    bulk_s2g(gl, zero_tile, CE_ROWS * 16);
                     bulk_commit();
                 }
                 if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
@@ -330,13 +370,21 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
         // ---------------- consumer warps: thread per row ----------------
         int s = 0;
         uint32_t ph = 0;
+        // global row (b * P + prior) of this thread's row in virtual tile `tile`
+        auto row_of = [&](long long tile) -> long long {
+            if (!LEVELS) return tile * CE_ROWS + t;
+            const int l = level_of_tile(*lvp, tile);
+            const unsigned lr = (unsigned)((tile - lvp->tile0[l]) * CE_ROWS) + (unsigned)t, n = (unsigned)lvp->cnt[l];
+            const unsigned b = lr / n;
+            return (long long)b * P + lvp->start[l] + (int)(lr - b * n);
+        };
         FusedPre pre, nxt;
-        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)(blockIdx.x * CE_ROWS + t), true);
+        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)row_of(blockIdx.x), true);
         for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
-            const long long row = tile * CE_ROWS + t;
+            const long long row = row_of(tile);
             if (MATCH) {
                 // issue the next tile's match inputs now; score this tile's match (independent of the conf tile)
-                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)((tile + gridDim.x) * CE_ROWS + t), true);
+                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)row_of(tile + gridDim.x), true);
                 fused_match_rows(fm, (unsigned)row, true, pre);
                 pre = nxt;
             }
@@ -348,22 +396,64 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
             if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
         }
         // rows past the last full tile (or every row when the pointers are not 16-byte aligned): plain loads
-        const long long rest0 = full_tiles * CE_ROWS;
-        for (long long row0 = rest0 + (long long)blockIdx.x * CE_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * CE_ROWS) {
-            const long long row = row0 + t;                  // the loop bound is CTA-uniform: warps stay converged
-            const bool valid = row < total_rows;
-            if (MATCH) fused_match_rows(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
-            if (valid) {
-                ce_out[row] = row_cross_entropy<C, true>(conf + (size_t)row * C, C - 1);
-                if (ZERO_FILL) {
+        if (!LEVELS) {
+            const long long rest0 = full_tiles * CE_ROWS;
+            for (long long row0 = rest0 + (long long)blockIdx.x * CE_ROWS; row0 < total_rows; row0 += (long long)gridDim.x * CE_ROWS) {
+                const long long row = row0 + t;                  // the loop bound is CTA-uniform: warps stay converged
+                const bool valid = row < total_rows;
+                if (MATCH) fused_match_rows(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
+                if (valid) {
+                    ce_out[row] = row_cross_entropy<C, true>(conf + (size_t)row * C, C - 1);
+                    if (ZERO_FILL) {
 #pragma unroll
-                    for (int q = 0; q < C; ++q) grad_conf[(size_t)row * C + q] = 0.0f;
+                        for (int q = 0; q < C; ++q) grad_conf[(size_t)row * C + q] = 0.0f;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) grad_loc[(size_t)row * 4 + q] = 0.0f;
+                        for (int q = 0; q < 4; ++q) grad_loc[(size_t)row * 4 + q] = 0.0f;
+                    }
+                }
+            }
+        } else {
+            // per level: the rows after its last full tile (fewer than 256 when B * n_l is not a multiple of 256)
+            for (int l = 0; l < lvp->n; ++l) {
+                const unsigned n = (unsigned)lvp->cnt[l];
+                const long long rows_l = total_rows / P * n;     // B * n_l
+                const long long rest0 = (lvp->tile0[l + 1] - lvp->tile0[l]) * CE_ROWS;
+                for (long long r0 = rest0 + (long long)blockIdx.x * CE_ROWS; r0 < rows_l; r0 += (long long)gridDim.x * CE_ROWS) {
+                    const long long lr = r0 + t;
+                    const bool valid = lr < rows_l;
+                    const unsigned b = valid ? (unsigned)(lr / n) : 0u;
+                    const long long row = valid ? (long long)b * P + lvp->start[l] + (int)(lr - (long long)b * n) : total_rows;
+                    if (MATCH) fused_match_rows(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
+                    if (valid) {
+                        ce_out[row] = row_cross_entropy<C, true>(lvp->conf[l] + (size_t)lr * C, C - 1);
+                        if (ZERO_FILL) {
+#pragma unroll
+                            for (int q = 0; q < C; ++q) lvp->gconf[l][(size_t)lr * C + q] = 0.0f;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) lvp->gloc[l][(size_t)lr * 4 + q] = 0.0f;
+                        }
+                    }
                 }
             }
         }
     }
+}
+
+template <int C, bool ZERO_FILL, bool MATCH>
+__global__ void __launch_bounds__(CE_THREADS, 2)
+ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
+                 float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma,
+                 const FusedMatch fm)
+{
+    ce_stream_body<C, ZERO_FILL, MATCH, false>(conf, ce_out, grad_conf, grad_loc, total_rows, use_tma, fm, nullptr);
+}
+
+// the same kernel reading / zero-filling per-level tensors in place (no concatenated [B,P,*] tensors exist)
+template <int C, bool ZERO_FILL>
+__global__ void __launch_bounds__(CE_THREADS, 2)
+ce_stream_levels_kernel(float* __restrict__ ce_out, long long total_rows, const FusedMatch fm, const LevelTab lv)
+{
+    ce_stream_body<C, ZERO_FILL, true, true>(nullptr, ce_out, nullptr, nullptr, total_rows, 1, fm, &lv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -377,6 +467,7 @@ struct MineParams {
     const float* loc;
     const float* conf;
     const float* ce;             // CE of every row against the BACKGROUND class (ce_stream_kernel)
+    float* ce_w;                 // host-side convenience: the same buffer, writable (level entry point)
     float* ce_tap;               // nullable: receives the true CE of positive rows (debug tap)
     const uint8_t* cls_u8;
     const float4* gt_xyxy;
@@ -439,9 +530,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 constexpr int MN_GC = 64;        // gt boxes staged in shared memory
 constexpr int MN_CAND = 512;     // boundary-bin candidates ranked directly (one per thread)
 
-template <int C, bool GRADS, bool FIN>
-__global__ void __launch_bounds__(MN_T, 2)    // two CTAs per SM: B = 256 images stay co-resident (cooperative launch)
-mine_kernel(const MineParams p)
+template <int C, bool GRADS, bool FIN, bool LEVELS>
+__device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* __restrict__ lvp)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_raw);            // [P]  CE bit pattern, 0 for positives; bit 31 = selected
@@ -464,6 +554,27 @@ mine_kernel(const MineParams p)
     const int off0 = p.gt_off[b];
     const int G = p.gt_off[b + 1] - off0;
     double acc_l1 = 0.0, acc_ce = 0.0;
+    // row j of this image in the head tensors: the concatenated [B,P,*] tensors, or the tensor of j's pyramid level
+    auto conf_row = [&](int j) -> const float* {
+        if (!LEVELS) return p.conf + (row0 + j) * C;
+        const int l = level_of_prior(*lvp, j);
+        return lvp->conf[l] + ((size_t)b * lvp->cnt[l] + (size_t)(j - lvp->start[l])) * C;
+    };
+    auto gconf_row = [&](int j) -> float* {
+        if (!LEVELS) return p.grad_conf + (row0 + j) * C;
+        const int l = level_of_prior(*lvp, j);
+        return lvp->gconf[l] + ((size_t)b * lvp->cnt[l] + (size_t)(j - lvp->start[l])) * C;
+    };
+    auto loc_row = [&](int j) -> const float4* {
+        if (!LEVELS) return reinterpret_cast<const float4*>(p.loc) + row0 + j;
+        const int l = level_of_prior(*lvp, j);
+        return reinterpret_cast<const float4*>(lvp->loc[l]) + (size_t)b * lvp->cnt[l] + (size_t)(j - lvp->start[l]);
+    };
+    auto gloc_row = [&](int j) -> float4* {
+        if (!LEVELS) return reinterpret_cast<float4*>(p.grad_loc) + row0 + j;
+        const int l = level_of_prior(*lvp, j);
+        return reinterpret_cast<float4*>(lvp->gloc[l]) + (size_t)b * lvp->cnt[l] + (size_t)(j - lvp->start[l]);
+    };
 
     // ---- 1. keys: CE bits for negatives, 0 for positives (Losses.py:188-190); class bytes; gts ----
     if (t == 0) { s_nsel = 0u; s_ncand = 0u; s_max = 0u; }
@@ -769,7 +880,7 @@ mine_kernel(const MineParams p)
             for (int i = 0; i < C; ++i) {
                 const int e = lane + 32 * i, r = e / C, q = e - r * C;
                 const int jr = __shfl_sync(FULL, j, r);
-                v[i] = r < nrw ? __ldg(p.conf + (row0 + jr) * C + q) : 0.0f;
+                v[i] = r < nrw ? __ldg(conf_row(jr) + q) : 0.0f;
             }
 #pragma unroll
             for (int i = 0; i < C; ++i) wstage[lane + 32 * i] = v[i];
@@ -784,7 +895,7 @@ mine_kernel(const MineParams p)
 #pragma unroll
                 for (int q = 0; q < C; ++q) x[q] = wstage[lane * C + q];
             } else {
-                const float* row = p.conf + (row0 + j) * C;
+                const float* row = conf_row(j);
 #pragma unroll
                 for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
             }
@@ -792,7 +903,7 @@ mine_kernel(const MineParams p)
         if (pos) {                                   // issue every independent load before the first use
             pb = p.pri_xyxy[j];
             pc = p.pri_cxcywh[j];
-            l = reinterpret_cast<const float4*>(p.loc)[row0 + j];
+            l = *loc_row(j);
         }
         if (pos) {
             // the streaming kernel scored every row against the background class; a positive row gets its
@@ -814,7 +925,7 @@ mine_kernel(const MineParams p)
                 for (int q = 0; q < C; ++q)
                     wstage[lane * C + q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
             } else {
-                float* grow = p.grad_conf + (row0 + j) * C;
+                float* grow = gconf_row(j);
 #pragma unroll
                 for (int q = 0; q < C; ++q)
                     grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
@@ -829,7 +940,7 @@ mine_kernel(const MineParams p)
             for (int i = 0; i < C; ++i) {
                 const int e = lane + 32 * i, r = e / C, q = e - r * C;
                 const int jr = __shfl_sync(FULL, j, r);
-                if (r < nrw) p.grad_conf[(row0 + jr) * C + q] = v[i];
+                if (r < nrw) gconf_row(jr)[q] = v[i];
             }
             __syncwarp();
         }
@@ -858,7 +969,7 @@ mine_kernel(const MineParams p)
                 gl.y = dy > 0.f ? gs_loc : (dy < 0.f ? -gs_loc : 0.f);
                 gl.z = dz > 0.f ? gs_loc : (dz < 0.f ? -gs_loc : 0.f);
                 gl.w = dw > 0.f ? gs_loc : (dw < 0.f ? -gs_loc : 0.f);
-                reinterpret_cast<float4*>(p.grad_loc)[row0 + j] = gl;
+                *gloc_row(j) = gl;
             }
         }
     }
@@ -929,6 +1040,22 @@ mine_kernel(const MineParams p)
             }
         }
     }
+}
+
+
+template <int C, bool GRADS, bool FIN>
+__global__ void __launch_bounds__(MN_T, 2)    // two CTAs per SM: B = 256 images stay co-resident (cooperative launch)
+mine_kernel(const MineParams p)
+{
+    mine_body<C, GRADS, FIN, false>(p, nullptr);
+}
+
+// the same kernel on per-level head tensors (ssdhead_multibox_step_levels)
+template <int C, bool GRADS, bool FIN>
+__global__ void __launch_bounds__(MN_T, 2)
+mine_levels_kernel(const MineParams p, const LevelTab lv)
+{
+    mine_body<C, GRADS, FIN, true>(p, &lv);
 }
 
 
@@ -1171,6 +1298,118 @@ int ssdhead_multibox_step_sharded(const float* loc, const float* conf,
                               sums, losses, grad_loc, grad_conf, cls_u8, best_prior, npos, nullptr, nullptr,
                               ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, R, rank, seq, peers_dev, xchg_local_dev,
                               err_flag_dev);
+}
+
+// ssdhead_multibox_step on per-level head tensors (Model.py:212-235 without the permute/cat copies)
+extern "C++" {
+template <bool GRADS>
+static int multibox_step_levels_impl(const LevelTab& lv, const FusedMatch& fm, MineParams prm, int B, int P,
+                                     unsigned int* image_counter, cudaStream_t st)
+{
+    constexpr int C = 21;
+    constexpr size_t tile = (size_t)CE_ROWS * C * 4;
+    const size_t smem_ce = tile * CE_STAGES + (GRADS ? tile : 0);
+    auto kce = ce_stream_levels_kernel<C, GRADS>;
+    SSD_CHECK_CUDA(cudaFuncSetAttribute(kce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ce));
+    const long long rows = (long long)B * P;
+    const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS + lv.n;
+    const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
+    SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, prm.ce_w, rows, fm, lv));
+    count_launch();
+
+    const size_t smem_mn = mine_smem_bytes(P);
+    auto kfin = mine_levels_kernel<C, GRADS, true>;
+    SSD_CHECK_CUDA(cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
+    int per_sm = 0;
+    SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfin, MN_T, smem_mn));
+    if ((long long)per_sm * num_sms() >= B) {
+        void* args[] = {&prm, (void*)&lv};
+        SSD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kfin, dim3(B), dim3(MN_T), args, smem_mn, st));
+        count_launch();
+        return 0;
+    }
+    // does not fit co-resident: separate finaliser, ordinary mining kernel
+    SSD_CHECK_CUDA(launch_pdl(2, match_finalize_kernel, dim3(B), dim3(64), 0, st, fm.gt_cls, fm.gt_off, B, P, C - 1,
+                              prm.best_prior_w, prm.npos_w, prm.cls_rw, prm.best_key, prm.npos_acc, image_counter));
+    count_launch();
+    prm.best_prior = prm.best_prior_w; prm.npos = prm.npos_w; prm.npos_norm = prm.npos_w + B;
+    auto kmn = mine_levels_kernel<C, GRADS, false>;
+    SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
+    SSD_CHECK_CUDA(launch_pdl(4, kmn, dim3(B), dim3(MN_T), smem_mn, st, prm, lv));
+    count_launch();
+    return 0;
+}
+}  // extern "C++"
+
+int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
+                                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                                 const float* pri_xyxy, const float* pri_cxcywh,
+                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                                 double* sums, float* losses,
+                                 uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                                 void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    if (!levels || B < 0 || P <= 0 || sumG < 0 || neg_ratio < 0) return SSDHEAD_E_BADARG;
+    if (!gt_off || !pri_xyxy || !pri_cxcywh || !sums || !losses || !cls_u8 || !npos || !ws_loss || !ws_match) return SSDHEAD_E_BADARG;
+    if (sumG > 0 && (!gt_xyxy || !gt_cls || !best_prior)) return SSDHEAD_E_BADARG;
+    if (levels->num_levels < 1 || levels->num_levels > MAX_LEVELS) return SSDHEAD_E_BADARG;
+    if (C != 21) return SSDHEAD_E_UNSUPPORTED;
+    if (B == 0) return 0;
+    if ((long long)B * P >= (1ll << 31)) return SSDHEAD_E_UNSUPPORTED;
+    if (!aligned16(ws_loss) || !aligned16(ws_match) || !aligned16(pri_xyxy) || !aligned16(pri_cxcywh) || (sumG > 0 && !aligned16(gt_xyxy)))
+        return SSDHEAD_E_ALIGN;
+    LevelTab lv = {};
+    lv.n = levels->num_levels;
+    int sum = 0, with_grads = 0;
+    long long t0 = 0;
+    for (int l = 0; l < lv.n; ++l) {
+        const int n = levels->count[l];
+        if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
+        if (!aligned16(levels->conf[l]) || !aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;
+        const bool g = levels->grad_conf[l] != nullptr;
+        if (g != (levels->grad_loc[l] != nullptr)) return SSDHEAD_E_BADARG;
+        if (g && (!aligned16(levels->grad_conf[l]) || !aligned16(levels->grad_loc[l]))) return SSDHEAD_E_ALIGN;
+        with_grads += g ? 1 : 0;
+        lv.cnt[l] = n; lv.start[l] = sum; lv.tile0[l] = t0;
+        lv.conf[l] = levels->conf[l]; lv.loc[l] = levels->loc[l]; lv.gconf[l] = levels->grad_conf[l]; lv.gloc[l] = levels->grad_loc[l];
+        sum += n;
+        t0 += ((long long)B * n) / CE_ROWS;
+    }
+    for (int l = lv.n; l <= MAX_LEVELS; ++l) { lv.start[l] = sum; lv.tile0[l] = t0; }
+    if (sum != P) return SSDHEAD_E_BADARG;
+    if (with_grads != 0 && with_grads != lv.n) return SSDHEAD_E_BADARG;
+    const size_t need = loss_workspace_bytes(B, P, C);
+    if (need == 0) return SSDHEAD_E_UNSUPPORTED;
+    if (ws_loss_bytes < need) return SSDHEAD_E_WORKSPACE;
+    if (ws_match_bytes < ssdhead_workspace_bytes(SSDHEAD_WS_MATCH, B, P, C, sumG)) return SSDHEAD_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)ws_match;
+    unsigned long long* best_key = (unsigned long long*)w;            w += round_up((size_t)sumG * 8, 16);
+    w += round_up((size_t)B * 4, 16);
+    int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
+    unsigned int* image_counter = (unsigned int*)w;
+    FusedMatch fm;
+    fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
+    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc;
+
+    MineParams prm = {};
+    prm.loc = nullptr; prm.conf = nullptr; prm.cls_u8 = cls_u8;
+    prm.gt_xyxy = (const float4*)gt_xyxy; prm.gt_cls = gt_cls; prm.gt_off = gt_off;
+    prm.pri_xyxy = (const float4*)pri_xyxy; prm.pri_cxcywh = (const float4*)pri_cxcywh;
+    prm.best_prior = best_prior; prm.npos = npos; prm.npos_norm = npos + B;
+    prm.B = B; prm.P = P; prm.neg_ratio = neg_ratio; prm.bg_class = C - 1; prm.pos_iou = pos_iou;
+    prm.sums = sums; prm.losses = losses; prm.grad_loc = nullptr; prm.grad_conf = nullptr;
+    prm.mined_mask = nullptr;
+    prm.done_counter = (unsigned int*)ws_loss;
+    prm.partials = (double*)((char*)ws_loss + 16);
+    prm.ce_w = ws_ce(ws_loss, B);
+    prm.ce = prm.ce_w;
+    prm.ce_tap = nullptr;
+    prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
+    prm.best_key = best_key; prm.npos_acc = npos_acc;
+    prm.arrive_total = (unsigned long long*)(image_counter + 2);
+    return with_grads ? multibox_step_levels_impl<true>(lv, fm, prm, B, P, image_counter, st)
+                      : multibox_step_levels_impl<false>(lv, fm, prm, B, P, image_counter, st);
 }
 
 size_t ssdhead_xchg_bytes(void) { return (size_t)XCHG_WORDS * 8; }

@@ -202,6 +202,63 @@ class MultiboxHead:
         return dict(losses=losses, sums=sums, npos=npos, npos_norm=npos_norm, grad_loc=grad_loc,
                     grad_conf=grad_conf, mined_mask=mined, ce=ce, best_prior=m["best_prior"], cls_u8=m["cls_u8"])
 
+    # ------------------------------------------------------------------ per-level head tensors
+    def _levels(self, loc_levels, conf_levels, grads=None):
+        """Validate per-level tensors ([B, n_l, 4] / [B, n_l, C], e.g. NHWC conv outputs viewed as rows) and build the
+        ``ssdhead_levels`` struct.  Returns (struct, loc list, conf list, B) - the lists keep the tensors alive."""
+        L = len(conf_levels)
+        if L < 1 or L > _lib.MAX_LEVELS or len(loc_levels) != L:
+            raise ValueError(f"expected 1..{_lib.MAX_LEVELS} levels with one loc and one conf tensor each")
+        B = int(conf_levels[0].shape[0])
+        locs, confs = [], []
+        for lo, co in zip(loc_levels, conf_levels):
+            lo = lo.detach().to(device=self.dev, dtype=torch.float32).reshape(B, -1, 4).contiguous()
+            co = co.detach().to(device=self.dev, dtype=torch.float32).reshape(B, -1, self.C).contiguous()
+            if lo.shape[1] != co.shape[1]:
+                raise ValueError(f"level with {lo.shape[1]} loc rows but {co.shape[1]} conf rows")
+            locs.append(lo)
+            confs.append(co)
+        if sum(int(c.shape[1]) for c in confs) != self.P:
+            raise ValueError(f"levels hold {sum(int(c.shape[1]) for c in confs)} priors per image, the prior table {self.P}")
+        st = _lib.Levels()
+        st.num_levels = L
+        for i in range(L):
+            st.count[i] = int(confs[i].shape[1])
+            st.conf[i] = confs[i].data_ptr()
+            st.loc[i] = locs[i].data_ptr()
+            st.grad_conf[i] = grads[1][i].data_ptr() if grads else None
+            st.grad_loc[i] = grads[0][i].data_ptr() if grads else None
+        return st, locs, confs, B
+
+    def loss_levels(self, loc_levels, conf_levels, gt: PackedGT, with_grads: bool,
+                    neg_ratio: int = NEG_RATIO, pos_iou: float = POS_IOU):
+        """``loss`` on per-level tensors (no concatenated [B,P,*] tensor in either direction): same two kernels,
+        bit-identical results; gradients come back as per-level lists in the layout of the inputs."""
+        B0 = int(conf_levels[0].shape[0])
+        grads = None
+        if with_grads:
+            grads = ([torch.empty(B0, int(c.shape[1]) if c.dim() == 3 else c.numel() // (B0 * self.C), 4, device=self.dev)
+                      for c in conf_levels],
+                     [torch.empty(B0, int(c.shape[1]) if c.dim() == 3 else c.numel() // (B0 * self.C), self.C, device=self.dev)
+                      for c in conf_levels])
+        st, locs, confs, B = self._levels(loc_levels, conf_levels, grads)
+        if gt.B != B:
+            raise ValueError(f"{B} images but {gt.B} gt lists")
+        sums = torch.empty(2, dtype=torch.float64, device=self.dev)
+        losses = torch.empty(2, dtype=torch.float32, device=self.dev)
+        m = self._match_outputs(gt, False)
+        ws = self._workspace(_lib.WS_LOSS, B, 0)
+        wm = self._workspace(_lib.WS_MATCH, B, gt.sumG)
+        import ctypes
+        _lib.check(self.lib.ssdhead_multibox_step_levels(
+            ctypes.addressof(st), _ptr(gt.boxes), _ptr(gt.classes), _ptr(gt.off),
+            _ptr(self.pri_xyxy), _ptr(self.pri_cxcywh), B, self.P, self.C, gt.sumG, int(neg_ratio), float(pos_iou),
+            _ptr(sums), _ptr(losses), _ptr(m["cls_u8"]), _ptr(m["best_prior"]), _ptr(m["npos"]),
+            _ptr(ws), ws.numel(), _ptr(wm), wm.numel(), _stream(self.dev)), "ssdhead_multibox_step_levels")
+        return dict(losses=losses, sums=sums, npos=m["npos"], grad_loc=grads[0] if grads else None,
+                    grad_conf=grads[1] if grads else None, best_prior=m["best_prior"], cls_u8=m["cls_u8"],
+                    _keep=(locs, confs))
+
     def scale_grads(self, grad_loc: torch.Tensor, grad_conf: torch.Tensor, gout: torch.Tensor):
         _lib.check(self.lib.ssdhead_scale_grads(_ptr(grad_loc), grad_loc.numel(), _ptr(grad_conf),
                                                 grad_conf.numel(), _ptr(gout), _stream(self.dev)),
@@ -284,3 +341,63 @@ def detect(head: MultiboxHead, loc, conf, min_score=0.2, iou_thr=0.45, top_k=200
 def detect_from_scores(head: MultiboxHead, boxes_cxcywh, probs, min_score=0.2, iou_thr=0.45, top_k=200,
                        img_wh=None, max_candidates=0):
     return _detect(head, boxes_cxcywh, probs, min_score, iou_thr, top_k, img_wh, max_candidates, True)
+
+
+class _MultiboxLossLevelsFn(torch.autograd.Function):
+    """``ssd()`` on per-level head tensors: inputs = L loc tensors then L conf tensors; the gradients come back per
+    level in the same layout, so autograd continues straight into each conv (the permute is a view)."""
+
+    @staticmethod
+    def forward(ctx, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, L, *tensors):
+        locs, confs = tensors[:L], tensors[L:]
+        need = any(t.requires_grad for t in tensors)
+        out = head.loss_levels(locs, confs, gt, with_grads=need, neg_ratio=neg_ratio, pos_iou=pos_iou)
+        ctx.head = head
+        ctx.meta = [(t.shape, t.device, t.dtype) for t in tensors]
+        ctx.grads = (out["grad_loc"], out["grad_conf"]) if need else None
+        losses = out["losses"]
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loc_loss, g_conf_loss):
+        if ctx.grads is None:
+            raise RuntimeError("ssd_levels(): backward called twice (or without grad-requiring inputs)")
+        gls, gcs = ctx.grads
+        ctx.grads = None
+        head = ctx.head
+        z = torch.zeros((), dtype=torch.float32, device=head.dev)
+        gout = torch.stack([(g_loc_loss if g_loc_loss is not None else z).to(head.dev, torch.float32).reshape(()),
+                            (g_conf_loss if g_conf_loss is not None else z).to(head.dev, torch.float32).reshape(())])
+        for gl, gc in zip(gls, gcs):
+            head.scale_grads(gl, gc, gout)
+        outs = [g.reshape(shape).to(device=dev, dtype=dt) for g, (shape, dev, dt) in zip(list(gls) + list(gcs), ctx.meta)]
+        return (None, None, None, None, None, *outs)
+
+
+def multibox_loss_levels(head: MultiboxHead, loc_levels, conf_levels, gt_boxes, gt_classes,
+                         neg_ratio: int = NEG_RATIO, pos_iou: float = POS_IOU):
+    """(loc_loss, conf_loss) from per-level head tensors - ``ssd()`` without Model.py:212-235's permute/cat copies."""
+    gt = PackedGT(gt_boxes, gt_classes, head.dev)
+    L = len(conf_levels)
+    return _MultiboxLossLevelsFn.apply(head, gt, neg_ratio, pos_iou, L, *loc_levels, *conf_levels)
+
+
+def detect_levels(head: MultiboxHead, loc_levels, conf_levels, min_score=0.2, iou_thr=0.45, top_k=200, img_wh=None,
+                  max_candidates=0):
+    """``detect`` on per-level head tensors (same output dict)."""
+    import ctypes
+    st, locs, confs, B = head._levels(loc_levels, conf_levels)
+    dev = head.dev
+    wh = None if img_wh is None else img_wh.to(device=dev, dtype=torch.float32).contiguous()
+    out = dict(boxes=torch.empty(B, top_k, 4, device=dev), prob=torch.empty(B, top_k, device=dev),
+               cls=torch.empty(B, top_k, dtype=torch.int32, device=dev),
+               prior=torch.empty(B, top_k, dtype=torch.int32, device=dev),
+               cnt=torch.empty(B, dtype=torch.int32, device=dev))
+    ws = head._workspace(_lib.WS_DETECT, B, int(max_candidates))
+    _lib.check(head.lib.ssdhead_detect_levels(
+        ctypes.addressof(st), _ptr(head.pri_cxcywh), B, head.P, head.C, float(min_score), float(iou_thr), int(top_k),
+        _ptr(wh), int(max_candidates),
+        _ptr(out["boxes"]), _ptr(out["prob"]), _ptr(out["cls"]), _ptr(out["prior"]), _ptr(out["cnt"]),
+        _ptr(ws), ws.numel(), _stream(dev)), "ssdhead_detect_levels")
+    return out
+
