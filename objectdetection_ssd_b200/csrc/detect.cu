@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(SC_T)
 detect_score_levels_kernel(int P, float min_score, int capI,
                            unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
                            unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
-                           unsigned int* __restrict__ overflow, const DetLevels dl)
+                           unsigned int* __restrict__ overflow, const __grid_constant__ DetLevels dl)
 {
     detect_score_body<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl);
 }
@@ -968,7 +968,7 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
 }
 
 __global__ void __launch_bounds__(NT, 2)
-detect_nms_levels_kernel(const DetLevels dl, const float4* __restrict__ pri_cxcywh,
+detect_nms_levels_kernel(const __grid_constant__ DetLevels dl, const float4* __restrict__ pri_cxcywh,
                          unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
                          unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                          const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,

@@ -290,13 +290,14 @@ struct LevelTab {
     int n;
     int cnt[MAX_LEVELS];
     int start[MAX_LEVELS + 1];
-    long long tile0[MAX_LEVELS + 1];
+    int tile0[MAX_LEVELS + 1];
+    int rows[MAX_LEVELS];        // B * cnt[l]; the last tile of a level may be partial (then rows % 4 == 0: 16-byte sizes)
     const float* conf[MAX_LEVELS];
     const float* loc[MAX_LEVELS];
     float* gconf[MAX_LEVELS];
     float* gloc[MAX_LEVELS];
 };
-__device__ __forceinline__ int level_of_tile(const LevelTab& lv, long long vt) {
+__device__ __forceinline__ int level_of_tile(const LevelTab& lv, int vt) {
     int l = 0;
 #pragma unroll
     for (int q = 1; q < MAX_LEVELS; ++q) if (q < lv.n && vt >= lv.tile0[q]) l = q;
@@ -346,20 +347,22 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
                 mbar_wait(&s_empty[s], ph ^ 1u);
-                mbar_expect_tx(&s_full[s], TILE_BYTES);
                 const float* src = conf + (size_t)tile * CE_ROWS * C;
                 float* gc = grad_conf + (size_t)tile * CE_ROWS * C;
                 float* gl = grad_loc + (size_t)tile * CE_ROWS * 4;
+                uint32_t nr = CE_ROWS;
                 if (LEVELS) {
-                    const int l = level_of_tile(*lvp, tile);
-                    const size_t r0 = (size_t)(tile - lvp->tile0[l]) * CE_ROWS;
+                    const int l = level_of_tile(*lvp, (int)tile);
+                    const size_t r0 = (size_t)((int)tile - lvp->tile0[l]) * CE_ROWS;
+                    nr = (uint32_t)min((long long)CE_ROWS, (long long)lvp->rows[l] - (long long)r0);
                     src = lvp->conf[l] + r0 * C;
                     if (ZERO_FILL) { gc = lvp->gconf[l] + r0 * C; gl = lvp->gloc[l] + r0 * 4; }
                 }
-                bulk_g2s(smem_raw + (size_t)s * TILE_BYTES, src, TILE_BYTES, &s_full[s]);
+                mbar_expect_tx(&s_full[s], nr * C * 4);
+                bulk_g2s(smem_raw + (size_t)s * TILE_BYTES, src, nr * C * 4, &s_full[s]);
                 if (ZERO_FILL) {
-                    bulk_s2g(gc, zero_tile, TILE_BYTES);
-                    bulk_s2g(gl, zero_tile, CE_ROWS * 16);
+                    bulk_s2g(gc, zero_tile, nr * C * 4);
+                    bulk_s2g(gl, zero_tile, nr * 16);
                     bulk_commit();
                 }
                 if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
@@ -371,28 +374,34 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
         int s = 0;
         uint32_t ph = 0;
         // global row (b * P + prior) of this thread's row in virtual tile `tile`
-        auto row_of = [&](long long tile) -> long long {
+        auto row_of = [&](long long tile) -> long long {          // -1: past the end of a level's partial last tile
             if (!LEVELS) return tile * CE_ROWS + t;
-            const int l = level_of_tile(*lvp, tile);
-            const unsigned lr = (unsigned)((tile - lvp->tile0[l]) * CE_ROWS) + (unsigned)t, n = (unsigned)lvp->cnt[l];
+            const int l = level_of_tile(*lvp, (int)tile);
+            const unsigned lr = (unsigned)((int)tile - lvp->tile0[l]) * CE_ROWS + (unsigned)t, n = (unsigned)lvp->cnt[l];
+            if (lr >= (unsigned)lvp->rows[l]) return -1;
             const unsigned b = lr / n;
             return (long long)b * P + lvp->start[l] + (int)(lr - b * n);
         };
         FusedPre pre, nxt;
-        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)row_of(blockIdx.x), true);
+        long long row = (long long)blockIdx.x < full_tiles ? row_of(blockIdx.x) : 0;
+        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)row, row >= 0);
         for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
-            const long long row = row_of(tile);
+            long long row_n = 0;
+            if (tile + gridDim.x < full_tiles) row_n = row_of(tile + gridDim.x);
+            const bool valid = !LEVELS || row >= 0;
             if (MATCH) {
                 // issue the next tile's match inputs now; score this tile's match (independent of the conf tile)
-                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)row_of(tile + gridDim.x), true);
-                fused_match_rows(fm, (unsigned)row, true, pre);
+                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)row_n, !LEVELS || row_n >= 0);
+                fused_match_rows(fm, (unsigned)row, valid, pre);
                 pre = nxt;
             }
             mbar_wait(&s_full[s], ph);
-            const float ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
+            float ce = 0.0f;
+            if (valid) ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
-            ce_out[row] = ce;
+            if (valid) ce_out[row] = ce;
+            row = row_n;
             if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
         }
         // rows past the last full tile (or every row when the pointers are not 16-byte aligned): plain loads
@@ -417,8 +426,10 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
             for (int l = 0; l < lvp->n; ++l) {
                 const unsigned n = (unsigned)lvp->cnt[l];
                 const long long rows_l = total_rows / P * n;     // B * n_l
-                const long long rest0 = (lvp->tile0[l + 1] - lvp->tile0[l]) * CE_ROWS;
-                for (long long r0 = rest0 + (long long)blockIdx.x * CE_ROWS; r0 < rows_l; r0 += (long long)gridDim.x * CE_ROWS) {
+                const long long rest0 = (long long)(lvp->tile0[l + 1] - lvp->tile0[l]) * CE_ROWS;
+                // each level's tail starts on a different CTA (otherwise CTA 0 would walk all of them one after the other)
+                const unsigned first = (blockIdx.x + gridDim.x - ((unsigned)l * (gridDim.x / MAX_LEVELS + 1)) % gridDim.x) % gridDim.x;
+                for (long long r0 = rest0 + (long long)first * CE_ROWS; r0 < rows_l; r0 += (long long)gridDim.x * CE_ROWS) {
                     const long long lr = r0 + t;
                     const bool valid = lr < rows_l;
                     const unsigned b = valid ? (unsigned)(lr / n) : 0u;
@@ -451,7 +462,7 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
 // the same kernel reading / zero-filling per-level tensors in place (no concatenated [B,P,*] tensors exist)
 template <int C, bool ZERO_FILL>
 __global__ void __launch_bounds__(CE_THREADS, 2)
-ce_stream_levels_kernel(float* __restrict__ ce_out, long long total_rows, const FusedMatch fm, const LevelTab lv)
+ce_stream_levels_kernel(float* __restrict__ ce_out, long long total_rows, const FusedMatch fm, const __grid_constant__ LevelTab lv)
 {
     ce_stream_body<C, ZERO_FILL, true, true>(nullptr, ce_out, nullptr, nullptr, total_rows, 1, fm, &lv);
 }
@@ -872,6 +883,8 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         const uint32_t wbase = base + (uint32_t)warp * 32u;
         const int nrw = wbase < nsel ? (int)min(32u, nsel - wbase) : 0;
         const int j = valid ? (int)s_list[idx] : 0;
+        const float* my_crow = LEVELS ? conf_row(j) : nullptr;      // per-level tensors: locate the row once, pass pointers
+        float* my_grow = (LEVELS && GRADS) ? gconf_row(j) : nullptr;
         if (staged) {
             // element e = lane + 32 i of the warp's 32 x C block belongs to row e / C, whose index lane e / C holds;
             // all loads are issued before the first shared-memory store (which the compiler must assume may alias)
@@ -879,8 +892,10 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #pragma unroll
             for (int i = 0; i < C; ++i) {
                 const int e = lane + 32 * i, r = e / C, q = e - r * C;
-                const int jr = __shfl_sync(FULL, j, r);
-                v[i] = r < nrw ? __ldg(conf_row(jr) + q) : 0.0f;
+                const float* rp;
+                if (LEVELS) rp = reinterpret_cast<const float*>(__shfl_sync(FULL, (unsigned long long)my_crow, r));
+                else rp = conf_row(__shfl_sync(FULL, j, r));
+                v[i] = r < nrw ? __ldg(rp + q) : 0.0f;
             }
 #pragma unroll
             for (int i = 0; i < C; ++i) wstage[lane + 32 * i] = v[i];
@@ -895,7 +910,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #pragma unroll
                 for (int q = 0; q < C; ++q) x[q] = wstage[lane * C + q];
             } else {
-                const float* row = conf_row(j);
+                const float* row = LEVELS ? my_crow : conf_row(j);
 #pragma unroll
                 for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
             }
@@ -925,7 +940,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 for (int q = 0; q < C; ++q)
                     wstage[lane * C + q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
             } else {
-                float* grow = gconf_row(j);
+                float* grow = LEVELS ? my_grow : gconf_row(j);
 #pragma unroll
                 for (int q = 0; q < C; ++q)
                     grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
@@ -939,8 +954,10 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #pragma unroll
             for (int i = 0; i < C; ++i) {
                 const int e = lane + 32 * i, r = e / C, q = e - r * C;
-                const int jr = __shfl_sync(FULL, j, r);
-                if (r < nrw) gconf_row(jr)[q] = v[i];
+                float* rp;
+                if (LEVELS) rp = reinterpret_cast<float*>(__shfl_sync(FULL, (unsigned long long)my_grow, r));
+                else rp = gconf_row(__shfl_sync(FULL, j, r));
+                if (r < nrw) rp[q] = v[i];
             }
             __syncwarp();
         }
@@ -1053,7 +1070,7 @@ mine_kernel(const MineParams p)
 // the same kernel on per-level head tensors (ssdhead_multibox_step_levels)
 template <int C, bool GRADS, bool FIN>
 __global__ void __launch_bounds__(MN_T, 2)
-mine_levels_kernel(const MineParams p, const LevelTab lv)
+mine_levels_kernel(const MineParams p, const __grid_constant__ LevelTab lv)
 {
     mine_body<C, GRADS, FIN, true>(p, &lv);
 }
@@ -1361,7 +1378,7 @@ int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
     LevelTab lv = {};
     lv.n = levels->num_levels;
     int sum = 0, with_grads = 0;
-    long long t0 = 0;
+    int t0 = 0;
     for (int l = 0; l < lv.n; ++l) {
         const int n = levels->count[l];
         if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
@@ -1373,7 +1390,10 @@ int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
         lv.cnt[l] = n; lv.start[l] = sum; lv.tile0[l] = t0;
         lv.conf[l] = levels->conf[l]; lv.loc[l] = levels->loc[l]; lv.gconf[l] = levels->grad_conf[l]; lv.gloc[l] = levels->grad_loc[l];
         sum += n;
-        t0 += ((long long)B * n) / CE_ROWS;
+        const long long rows_l = (long long)B * n;
+        lv.rows[l] = (int)rows_l;
+        // the partial last tile of a level rides the TMA pipeline too when its byte counts are multiples of 16
+        t0 += (int)(rows_l / CE_ROWS) + ((rows_l % CE_ROWS) != 0 && (rows_l % 4) == 0 ? 1 : 0);
     }
     for (int l = lv.n; l <= MAX_LEVELS; ++l) { lv.start[l] = sum; lv.tile0[l] = t0; }
     if (sum != P) return SSDHEAD_E_BADARG;
