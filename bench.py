@@ -433,6 +433,75 @@ def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
                 detections=int(out["cnt"].clamp(min=0).sum()))
 
 
+def time_train_levels(rank, dev, B=256, steps=200):
+    """Training-head step on the six per-level tensors (NHWC conv outputs viewed as rows) instead of the concatenated
+    [B,8732,*] pair - SURVEY.md 8(f) #3 - next to what building that pair costs (the torch.cat of Model.py:234-235)."""
+    import ctypes
+    from objectdetection_ssd_b200 import _lib, synth, priors as PR
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    lib = _lib.load()
+    pri = PR.make_priors()
+    P = pri.shape[0]
+    head = MultiboxHead(pri, dev)
+    gb, gc = synth.make_gt(1 + rank, B)
+    gt = PackedGT([torch.from_numpy(b) for b in gb], [torch.from_numpy(c) for c in gc], head.dev)
+    loc, conf = synth.make_head(1 + rank, B, P)
+    counts = (5776, 2166, 600, 150, 36, 4)
+    nset = max(2, -(-2 * L2_BYTES // (B * P * 25 * 4)))
+    sets, structs = [], []
+    for i in range(nset):
+        l, c = torch.from_numpy(loc).to(dev) + 0.001 * i, torch.from_numpy(conf).to(dev) + 0.001 * i
+        ls, cs, s0 = [], [], 0
+        for n in counts:
+            ls.append(l[:, s0:s0 + n].contiguous())
+            cs.append(c[:, s0:s0 + n].contiguous())
+            s0 += n
+        sets.append((ls, cs))
+    gls = [torch.empty_like(t) for t in sets[0][0]]
+    gcs = [torch.empty_like(t) for t in sets[0][1]]
+    for ls, cs in sets:
+        st_ = _lib.Levels()
+        st_.num_levels = len(counts)
+        for i in range(len(counts)):
+            st_.count[i] = counts[i]
+            st_.conf[i], st_.loc[i] = cs[i].data_ptr(), ls[i].data_ptr()
+            st_.grad_conf[i], st_.grad_loc[i] = gcs[i].data_ptr(), gls[i].data_ptr()
+        structs.append(st_)
+    sums = torch.empty(2, dtype=torch.float64, device=dev)
+    losses = torch.empty(2, device=dev)
+    m = head._match_outputs(gt, False)
+    ws = head._workspace(_lib.WS_LOSS, B, 0)
+    wm = head._workspace(_lib.WS_MATCH, B, gt.sumG)
+    stream = torch.cuda.current_stream(dev)
+    st = stream.cuda_stream
+
+    def step(i):
+        return lib.ssdhead_multibox_step_levels(
+            ctypes.addressof(structs[i % nset]), gt.boxes.data_ptr(), gt.classes.data_ptr(), gt.off.data_ptr(),
+            head.pri_xyxy.data_ptr(), head.pri_cxcywh.data_ptr(), B, P, 21, gt.sumG, 3, 0.5, sums.data_ptr(), losses.data_ptr(),
+            m["cls_u8"].data_ptr(), m["best_prior"].data_ptr(), m["npos"].data_ptr(),
+            ws.data_ptr(), ws.numel(), wm.data_ptr(), wm.numel(), st)
+
+    def cat(i):
+        ls, cs = sets[i % nset]
+        return torch.cat(ls, 1), torch.cat(cs, 1)
+
+    def timeit(f):
+        for i in range(5):
+            f(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            f(i)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    _lib.check(step(0), "ssdhead_multibox_step_levels")
+    return dict(ms_step=timeit(step), ms_cat=timeit(cat), losses=losses.tolist())
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -514,6 +583,14 @@ def run_ours(args):
             others.append({"workload": "detect, batch 64, bias +6 (configs[2])", "images_per_s": 64 / (m3 * 1e-3),
                            "ms_per_step": m3, "step_roofline_frac": ALGO_BYTES['detect'] * 64 / (m3 * 1e-3) / 1e9 / peak,
                            "e2e_images_per_s": 64 / (r3["e2e_ms"] * 1e-3)})
+            r4 = time_train_levels(rank, dev)
+            others.append({"workload": "train head, batch 256, from the 6 per-level tensors (ssdhead_multibox_step_levels, "
+                                       "SURVEY 8(f) #3; no concatenated tensor in either direction)",
+                           "images_per_s": 256 / (r4["ms_step"] * 1e-3), "ms_per_step": r4["ms_step"],
+                           "step_roofline_frac": ALGO_BYTES['train'] * 256 / (r4["ms_step"] * 1e-3) / 1e9 / peak,
+                           "torch_cat_of_the_levels_ms": r4["ms_cat"],
+                           "note": "the concatenated layout pays value's step PLUS torch_cat_of_the_levels_ms (Model.py:234-235) "
+                                   "and the same again in backward"})
             line["others"] = others
     elif rank == 0:
         line["cpu_baseline"] = None
