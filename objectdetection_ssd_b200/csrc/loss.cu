@@ -104,15 +104,15 @@ struct FusedPre {
     int b_first, b_last, off0, G;
 };
 
-__device__ __forceinline__ FusedPre fused_prefetch(const FusedMatch& m, unsigned row, bool valid)
+__device__ __forceinline__ FusedPre fused_prefetch_bp(const FusedMatch& m, int b, int p, bool valid)
 {
     FusedPre r;
     const int lane = threadIdx.x & 31;
-    r.b = valid ? (int)(row / (unsigned)m.P) : -1;
-    r.p = valid ? (int)(row - (unsigned)r.b * (unsigned)m.P) : 0;
+    r.b = valid ? b : -1;
+    r.p = valid ? p : 0;
     r.b_first = (int)__reduce_min_sync(FULL, valid ? (unsigned)r.b : 0x7fffffffu);
     r.b_last = __reduce_max_sync(FULL, r.b);
-    r.pb = valid ? m.pri_xyxy[r.p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.pb = m.pri_xyxy[r.p];                                  // unconditional (p = 0 past the end): issued at once
     r.off0 = 0; r.G = 0;
     r.gbox = make_float4(0.f, 0.f, 0.f, 0.f);
     r.gcls = 0.0f;
@@ -122,6 +122,12 @@ __device__ __forceinline__ FusedPre fused_prefetch(const FusedMatch& m, unsigned
         if (lane < min(r.G, 32)) { r.gbox = m.gt_xyxy[r.off0 + lane]; r.gcls = m.gt_cls[r.off0 + lane]; }
     }
     return r;
+}
+
+__device__ __forceinline__ FusedPre fused_prefetch(const FusedMatch& m, unsigned row, bool valid)
+{
+    const int b = (int)(row / (unsigned)m.P);
+    return fused_prefetch_bp(m, b, (int)(row - (unsigned)b * (unsigned)m.P), valid);
 }
 
 __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned row, bool valid, const FusedPre& pre)
@@ -292,6 +298,8 @@ struct LevelTab {
     int start[MAX_LEVELS + 1];
     int tile0[MAX_LEVELS + 1];
     int rows[MAX_LEVELS];        // B * cnt[l]; the last tile of a level may be partial (then rows % 4 == 0: 16-byte sizes)
+    int perm_stride, perm_inc;   // the k-th tile a CTA visits is virtual tile (k * stride) mod total: levels interleave, so the
+                                 // match-heavy tiles of the coarse levels hide under the memory time of the fine ones
     const float* conf[MAX_LEVELS];
     const float* loc[MAX_LEVELS];
     float* gconf[MAX_LEVELS];
@@ -345,7 +353,10 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+            int vt = LEVELS ? (int)(((long long)blockIdx.x * lvp->perm_stride) % full_tiles) : 0;
+            for (long long k = blockIdx.x; k < full_tiles; k += gridDim.x) {
+                const long long tile = LEVELS ? (long long)vt : k;
+                if (LEVELS) { vt += lvp->perm_inc; if (vt >= (int)full_tiles) vt -= (int)full_tiles; }
                 mbar_wait(&s_empty[s], ph ^ 1u);
                 const float* src = conf + (size_t)tile * CE_ROWS * C;
                 float* gc = grad_conf + (size_t)tile * CE_ROWS * C;
@@ -374,35 +385,55 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
         int s = 0;
         uint32_t ph = 0;
         // global row (b * P + prior) of this thread's row in virtual tile `tile`
-        auto row_of = [&](long long tile) -> long long {          // -1: past the end of a level's partial last tile
-            if (!LEVELS) return tile * CE_ROWS + t;
-            const int l = level_of_tile(*lvp, (int)tile);
-            const unsigned lr = (unsigned)((int)tile - lvp->tile0[l]) * CE_ROWS + (unsigned)t, n = (unsigned)lvp->cnt[l];
-            if (lr >= (unsigned)lvp->rows[l]) return -1;
-            const unsigned b = lr / n;
-            return (long long)b * P + lvp->start[l] + (int)(lr - b * n);
-        };
         FusedPre pre, nxt;
-        long long row = (long long)blockIdx.x < full_tiles ? row_of(blockIdx.x) : 0;
-        if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)row, row >= 0);
-        for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
-            long long row_n = 0;
-            if (tile + gridDim.x < full_tiles) row_n = row_of(tile + gridDim.x);
-            const bool valid = !LEVELS || row >= 0;
-            if (MATCH) {
-                // issue the next tile's match inputs now; score this tile's match (independent of the conf tile)
-                if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)row_n, !LEVELS || row_n >= 0);
+        if (!LEVELS) {
+            if (MATCH && (long long)blockIdx.x < full_tiles) pre = fused_prefetch(fm, (unsigned)(blockIdx.x * CE_ROWS + t), true);
+            for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+                const long long row = tile * CE_ROWS + t;
+                if (MATCH) {
+                    // issue the next tile's match inputs now; score this tile's match (independent of the conf tile)
+                    if (tile + gridDim.x < full_tiles) nxt = fused_prefetch(fm, (unsigned)((tile + gridDim.x) * CE_ROWS + t), true);
+                    fused_match_rows(fm, (unsigned)row, true, pre);
+                    pre = nxt;
+                }
+                mbar_wait(&s_full[s], ph);
+                const float ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);
+                ce_out[row] = ce;
+                if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
+            }
+        } else {
+            // image / prior of this thread's row in virtual tile `tile` (b = -1 past the end of a partial last tile)
+            auto locate = [&](int tile, int& b, int& p) {
+                const int l = level_of_tile(*lvp, tile);
+                const unsigned lr = (unsigned)(tile - lvp->tile0[l]) * CE_ROWS + (unsigned)t, n = (unsigned)lvp->cnt[l];
+                if (lr >= (unsigned)lvp->rows[l]) { b = -1; p = 0; return; }
+                const unsigned bb = lr / n;
+                b = (int)bb;
+                p = lvp->start[l] + (int)(lr - bb * n);
+            };
+            int cb = -1, cp = 0, nb = -1, np = 0;
+            const int T = (int)full_tiles;
+            int vt = T > 0 ? (int)(((long long)blockIdx.x * lvp->perm_stride) % T) : 0;       // same walk as the producer
+            if ((long long)blockIdx.x < full_tiles) { locate(vt, cb, cp); pre = fused_prefetch_bp(fm, cb, cp, cb >= 0); }
+            for (long long k = blockIdx.x; k < full_tiles; k += gridDim.x) {
+                const bool valid = cb >= 0;
+                const long long row = (long long)cb * P + cp;
+                vt += lvp->perm_inc;
+                if (vt >= T) vt -= T;
+                if (k + gridDim.x < full_tiles) { locate(vt, nb, np); nxt = fused_prefetch_bp(fm, nb, np, nb >= 0); }
                 fused_match_rows(fm, (unsigned)row, valid, pre);
                 pre = nxt;
+                mbar_wait(&s_full[s], ph);
+                float ce = 0.0f;
+                if (valid) ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);
+                if (valid) ce_out[row] = ce;
+                cb = nb; cp = np;
+                if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
             }
-            mbar_wait(&s_full[s], ph);
-            float ce = 0.0f;
-            if (valid) ce = row_cross_entropy<C, true>(reinterpret_cast<const float*>(smem_raw + (size_t)s * TILE_BYTES) + t * C, C - 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[s]);
-            if (valid) ce_out[row] = ce;
-            row = row_n;
-            if (++s == CE_STAGES) { s = 0; ph ^= 1u; }
         }
         // rows past the last full tile (or every row when the pointers are not 16-byte aligned): plain loads
         if (!LEVELS) {
@@ -1331,7 +1362,17 @@ static int multibox_step_levels_impl(const LevelTab& lv, const FusedMatch& fm, M
     const long long rows = (long long)B * P;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS + lv.n;
     const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
-    SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, prm.ce_w, rows, fm, lv));
+    LevelTab lt = lv;
+    {
+        // stride ~ 0.618 T, coprime with T: consecutive visits land in different levels in proportion to their sizes
+        const long long T = lv.tile0[lv.n];
+        auto gcd = [](long long a, long long b) { while (b) { const long long c = a % b; a = b; b = c; } return a; };
+        long long S = std::max<long long>(1, (long long)(0.6180339887 * (double)T));
+        while (S > 1 && gcd(S, T) != 1) --S;
+        lt.perm_stride = (int)S;
+        lt.perm_inc = T > 0 ? (int)(((long long)grid_ce * S) % T) : 0;
+    }
+    SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, prm.ce_w, rows, fm, lt));
     count_launch();
 
     const size_t smem_mn = mine_smem_bytes(P);
