@@ -162,6 +162,12 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     if (bulk) {
         if (t == 0) { mbar_expect_tx(&s_bar, bytes); bulk_g2s(s_conf, src, bytes, &s_bar); }
         mbar_wait(&s_bar, 0u);
+    } else if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 7u) == 0) {
+        // 8-byte aligned rows (e.g. an odd image of a level with an odd half-count of priors): float2 loads
+        const float2* src2 = reinterpret_cast<const float2*>(src);
+        float2* dst2 = reinterpret_cast<float2*>(s_conf);
+        for (int i = t; i < (nrows * C) / 2; i += SC_T) dst2[i] = __ldg(src2 + i);
+        __syncthreads();
     } else {
         for (int i = t; i < nrows * C; i += SC_T) s_conf[i] = __ldg(src + i);
         __syncthreads();

@@ -211,9 +211,14 @@ class MultiboxHead:
             raise ValueError(f"expected 1..{_lib.MAX_LEVELS} levels with one loc and one conf tensor each")
         B = int(conf_levels[0].shape[0])
         locs, confs = [], []
+        def rows(t, width):
+            # the common case (fp32, on this device, dense) costs no torch call beyond the view
+            if not (t.dtype == torch.float32 and t.device == self.dev and t.is_contiguous()):
+                t = t.to(device=self.dev, dtype=torch.float32).contiguous()
+            return t.detach().view(B, -1, width)
+
         for lo, co in zip(loc_levels, conf_levels):
-            lo = lo.detach().to(device=self.dev, dtype=torch.float32).reshape(B, -1, 4).contiguous()
-            co = co.detach().to(device=self.dev, dtype=torch.float32).reshape(B, -1, self.C).contiguous()
+            lo, co = rows(lo, 4), rows(co, self.C)
             if lo.shape[1] != co.shape[1]:
                 raise ValueError(f"level with {lo.shape[1]} loc rows but {co.shape[1]} conf rows")
             locs.append(lo)
