@@ -130,6 +130,7 @@ __device__ __forceinline__ FusedPre fused_prefetch(const FusedMatch& m, unsigned
     return fused_prefetch_bp(m, b, (int)(row - (unsigned)b * (unsigned)m.P), valid);
 }
 
+template <bool MULTI = false>       // MULTI: a warp may span three or more images (per-level layout only)
 __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned row, bool valid, const FusedPre& pre)
 {
     const int lane = threadIdx.x & 31;
@@ -137,6 +138,36 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
     const int b = pre.b, p = pre.p;
     const float4 pb = pre.pb;
     const float pa = box_area(pb);
+    if (MULTI && pre.b_last - pre.b_first >= 2) {
+        // The warp's 32 rows belong to three or more images (only the per-level layout does this, in the levels with a
+        // handful of priors per image): walking the images one after the other would leave most lanes idle for a long
+        // chain.  Each lane matches its own row against its own image's gts instead; the per-gt arg-max goes straight
+        // to the 64-bit atomicMax (same key: highest IoU, then lowest prior - T2), the per-prior best stays strict-> (T1).
+        if (valid) {
+            const int off0 = m.gt_off[b], G = m.gt_off[b + 1] - off0;
+            float bst = 0.0f;
+            float cls_b = G > 0 ? m.gt_cls[off0] : (float)m.bg_class;
+            for (int g = 0; g < G; ++g) {
+                const float4 gb = m.gt_xyxy[off0 + g];
+                const float dx = __fsub_rn(fminf(gb.z, pb.z), fmaxf(gb.x, pb.x));
+                const float dy = __fsub_rn(fminf(gb.w, pb.w), fmaxf(gb.y, pb.y));
+                float v = 0.0f;
+                if (dx > 0.0f && dy > 0.0f) {
+                    const float inter = __fmul_rn(dx, dy);
+                    v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(box_area(gb), pa), inter));
+                    if (v > bst) { bst = v; cls_b = m.gt_cls[off0 + g]; }
+                }
+                if (v != 0.0f || p == 0)                    // an all-zero IoU row resolves to prior 0 (T2)
+                    atomicMax(&m.best_key[off0 + g],
+                              ((unsigned long long)(__float_as_uint(v) | 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p));
+            }
+            const bool hit = (G > 0) && !(bst < m.pos_iou);                           // T6
+            const int c = hit ? (int)cls_b : m.bg_class;
+            m.cls_u8[row] = (uint8_t)c;
+            if (c != m.bg_class) atomicAdd(&m.npos_acc[b], 1);
+        }
+        return;
+    }
     float best = 0.0f;                 // IoU >= 0 and ties keep the first gt: (0, gt 0) equals max() over the column
     int g_mine = 0;
     float cls_mine = (float)m.bg_class;
@@ -423,7 +454,7 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
                 vt += lvp->perm_inc;
                 if (vt >= T) vt -= T;
                 if (k + gridDim.x < full_tiles) { locate(vt, nb, np); nxt = fused_prefetch_bp(fm, nb, np, nb >= 0); }
-                fused_match_rows(fm, (unsigned)row, valid, pre);
+                fused_match_rows<true>(fm, (unsigned)row, valid, pre);
                 pre = nxt;
                 mbar_wait(&s_full[s], ph);
                 float ce = 0.0f;
@@ -465,7 +496,7 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
                     const bool valid = lr < rows_l;
                     const unsigned b = valid ? (unsigned)(lr / n) : 0u;
                     const long long row = valid ? (long long)b * P + lvp->start[l] + (int)(lr - (long long)b * n) : total_rows;
-                    if (MATCH) fused_match_rows(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
+                    if (MATCH) fused_match_rows<true>(fm, (unsigned)row, valid, fused_prefetch(fm, (unsigned)row, valid));
                     if (valid) {
                         ce_out[row] = row_cross_entropy<C, true>(lvp->conf[l] + (size_t)lr * C, C - 1);
                         if (ZERO_FILL) {
