@@ -274,6 +274,16 @@ int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
                                  uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
                                  void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
                                  void* stream);
+/* ... and of a batch sharded by image over R GPUs: ssdhead_multibox_step_sharded on per-level tensors. */
+int ssdhead_multibox_step_levels_sharded(const ssdhead_levels* levels,
+                                 const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                 const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                                 double* sums_dev, float* losses_dev,
+                                 uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                                 void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                                 int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev,
+                                 int32_t* err_flag_dev, void* stream);
 /* ssdhead_detect on per-level tensors (grad pointers unused). */
 int ssdhead_detect_levels(const ssdhead_levels* levels, const float* pri_cxcywh_dev,
                           int B, int P, int C, float min_score, float iou_thr, int top_k,
@@ -313,6 +323,12 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* ctx, const float* loc_dev, const 
                                   int B, int sumG, int neg_ratio, float pos_iou,
                                   double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
                                   void* stream);
+/* ssdhead_ctx_multibox_loss_dev on per-level head tensors (ssdhead_levels, gradients inside the struct): one GPU, or
+ * - after ssdhead_ctx_xchg_import - the sharded two-kernel step with global normalisation. */
+int ssdhead_ctx_multibox_loss_levels_dev(ssdhead_ctx* ctx, const ssdhead_levels* levels,
+                                         const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                         int B, int sumG, int neg_ratio, float pos_iou,
+                                         double* sums_dev, float* losses_dev, void* stream);
 /* The same step in two halves for a batch sharded by image over several GPUs: `begin` runs the match and
  * the CE streaming kernel and hands back a device pointer to this rank's int32 positive count; the
  * caller all-reduces it (NCCL, 4 bytes) and passes the total to `end` as npos_norm_dev (null = local

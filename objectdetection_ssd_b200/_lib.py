@@ -65,6 +65,9 @@ SIGNATURES = {
     "ssdhead_pack_gt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "ssdhead_multibox_step_levels": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _sz, _vp, _sz, _vp]),
+    "ssdhead_multibox_step_levels_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
+                                                  _vp, _sz, _vp, _sz, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
+    "ssdhead_ctx_multibox_loss_levels_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "ssdhead_detect_levels": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -261,6 +261,23 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
                                  nullptr, nullptr, c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, stream);
 }
 
+int ssdhead_ctx_multibox_loss_levels_dev(ssdhead_ctx* c, const ssdhead_levels* levels,
+                                         const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                                         int B, int sumG, int neg_ratio, float pos_iou,
+                                         double* sums, float* losses, void* stream)
+{
+    if (!c || !levels) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    if (c->xchg_R > 1)
+        return ssdhead_multibox_step_levels_sharded(levels, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
+                                                    neg_ratio, pos_iou, sums, losses, c->cls_u8, c->best_prior, c->npos,
+                                                    c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes,
+                                                    c->xchg_R, c->xchg_rank, ++c->xchg_seq, c->xchg_peers_dev, c->xchg_local, c->err_flag, stream);
+    return ssdhead_multibox_step_levels(levels, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
+                                        neg_ratio, pos_iou, sums, losses, c->cls_u8, c->best_prior, c->npos,
+                                        c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, stream);
+}
+
 int ssdhead_ctx_xchg_export(ssdhead_ctx* c, void* handle64_out)
 {
     if (!c || !handle64_out) return SSDHEAD_E_BADARG;

@@ -1417,6 +1417,7 @@ static int multibox_step_levels_impl(const LevelTab& lv, const FusedMatch& fm, M
         count_launch();
         return 0;
     }
+    if (prm.xchg_R > 1) return SSDHEAD_E_UNSUPPORTED;    // the peer exchange needs the co-resident grid
     // does not fit co-resident: separate finaliser, ordinary mining kernel
     SSD_CHECK_CUDA(launch_pdl(2, match_finalize_kernel, dim3(B), dim3(64), 0, st, fm.gt_cls, fm.gt_off, B, P, C - 1,
                               prm.best_prior_w, prm.npos_w, prm.cls_rw, prm.best_key, prm.npos_acc, image_counter));
@@ -1430,13 +1431,14 @@ static int multibox_step_levels_impl(const LevelTab& lv, const FusedMatch& fm, M
 }
 }  // extern "C++"
 
-int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
-                                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
-                                 const float* pri_xyxy, const float* pri_cxcywh,
-                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
-                                 double* sums, float* losses,
-                                 uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
-                                 void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+static int step_levels_common(const ssdhead_levels* levels,
+                              const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                              const float* pri_xyxy, const float* pri_cxcywh,
+                              int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                              double* sums, float* losses,
+                              uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                              void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
+                              int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag)
 {
     if (!levels || B < 0 || P <= 0 || sumG < 0 || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!gt_off || !pri_xyxy || !pri_cxcywh || !sums || !losses || !cls_u8 || !npos || !ws_loss || !ws_match) return SSDHEAD_E_BADARG;
@@ -1500,8 +1502,42 @@ int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
     prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
     prm.best_key = best_key; prm.npos_acc = npos_acc;
     prm.arrive_total = (unsigned long long*)(image_counter + 2);
+    prm.xchg_R = R; prm.xchg_rank = rank; prm.xchg_seq = seq;
+    prm.xchg_peers = (unsigned long long* const*)peers_dev; prm.xchg_local = (unsigned long long*)xchg_local; prm.err_flag = err_flag;
     return with_grads ? multibox_step_levels_impl<true>(lv, fm, prm, B, P, image_counter, st)
                       : multibox_step_levels_impl<false>(lv, fm, prm, B, P, image_counter, st);
+}
+
+int ssdhead_multibox_step_levels(const ssdhead_levels* levels,
+                                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                                 const float* pri_xyxy, const float* pri_cxcywh,
+                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                                 double* sums, float* losses,
+                                 uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                                 void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream)
+{
+    return step_levels_common(levels, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, B, P, C, sumG, neg_ratio, pos_iou,
+                              sums, losses, cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream,
+                              0, 0, 0u, nullptr, nullptr, nullptr);
+}
+
+// the per-level step of a batch sharded by image over R GPUs (peer-memory exchange inside the mining kernel, as in
+// ssdhead_multibox_step_sharded)
+int ssdhead_multibox_step_levels_sharded(const ssdhead_levels* levels,
+                                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                                 const float* pri_xyxy, const float* pri_cxcywh,
+                                 int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                                 double* sums, float* losses,
+                                 uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                                 void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes,
+                                 int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev, int32_t* err_flag_dev,
+                                 void* stream)
+{
+    if (R < 1 || R > XCHG_MAX_R || rank < 0 || rank >= R || seq == 0u) return SSDHEAD_E_BADARG;
+    if (R > 1 && (!peers_dev || !xchg_local_dev || !err_flag_dev)) return SSDHEAD_E_BADARG;
+    return step_levels_common(levels, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, B, P, C, sumG, neg_ratio, pos_iou,
+                              sums, losses, cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream,
+                              R, rank, seq, peers_dev, xchg_local_dev, err_flag_dev);
 }
 
 size_t ssdhead_xchg_bytes(void) { return (size_t)XCHG_WORDS * 8; }

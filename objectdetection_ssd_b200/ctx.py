@@ -92,6 +92,14 @@ class SSDHeadContext:
             self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
             float(pos_iou), sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_dev")
 
+    def loss_levels_dev(self, levels, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, sums_ptr, losses_ptr, stream,
+                        neg_ratio: int = 3, pos_iou: float = 0.5):
+        """``loss_dev`` on per-level head tensors: ``levels`` is a filled ``_lib.Levels`` (conf / loc / grad pointers per
+        level).  After ``xchg_import`` this is the sharded two-kernel step with global normalisation."""
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_levels_dev(
+            self._h, C.addressof(levels), gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
+            float(pos_iou), sums_ptr, losses_ptr, stream), "ssdhead_ctx_multibox_loss_levels_dev")
+
     def loss_begin(self, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, grad_loc_ptr, grad_conf_ptr, stream,
                    pos_iou: float = 0.5) -> int:
         """First half of a sharded step; returns the device address of this rank's int32 positive count."""

@@ -55,6 +55,27 @@ def _worker(rank, world, port, q):
                          sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
         torch.cuda.synchronize()
         assert not ctx.xchg_error()
+        # --- the same sharded step on the six per-level tensors (ssdhead_multibox_step_levels_sharded)
+        from objectdetection_ssd_b200 import _lib as L
+        counts, s0 = (5776, 2166, 600, 150, 36, 4), 0
+        lv = L.Levels()
+        lv.num_levels = len(counts)
+        keep = []
+        for i, n in enumerate(counts):
+            lc, cc = tl[:, s0:s0 + n].contiguous(), tc[:, s0:s0 + n].contiguous()
+            glv, gcv = torch.empty_like(lc), torch.empty_like(cc)
+            keep.append((lc, cc, glv, gcv))
+            lv.count[i] = n
+            lv.loc[i], lv.conf[i], lv.grad_loc[i], lv.grad_conf[i] = lc.data_ptr(), cc.data_ptr(), glv.data_ptr(), gcv.data_ptr()
+            s0 += n
+        sums_lv = torch.empty(2, dtype=torch.float64, device=dev)
+        losses_lv = torch.empty(2, device=dev)
+        ctx.loss_levels_dev(lv, tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
+                            sums_lv.data_ptr(), losses_lv.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert not ctx.xchg_error()
+        assert torch.equal(losses_lv, losses) and torch.equal(sums_lv, sums), (losses_lv, losses)
+        assert torch.equal(torch.cat([k[2] for k in keep], 1), gl) and torch.equal(torch.cat([k[3] for k in keep], 1), gcf)
         # --- NCCL route through the drop-in surface
         head = MultiboxHead(pri, dev)
         l2 = tl.clone().requires_grad_(True)
