@@ -138,6 +138,17 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const unsigned long long* p) {
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Polling load: ld.cg may keep hitting a stale copy of the line in the SM's near L2 partition when the data was written
+// with a plain store from the other die (observed on B200: a poll that never saw the store); a relaxed gpu-scope load is
+// coherent at the point the writer's store becomes visible.
+__device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ int ld_cg_s32(const int* p) {
     int v;
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -33,7 +33,7 @@ __global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nch
 }  // namespace ssdhead
 
 struct ssdhead_ctx {
-    int device, maxB, P, C, max_sumG, top_k, last_detect_B;
+    int device, maxB, P, C, max_sumG, top_k, last_detect_B, last_loss_B;
     // cross-GPU exchange (sharded batches)
     int xchg_R, xchg_rank;
     unsigned int xchg_seq;
@@ -56,13 +56,26 @@ struct ssdhead_ctx {
     float *losses;
     // workspaces
     void *ws_match, *ws_loss, *ws_detect;
-    size_t ws_match_bytes, ws_loss_bytes, ws_detect_bytes;
+    size_t ws_match_bytes, ws_loss_bytes, ws_loss_total, ws_detect_bytes;
     // detect outputs (host-buffer path)
     float *det_boxes, *det_prob;
     int32_t *det_cls, *det_prior, *det_cnt;
     // pinned scratch for small results
     float* h_losses;
 };
+
+// The loss workspace keeps its counters and per-image partial sums zeroed between steps, but their extent depends on
+// the batch size (include/ssdhead.h: "re-zero a buffer before reusing it with another shape"): re-zero the headers of
+// all chunk workspaces when B changes.
+static int ctx_loss_ws_for(ssdhead_ctx* c, int B, cudaStream_t st)
+{
+    if (c->last_loss_B == B) return 0;
+    const size_t head = 16 + (size_t)c->maxB * 16 + 256;
+    for (size_t off = 0; off + head <= c->ws_loss_total; off += c->ws_loss_bytes)
+        SSD_CHECK_CUDA(cudaMemsetAsync((char*)c->ws_loss + off, 0, std::min(head, c->ws_loss_bytes), st));
+    c->last_loss_B = B;
+    return 0;
+}
 
 #define CTX_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
 
@@ -182,6 +195,7 @@ int ssdhead_ctx_create(ssdhead_ctx** out, int device, int maxB, int P, int C, in
         CTX_CUDA(cudaMemset(c->ws_match, 0, c->ws_match_bytes));
         if (c->ws_loss_bytes) {
             // one workspace per chunk slot so chunk i+1 can stream while chunk i is being mined
+            c->ws_loss_total = c->ws_loss_bytes * kMaxChunks;
             CTX_CUDA(cudaMalloc(&c->ws_loss, c->ws_loss_bytes * kMaxChunks));
             CTX_CUDA(cudaMemset(c->ws_loss, 0, c->ws_loss_bytes * kMaxChunks));
         }
@@ -219,6 +233,7 @@ int ssdhead_ctx_multibox_loss_begin(ssdhead_ctx* c, const float* conf,
     if (!c) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
     cudaStream_t st = (cudaStream_t)stream;
+    { const int zr = ctx_loss_ws_for(c, B, st); if (zr) return zr; }
     // the natural match rides inside the CE streaming kernel; a small finaliser applies the forced-match override
     const int rc = ssdhead_ce_match_stream(conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, B, c->P, c->C, sumG, pos_iou,
                                            nullptr, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
@@ -251,6 +266,7 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
 {
     if (!c) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    { const int zr = ctx_loss_ws_for(c, B, (cudaStream_t)stream); if (zr) return zr; }
     if (c->xchg_R > 1)
         return ssdhead_multibox_step_sharded(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
                                              neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
@@ -268,6 +284,7 @@ int ssdhead_ctx_multibox_loss_levels_dev(ssdhead_ctx* c, const ssdhead_levels* l
 {
     if (!c || !levels) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    { const int zr = ctx_loss_ws_for(c, B, (cudaStream_t)stream); if (zr) return zr; }
     if (c->xchg_R > 1)
         return ssdhead_multibox_step_levels_sharded(levels, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
                                                     neg_ratio, pos_iou, sums, losses, c->cls_u8, c->best_prior, c->npos,
@@ -331,6 +348,7 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     SSD_CHECK_CUDA(cudaSetDevice(c->device));
     const int P = c->P, C = c->C;
     const bool grads = grad_loc_h != nullptr;
+    { const int zr = ctx_loss_ws_for(c, -B, c->s_main); if (zr) return zr; }   // (-B: the chunked layout of batch B)
 
     // gt -> device, match on the auxiliary stream
     if (sumG > 0) {

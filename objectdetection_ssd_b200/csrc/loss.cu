@@ -559,7 +559,7 @@ struct MineParams {
     float* grad_conf;
     uint32_t* mined_mask;
     double* partials;            // [B][2]
-    unsigned int* done_counter;  // self-resetting
+    unsigned int* done_counter;  // (unused since the reducer CTA is fixed; the word stays reserved in the workspace)
     // fused forced-match finaliser (FIN = true; cooperative launch, all CTAs co-resident):
     uint8_t* cls_rw;             // class bytes, patched in place
     int* best_prior_w;           // [sumG] out
@@ -619,7 +619,6 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     __shared__ float s_garea[MN_GC];
     __shared__ int s_gbp[MN_GC];
     __shared__ double s_redd[2][MN_W];
-    __shared__ int s_is_last;
 
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int P = p.P;
@@ -919,7 +918,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 s_total = tot;
             } else {
                 unsigned long long w;
-                while ((unsigned)((w = ld_cg_u64(p.arrive_total)) >> 32) < gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
+                while ((unsigned)((w = ld_relaxed_gpu_u64(p.arrive_total)) >> 32) < gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
                 s_total = (int)(unsigned)w;
             }
         }
@@ -1059,26 +1058,33 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     acc_ce = warp_sum(acc_ce);
     if (lane == 0) { s_redd[0][warp] = acc_l1; s_redd[1][warp] = acc_ce; }
     __syncthreads();
-    // The publisher is the LAST thread of the CTA: its fence only has to drain its own stores, and unlike thread 0 it
-    // normally wrote no gradient row (rows go to threads 0..nsel-1), so the fence does not wait on scattered DRAM
-    // writes (measured: 11 us -> ~1 us at B=256).
+    // Publication without a fence or a ticket: both sums are non-negative (sums of |d| and of CE >= +0) or NaN, so their
+    // sign bit is free and serves as the "valid" mark of a partial; the workspace is zero between steps.  One fixed CTA
+    // polls the partials until every sign bit is set, adds them in a fixed order (run-to-run deterministic) and zeroes
+    // them again.  The polls are relaxed gpu-scope loads: an ld.cg poll was observed to spin forever on a stale copy of
+    // the line in the near L2 partition while the store sat in the far one (B200 has two L2 partitions).
+    constexpr unsigned long long SIGN = 0x8000000000000000ull;
     if (t == MN_T - 1) {
         double a = 0.0, c = 0.0;
         for (int w = 0; w < MN_W; ++w) { a += s_redd[0][w]; c += s_redd[1][w]; }
-        p.partials[2 * b] = a;
-        p.partials[2 * b + 1] = c;
-        __threadfence();
-        const unsigned done = atomicAdd(p.done_counter, 1u);
-        s_is_last = (done == gridDim.x - 1u) ? 1 : 0;
+        unsigned long long* pp = reinterpret_cast<unsigned long long*>(p.partials) + 2 * (size_t)b;
+        st_relaxed_gpu_u64(pp, (unsigned long long)__double_as_longlong(a) | SIGN);
+        st_relaxed_gpu_u64(pp + 1, (unsigned long long)__double_as_longlong(c) | SIGN);
     }
-    __syncthreads();
+    __syncthreads();                                         // (s_redd is reused by the reducer below)
     LPHASE(6);
-    if (s_is_last) {
-        __threadfence();
+    // The reducer is fixed: the CTA of the last image (dispatched last); it polls until every partial has arrived.
+    if (b == (int)gridDim.x - 1) {
         double a = 0.0, c = 0.0;
         for (int s = t; s < (int)gridDim.x; s += MN_T) {
-            a += __ldcg(&p.partials[2 * s]);
-            c += __ldcg(&p.partials[2 * s + 1]);
+            unsigned long long* pp = reinterpret_cast<unsigned long long*>(p.partials) + 2 * (size_t)s;
+            unsigned long long ua, uc;
+            unsigned spins = 0;
+            do { ua = ld_relaxed_gpu_u64(pp); uc = ld_relaxed_gpu_u64(pp + 1); } while (((ua & uc) >> 63) == 0ull && ++spins < (1u << 24));
+            a += __longlong_as_double((long long)(ua & ~SIGN));
+            c += __longlong_as_double((long long)(uc & ~SIGN));
+            __stcg(pp, 0ull);                                  // leave the workspace zeroed
+            __stcg(pp + 1, 0ull);
         }
         a = warp_sum(a);
         c = warp_sum(c);
@@ -1112,7 +1118,6 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             const double N = (double)npos_total;
             p.losses[0] = (float)(a / (4.0 * N));
             p.losses[1] = (float)(c / N);
-            *p.done_counter = 0u;
             if (FIN) {                   // every CTA has read the total (it did so before it reported done)
                 p.npos_w[p.B] = (p.xchg_R > 1) ? (int)(unsigned)ld_cg_u64(p.arrive_total) : npos_total;    // this rank's own count
                 *p.arrive_total = 0ull;
