@@ -146,6 +146,11 @@ __device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const unsigned long long*
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }

@@ -305,7 +305,7 @@ match_finalize_kernel(const float* __restrict__ gt_cls, const int* __restrict__ 
         if (done == gridDim.x - 1) {                         // last image: batch total, fixed order
             __threadfence();
             int tot = 0;
-            for (int i = 0; i < B; ++i) tot += ld_cg_s32(&npos[i]);
+            for (int i = 0; i < B; ++i) tot += ld_relaxed_gpu_s32(&npos[i]);   // other CTAs of this grid wrote them: coherent loads
             npos[B] = tot;
             *image_counter = 0u;
         }

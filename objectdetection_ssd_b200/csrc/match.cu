@@ -179,7 +179,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         uint32_t* s_bp = reinterpret_cast<uint32_t*>(s_key);                    // reuse: best prior per gt
         uint32_t p = 0u;
         if (t < G) {
-            p = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + t]) & 0xffffffffull);
+            p = 0xffffffffu - (uint32_t)(ld_relaxed_gpu_u64(&best_key[off0 + t]) & 0xffffffffull);
             best_key[off0 + t] = 0ull;                                          // leave the workspace zeroed
             best_prior[off0 + t] = (int)p;
         }
@@ -208,11 +208,11 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         }
     } else {
         for (int g = t; g < G; g += MT) {
-            const uint32_t p = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g]) & 0xffffffffull);
+            const uint32_t p = 0xffffffffu - (uint32_t)(ld_relaxed_gpu_u64(&best_key[off0 + g]) & 0xffffffffull);
             best_prior[off0 + g] = (int)p;
             bool winner = true;
             for (int g2 = g + 1; g2 < G; ++g2) {
-                const uint32_t p2 = 0xffffffffu - (uint32_t)(ld_cg_u64(&best_key[off0 + g2]) & 0xffffffffull);
+                const uint32_t p2 = 0xffffffffu - (uint32_t)(ld_relaxed_gpu_u64(&best_key[off0 + g2]) & 0xffffffffull);
                 if (p2 == p) { winner = false; break; }
             }
             if (!winner) continue;
@@ -242,7 +242,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
     if (t == 0) {
         int e = 0;
         for (int w = 0; w < MT / 32; ++w) e += s_red[w];
-        npos[b] = ld_cg_s32(&npos_acc[b]) + e;
+        npos[b] = ld_relaxed_gpu_s32(&npos_acc[b]) + e;
         npos_acc[b] = 0;
         tile_counter[b] = 0u;
         __threadfence();
@@ -250,7 +250,7 @@ match_kernel(const float4* __restrict__ gt_xyxy, const float* __restrict__ gt_cl
         if (done == gridDim.y - 1) {                                            // last image: batch total, fixed order
             __threadfence();
             int tot = 0;
-            for (int i = 0; i < B; ++i) tot += ld_cg_s32(&npos[i]);
+            for (int i = 0; i < B; ++i) tot += ld_relaxed_gpu_s32(&npos[i]);
             npos[B] = tot;
             *image_counter = 0u;
         }
