@@ -253,7 +253,8 @@ int ssdhead_voc_ap(const float* det_boxes_xyxy_dev, const int32_t* det_cls_dev, 
  * layout [B, n_l, 21] of its level (n_l = H*W*A priors, cell-major then anchor - the prior order of Util.py:105-137),
  * so these entry points read the level tensors in place and write the gradients per level in the same layout:
  * no concatenated tensor exists in either direction.  count[l] priors per image in level l (sum = P), conf[l]
- * [B, count[l], C], loc[l] [B, count[l], 4], grads likewise (all or none), every pointer 16-byte aligned. */
+ * [B, count[l], C], loc[l] [B, count[l], 4], grads likewise (all or none); loc / grad_loc pointers 16-byte aligned, and
+ * conf / grad_conf too for the fast (TMA) path - a level with unaligned conf pointers is read with plain loads. */
 #define SSDHEAD_MAX_LEVELS 8
 typedef struct ssdhead_levels {
     int32_t      num_levels;

@@ -1073,7 +1073,7 @@ int ssdhead_detect_levels(const ssdhead_levels* levels, const float* pri_cxcywh,
     for (int l = 0; l < dl.n; ++l) {
         const int n = levels->count[l];
         if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
-        if (!aligned16(levels->conf[l]) || !aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;
+        if (!aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;             // float4 rows; conf rows may sit anywhere
         dl.cnt[l] = n; dl.start[l] = sum; dl.tile0[l] = t0;
         dl.conf[l] = levels->conf[l]; dl.loc[l] = levels->loc[l];
         sum += n;

@@ -1461,10 +1461,13 @@ static int step_levels_common(const ssdhead_levels* levels,
     for (int l = 0; l < lv.n; ++l) {
         const int n = levels->count[l];
         if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
-        if (!aligned16(levels->conf[l]) || !aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;
+        if (!aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;                        // float4 rows
         const bool g = levels->grad_conf[l] != nullptr;
         if (g != (levels->grad_loc[l] != nullptr)) return SSDHEAD_E_BADARG;
-        if (g && (!aligned16(levels->grad_conf[l]) || !aligned16(levels->grad_loc[l]))) return SSDHEAD_E_ALIGN;
+        if (g && !aligned16(levels->grad_loc[l])) return SSDHEAD_E_ALIGN;
+        // conf / grad_conf rows are 84 bytes: a level whose pointers are not 16-byte aligned (e.g. a view into a larger
+        // tensor) cannot ride the TMA pipeline and goes through the plain-load path entirely
+        const bool tma_ok = aligned16(levels->conf[l]) && (!g || aligned16(levels->grad_conf[l]));
         with_grads += g ? 1 : 0;
         lv.cnt[l] = n; lv.start[l] = sum; lv.tile0[l] = t0;
         lv.conf[l] = levels->conf[l]; lv.loc[l] = levels->loc[l]; lv.gconf[l] = levels->grad_conf[l]; lv.gloc[l] = levels->grad_loc[l];
@@ -1472,7 +1475,7 @@ static int step_levels_common(const ssdhead_levels* levels,
         const long long rows_l = (long long)B * n;
         lv.rows[l] = (int)rows_l;
         // the partial last tile of a level rides the TMA pipeline too when its byte counts are multiples of 16
-        t0 += (int)(rows_l / CE_ROWS) + ((rows_l % CE_ROWS) != 0 && (rows_l % 4) == 0 ? 1 : 0);
+        if (tma_ok) t0 += (int)(rows_l / CE_ROWS) + ((rows_l % CE_ROWS) != 0 && (rows_l % 4) == 0 ? 1 : 0);
     }
     for (int l = lv.n; l <= MAX_LEVELS; ++l) { lv.start[l] = sum; lv.tile0[l] = t0; }
     if (sum != P) return SSDHEAD_E_BADARG;

@@ -197,3 +197,36 @@ def test_detect_unaligned_prior_count_takes_the_plain_load_path():
     out2 = detect(_head(pri), loc, conf, 0.02, 0.45, 50)             # own softmax + decode on the same odd shape
     torch.cuda.synchronize()
     assert (out2["cnt"].cpu() == out["cnt"].cpu()).all()
+
+
+def test_detect_randomised_differential():
+    """Seeded random shapes, thresholds, top_k, tie densities and overlap densities (P not a multiple of 4 included):
+    detections must equal the oracle's exactly (stage-isolated, so no expf boundary effects)."""
+    from objectdetection_ssd_b200.head import MultiboxHead, detect_from_scores
+    g = torch.Generator().manual_seed(2024)
+    for trial in range(24):
+        P = int(torch.randint(33, 2600, (1,), generator=g))
+        B = int(torch.randint(1, 4, (1,), generator=g))
+        top_k = [1, 5, 50, 200, 500][trial % 5]
+        min_score = [0.01, 0.05, 0.3][trial % 3]
+        iou_thr = [0.3, 0.45, 0.7][(trial // 3) % 3]
+        ncls = [1, 3, 20][(trial // 2) % 3]                       # how many foreground classes are populated
+        spread = [0.05, 0.3][(trial // 4) % 2]                   # small spread -> heavy overlap
+        cx = 0.5 + spread * torch.randn(B, P, 2, generator=g)
+        wh = 0.05 + 0.25 * torch.rand(B, P, 2, generator=g)
+        boxes = torch.cat([cx, wh], 2).contiguous()
+        probs = torch.zeros(B, P, 21)
+        cls_ids = torch.randperm(20, generator=g)[:ncls]
+        raw = torch.rand(B, P, ncls, generator=g) ** 3           # skewed towards small scores
+        if trial % 4 == 1:
+            raw = torch.round(raw * 16) / 16                     # exact ties
+        probs[:, :, cls_ids] = raw * 0.9
+        probs[..., 20] = 1.0 - probs[..., :20].max(-1).values
+        pri = torch.cat([torch.rand(P, 2, generator=g), 0.1 + 0.2 * torch.rand(P, 2, generator=g)], 1)   # unused by from_scores
+        out = detect_from_scores(MultiboxHead(pri, "cuda"), boxes, probs, min_score, iou_thr, top_k)
+        torch.cuda.synchronize()
+        ref = _oracle_stage(boxes, probs, min_score, iou_thr, top_k)
+        try:
+            _check_exact(out, ref, top_k)
+        except AssertionError as e:
+            raise AssertionError(f"trial {trial}: P={P} B={B} top_k={top_k} min_score={min_score} iou={iou_thr} ncls={ncls}: {e}")

@@ -114,3 +114,41 @@ def test_detect_levels_equals_concatenated(bias, B):
         k = int(ref["cnt"][i])
         for key in ("boxes", "prob", "cls", "prior"):
             assert torch.equal(out[key][i, :k], ref[key][i, :k]), (i, key)
+
+
+def test_levels_random_splits_equal_concatenated():
+    """Random level structures (1..8 levels, odd and tiny counts, rows not multiples of 4 -> plain-load tails): loss,
+    gradients and detections must stay bit-identical to the concatenated calls."""
+    from objectdetection_ssd_b200.head import PackedGT, detect, detect_levels
+    g = torch.Generator().manual_seed(77)
+    pri = H.priors()
+    P = pri.shape[0]
+    head = _head(pri)
+    for trial in range(8):
+        B = [1, 2, 5, 16][trial % 4]
+        L = int(torch.randint(1, 9, (1,), generator=g))
+        cuts = sorted(set(int(x) for x in torch.randint(1, P, (L - 1,), generator=g).tolist()))
+        if trial == 3:
+            cuts = [P - 7, P - 3, P - 2, P - 1]                  # tiny levels at the end: warps span many images
+        if trial == 5:
+            cuts = [1, 2, 5]                                     # ... and at the start
+        counts = [b - a for a, b in zip([0] + cuts, cuts + [P])]
+        loc, conf, tb, tc = H.train_inputs(60 + trial, B, P)
+        gt = PackedGT(tb, tc, head.dev)
+        ref = head.loss(loc.cuda(), conf.cuda(), gt, with_grads=True)
+        lv = head.loss_levels(_split(loc.cuda(), counts), _split(conf.cuda(), counts), gt, with_grads=True)
+        torch.cuda.synchronize()
+        msg = f"trial {trial}: B={B} counts={counts}"
+        assert torch.equal(lv["losses"], ref["losses"]) and torch.equal(lv["sums"], ref["sums"]), msg
+        assert torch.equal(lv["cls_u8"], ref["cls_u8"]) and torch.equal(lv["best_prior"], ref["best_prior"]), msg
+        assert torch.equal(torch.cat(lv["grad_loc"], 1), ref["grad_loc"]), msg
+        assert torch.equal(torch.cat(lv["grad_conf"], 1), ref["grad_conf"]), msg
+        dl, dc = H.detect_inputs(70 + trial, B, P, bg_bias=7.0)
+        r = detect(head, dl.cuda(), dc.cuda(), 0.01, 0.45, 100)
+        o = detect_levels(head, _split(dl.cuda(), counts), _split(dc.cuda(), counts), 0.01, 0.45, 100)
+        torch.cuda.synchronize()
+        assert torch.equal(o["cnt"], r["cnt"]), msg
+        for i in range(B):
+            k = int(r["cnt"][i])
+            for key in ("boxes", "prob", "cls", "prior"):
+                assert torch.equal(o[key][i, :k], r[key][i, :k]), (msg, i, key)
