@@ -92,6 +92,7 @@ struct FusedMatch {
     uint8_t* cls_u8;
     unsigned long long* best_key;
     int* npos_acc;
+    unsigned short* obj_u16;     // nullable: natural best gt (local index) of every prior, for batches with many gts per image
 };
 
 // Everything the match of one row needs from global memory, fetched ONE TILE AHEAD so the two dependent L2 round trips
@@ -146,6 +147,7 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
         if (valid) {
             const int off0 = m.gt_off[b], G = m.gt_off[b + 1] - off0;
             float bst = 0.0f;
+            int obj_b = 0;
             float cls_b = G > 0 ? m.gt_cls[off0] : (float)m.bg_class;
             for (int g = 0; g < G; ++g) {
                 const float4 gb = m.gt_xyxy[off0 + g];
@@ -155,7 +157,7 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
                 if (dx > 0.0f && dy > 0.0f) {
                     const float inter = __fmul_rn(dx, dy);
                     v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(box_area(gb), pa), inter));
-                    if (v > bst) { bst = v; cls_b = m.gt_cls[off0 + g]; }
+                    if (v > bst) { bst = v; cls_b = m.gt_cls[off0 + g]; obj_b = g; }
                 }
                 if (v != 0.0f || p == 0)                    // an all-zero IoU row resolves to prior 0 (T2)
                     atomicMax(&m.best_key[off0 + g],
@@ -164,12 +166,13 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
             const bool hit = (G > 0) && !(bst < m.pos_iou);                           // T6
             const int c = hit ? (int)cls_b : m.bg_class;
             m.cls_u8[row] = (uint8_t)c;
+            if (m.obj_u16) m.obj_u16[row] = (unsigned short)obj_b;
             if (c != m.bg_class) atomicAdd(&m.npos_acc[b], 1);
         }
         return;
     }
     float best = 0.0f;                 // IoU >= 0 and ties keep the first gt: (0, gt 0) equals max() over the column
-    int g_mine = 0;
+    int g_mine = 0, obj_mine = 0;
     float cls_mine = (float)m.bg_class;
     // bounding box of the warp's 32 consecutive priors: a gt that misses it has IoU 0 with all of them, so the whole
     // pair test, the reduction and the atomic are skipped for that gt (about 3 of 4 gts for the dense 38x38 level)
@@ -233,7 +236,7 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
             const float c_first = __shfl_sync(FULL, mycls, 0);
             const float c_best = __shfl_sync(FULL, mycls, chunk_best < 0 ? 0 : chunk_best);
             if (act) {
-                if (chunk_best >= 0) cls_mine = c_best;
+                if (chunk_best >= 0) { cls_mine = c_best; obj_mine = g0 + chunk_best; }
                 else if (g0 == 0) cls_mine = c_first;
             }
         }
@@ -242,6 +245,7 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
         const bool hit = (g_mine > 0) && !(best < m.pos_iou);                     // T6
         const int c = hit ? (int)cls_mine : m.bg_class;
         m.cls_u8[row] = (uint8_t)c;                                               // natural class; forced matches patched later
+        if (m.obj_u16) m.obj_u16[row] = (unsigned short)obj_mine;
         if (c != m.bg_class) atomicAdd(&m.npos_acc[b], 1);
     }
 }
@@ -559,8 +563,9 @@ struct MineParams {
     float* grad_conf;
     uint32_t* mined_mask;
     double* partials;            // [B][2]
-    unsigned int* done_counter;  // (unused since the reducer CTA is fixed; the word stays reserved in the workspace)
+    unsigned int* done_counter;  // self-resetting
     // fused forced-match finaliser (FIN = true; cooperative launch, all CTAs co-resident):
+    unsigned short* obj_u16;     // nullable: best gt per prior from the streaming kernel (forced ones patched by FIN)
     uint8_t* cls_rw;             // class bytes, patched in place
     int* best_prior_w;           // [sumG] out
     int* npos_w;                 // [B+1] out
@@ -683,6 +688,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 const int c_nat = (int)p.cls_rw[row0 + bp];
                 extra += (c_new != p.bg_class ? 1 : 0) - (c_nat != p.bg_class ? 1 : 0);
                 p.cls_rw[row0 + bp] = (uint8_t)c_new;        // read back below by this same CTA (after the barrier)
+                if (p.obj_u16) p.obj_u16[row0 + bp] = (unsigned short)g;
             }
         }
         if (extra) atomicAdd(&s_fin_extra, extra);
@@ -1027,7 +1033,8 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             const float pa = box_area(pb);
             int obj = -1, ng = 0;
             float nb = 0.0f;
-            for (int g = 0; g < G; ++g) {
+            if (FIN && p.obj_u16) obj = (int)p.obj_u16[row0 + j];   // recorded by the match: no walk over the image's gts
+            else for (int g = 0; g < G; ++g) {
                 float4 gb; float ga; int bp;
                 if (g < MN_GC) { gb = s_gbox[g]; ga = s_garea[g]; bp = s_gbp[g]; }
                 else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = bprior[off0 + g]; }
@@ -1058,33 +1065,30 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     acc_ce = warp_sum(acc_ce);
     if (lane == 0) { s_redd[0][warp] = acc_l1; s_redd[1][warp] = acc_ce; }
     __syncthreads();
-    // Publication without a fence or a ticket: both sums are non-negative (sums of |d| and of CE >= +0) or NaN, so their
-    // sign bit is free and serves as the "valid" mark of a partial; the workspace is zero between steps.  One fixed CTA
-    // polls the partials until every sign bit is set, adds them in a fixed order (run-to-run deterministic) and zeroes
-    // them again.  The polls are relaxed gpu-scope loads: an ld.cg poll was observed to spin forever on a stale copy of
-    // the line in the near L2 partition while the store sat in the far one (B200 has two L2 partitions).
-    constexpr unsigned long long SIGN = 0x8000000000000000ull;
+    // The publisher is the LAST thread of the CTA: its fence only has to drain its own stores, and unlike thread 0 it
+    // normally wrote no gradient row (rows go to threads 0..nsel-1).  The CTA that draws the last ticket adds the
+    // partials in a fixed order (run-to-run deterministic).  (A fence-free variant - sign bit of the non-negative sums as
+    // a "valid" mark, one fixed CTA polling - was measured 1-2 us SLOWER per step, and taught a hardware lesson: its
+    // polls must be relaxed gpu-scope loads; an ld.cg poll spun forever on a stale copy of the line in the SM's near L2
+    // partition while the plain store from the other die sat in the far one.)
+    __shared__ int s_is_last;
     if (t == MN_T - 1) {
         double a = 0.0, c = 0.0;
         for (int w = 0; w < MN_W; ++w) { a += s_redd[0][w]; c += s_redd[1][w]; }
-        unsigned long long* pp = reinterpret_cast<unsigned long long*>(p.partials) + 2 * (size_t)b;
-        st_relaxed_gpu_u64(pp, (unsigned long long)__double_as_longlong(a) | SIGN);
-        st_relaxed_gpu_u64(pp + 1, (unsigned long long)__double_as_longlong(c) | SIGN);
+        p.partials[2 * b] = a;
+        p.partials[2 * b + 1] = c;
+        __threadfence();
+        const unsigned done = atomicAdd(p.done_counter, 1u);
+        s_is_last = (done == gridDim.x - 1u) ? 1 : 0;
     }
-    __syncthreads();                                         // (s_redd is reused by the reducer below)
+    __syncthreads();
     LPHASE(6);
-    // The reducer is fixed: the CTA of the last image (dispatched last); it polls until every partial has arrived.
-    if (b == (int)gridDim.x - 1) {
+    if (s_is_last) {
+        __threadfence();
         double a = 0.0, c = 0.0;
-        for (int s = t; s < (int)gridDim.x; s += MN_T) {
-            unsigned long long* pp = reinterpret_cast<unsigned long long*>(p.partials) + 2 * (size_t)s;
-            unsigned long long ua, uc;
-            unsigned spins = 0;
-            do { ua = ld_relaxed_gpu_u64(pp); uc = ld_relaxed_gpu_u64(pp + 1); } while (((ua & uc) >> 63) == 0ull && ++spins < (1u << 24));
-            a += __longlong_as_double((long long)(ua & ~SIGN));
-            c += __longlong_as_double((long long)(uc & ~SIGN));
-            __stcg(pp, 0ull);                                  // leave the workspace zeroed
-            __stcg(pp + 1, 0ull);
+        for (int s = t; s < (int)gridDim.x; s += MN_T) {     // written by the other CTAs of this grid: coherent loads
+            a += __longlong_as_double((long long)ld_relaxed_gpu_u64(reinterpret_cast<const unsigned long long*>(p.partials) + 2 * (size_t)s));
+            c += __longlong_as_double((long long)ld_relaxed_gpu_u64(reinterpret_cast<const unsigned long long*>(p.partials) + 2 * (size_t)s + 1));
         }
         a = warp_sum(a);
         c = warp_sum(c);
@@ -1118,6 +1122,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             const double N = (double)npos_total;
             p.losses[0] = (float)(a / (4.0 * N));
             p.losses[1] = (float)(c / N);
+            *p.done_counter = 0u;
             if (FIN) {                   // every CTA has read the total (it did so before it reported done)
                 p.npos_w[p.B] = (p.xchg_R > 1) ? (int)(unsigned)ld_cg_u64(p.arrive_total) : npos_total;    // this rank's own count
                 *p.arrive_total = 0ull;
@@ -1175,7 +1180,8 @@ static size_t mine_smem_bytes(int P) { return (size_t)P * 4 + MN_BINS * 4 + (siz
 size_t loss_workspace_bytes(int B, int P, int C)
 {
     if (mine_smem_bytes(P) > 220 * 1024 || P >= 65536) return 0;   // P <= ~31 000 priors
-    return 16 + round_up((size_t)B * 2 * sizeof(double), 16) + round_up((size_t)B * P * sizeof(float), 16);
+    return 16 + round_up((size_t)B * 2 * sizeof(double), 16) + round_up((size_t)B * P * sizeof(float), 16) +
+           round_up((size_t)B * P * sizeof(unsigned short), 16);      // CE, then the best-gt map of large-G batches
 }
 
 static int g_num_sms = 0;
@@ -1257,6 +1263,10 @@ static int launch_mine_fin(MineParams prm, cudaStream_t st)
 }
 
 static float* ws_ce(void* ws, int B) { return (float*)((char*)ws + 16 + round_up((size_t)B * 2 * sizeof(double), 16)); }
+static unsigned short* ws_obj(void* ws, int B, int P) { return (unsigned short*)((char*)ws_ce(ws, B) + round_up((size_t)B * P * sizeof(float), 16)); }
+// the walk over an image's gts in the mining kernel costs G x ~30 instructions per positive row: from this average G on
+// the streaming kernel records the best gt of every prior (2 bytes per row) and the walk disappears
+static bool use_obj_map(int B, int sumG) { return sumG >= 16 * B && sumG <= 65535; }
 
 }  // namespace ssdhead
 
@@ -1289,7 +1299,7 @@ static int ce_match_stream_impl(const float* conf, const float* gt_xyxy, const f
                             float* ce, float* grad_loc, float* grad_conf,
                             uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
                             void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
-                            bool run_finalizer)
+                            bool run_finalizer, unsigned short* obj_u16 = nullptr)
 {
     if (B < 0 || P <= 0 || sumG < 0 || !conf || !gt_off || !pri_xyxy || !cls_u8 || !npos || !ws_loss || !ws_match) return SSDHEAD_E_BADARG;
     if (sumG > 0 && (!gt_xyxy || !gt_cls || !best_prior)) return SSDHEAD_E_BADARG;
@@ -1313,7 +1323,7 @@ static int ce_match_stream_impl(const float* conf, const float* gt_xyxy, const f
     unsigned int* image_counter = (unsigned int*)w;
     FusedMatch fm;
     fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
-    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc;
+    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc; fm.obj_u16 = obj_u16;
     float* ce_buf = ce ? ce : ws_ce(ws_loss, B);
     const long long rows = (long long)B * P;
     const int rc = grad_loc ? launch_ce_stream<21, true, true>(conf, ce_buf, grad_conf, grad_loc, rows, fm, st)
@@ -1492,7 +1502,7 @@ static int step_levels_common(const ssdhead_levels* levels,
     unsigned int* image_counter = (unsigned int*)w;
     FusedMatch fm;
     fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
-    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc;
+    fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc; fm.obj_u16 = use_obj_map(B, sumG) ? ws_obj(ws_loss, B, P) : nullptr;
 
     MineParams prm = {};
     prm.loc = nullptr; prm.conf = nullptr; prm.cls_u8 = cls_u8;
@@ -1507,6 +1517,7 @@ static int step_levels_common(const ssdhead_levels* levels,
     prm.ce_w = ws_ce(ws_loss, B);
     prm.ce = prm.ce_w;
     prm.ce_tap = nullptr;
+    prm.obj_u16 = fm.obj_u16;
     prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
     prm.best_key = best_key; prm.npos_acc = npos_acc;
     prm.arrive_total = (unsigned long long*)(image_counter + 2);
@@ -1585,6 +1596,7 @@ int ssdhead_mine(const float* loc, const float* conf,
     prm.partials = (double*)((char*)ws + 16);
     prm.ce = ce ? ce : ws_ce(ws, B);
     prm.ce_tap = ce;
+    prm.obj_u16 = nullptr;
     prm.cls_rw = nullptr; prm.best_prior_w = nullptr; prm.npos_w = nullptr; prm.best_key = nullptr; prm.npos_acc = nullptr;
     prm.arrive_total = nullptr;
     prm.xchg_R = 0; prm.xchg_rank = 0; prm.xchg_seq = 0; prm.xchg_peers = nullptr; prm.xchg_local = nullptr; prm.err_flag = nullptr;
@@ -1607,8 +1619,11 @@ static int multibox_step_impl(const float* loc, const float* conf,
 {
     if (!loc || !pri_cxcywh || !sums || !losses || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!aligned16(loc) || !aligned16(pri_cxcywh)) return SSDHEAD_E_ALIGN;
+    // (ws_loss is validated by the call below before anything is written through this pointer)
+    unsigned short* obj_map = (ws_loss && B > 0 && use_obj_map(B, sumG) && loss_workspace_bytes(B, P, C) && ws_loss_bytes >= loss_workspace_bytes(B, P, C))
+                                  ? ws_obj(ws_loss, B, P) : nullptr;
     int rc = ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce, grad_loc, grad_conf,
-                                  cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, false);
+                                  cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, false, obj_map);
     if (rc || B == 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* w = (char*)ws_match;
@@ -1629,6 +1644,7 @@ static int multibox_step_impl(const float* loc, const float* conf,
     prm.partials = (double*)((char*)ws_loss + 16);
     prm.ce = ce ? ce : ws_ce(ws_loss, B);
     prm.ce_tap = ce;
+    prm.obj_u16 = obj_map;
     prm.cls_rw = cls_u8; prm.best_prior_w = best_prior; prm.npos_w = npos;
     prm.best_key = best_key; prm.npos_acc = npos_acc;
     prm.arrive_total = (unsigned long long*)(image_counter + 2);   // 8-byte aligned word of the 16-byte tail

@@ -9,9 +9,10 @@ from objectdetection_ssd_b200 import synth, priors as PR, _lib
 from objectdetection_ssd_b200.ctx import SSDHeadContext
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-pri = PR.make_priors(); P = pri.shape[0]
-ctx = SSDHeadContext(pri.numpy(), max_batch=B)
-gb, gc = synth.make_gt(1, B); gx, gcl, off = synth.pack_gt(gb, gc)
+G = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # > 0: the stress configuration (SSD512-style priors, G gts per image)
+pri = PR.make_priors(PR.SSD512_SPEC) if G else PR.make_priors(); P = pri.shape[0]
+ctx = SSDHeadContext(pri.numpy(), max_batch=B, max_total_gt=B * max(G, 10))
+gb, gc = synth.make_gt(1, B, G, G) if G else synth.make_gt(1, B); gx, gcl, off = synth.pack_gt(gb, gc)
 loc, conf = synth.make_head(1, B, P)
 d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 tgx, tgc, toff = d(gx), d(gcl), d(off)
