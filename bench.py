@@ -357,7 +357,9 @@ def time_train(args, rank, world, dev, sampler):
         ctx.loss_host(hl, hc, gx, gcl, off, hgl, hgc)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
-    h2d = loc.nbytes + conf.nbytes + gx.nbytes + gcl.nbytes + off.nbytes
+    # conf and gt are copied; loc is read in place from the page-locked host buffer, positive rows only (counted as 128
+    # rows of 32-byte sectors per image, an upper bound at 1-10 gts per image)
+    h2d = conf.nbytes + gx.nbytes + gcl.nbytes + off.nbytes + B * 128 * 32
     d2h = loc.nbytes + conf.nbytes + 8
     ctx.close()
     return dict(ms_total=ms, launches=launches, kern_ms=kern_ms, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, losses=loss_val,
@@ -427,7 +429,9 @@ def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
         ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
     ctx.close()
-    return dict(ms_total=ms, launches=launches, kern_ms=None, e2e_ms=e2e_ms, h2d=loc.nbytes + conf.nbytes,
+    # conf is copied; of loc only the rows of the candidates the sweep visits cross PCIe (the kernel reads the page-locked
+    # host buffer in place): counted as 512 rows of 32-byte sectors per image, an upper bound at this workload
+    return dict(ms_total=ms, launches=launches, kern_ms=None, e2e_ms=e2e_ms, h2d=conf.nbytes + B * 512 * 32,
                 d2h=ob.nbytes + op.nbytes + oc.nbytes + oi.nbytes + on.nbytes, B=B, steps=steps,
                 kernel="detect_score_kernel + detect_nms_kernel (whole step)", algo=ALGO_BYTES["detect"], e2e_steps=en,
                 detections=int(out["cnt"].clamp(min=0).sum()))

@@ -64,6 +64,19 @@ struct ssdhead_ctx {
     float* h_losses;
 };
 
+// Device-visible alias of a page-locked host buffer (UVA maps cudaHostAlloc / cudaHostRegister memory), or null for
+// pageable / unaligned memory.  Kernels that touch only a few rows of a tensor read it in place instead of copying it.
+static const float* mapped_host_alias(const float* host)
+{
+    cudaPointerAttributes attr;
+    float* mapped = nullptr;
+    if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        cudaHostGetDevicePointer((void**)&mapped, (void*)host, 0) == cudaSuccess && mapped && aligned16(mapped))
+        return mapped;
+    (void)cudaGetLastError();
+    return nullptr;
+}
+
 // The loss workspace keeps its counters and per-image partial sums zeroed between steps, but their extent depends on
 // the batch size (include/ssdhead.h: "re-zero a buffer before reusing it with another shape"): re-zero the headers of
 // all chunk workspaces when B changes.
@@ -361,6 +374,7 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     if (rc) return rc;
     SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
 
+    const float* loc_alias = mapped_host_alias(loc_h);
     // >= 8 images per chunk, at most 8 chunks (measured on B200/PCIe5: 1 chunk 8.2 ms, 4: 5.8, 8: 5.6, 16: 6.3 at B=256)
     const int nchunks = std::min(8, std::max(1, B / 8));
     const int per = (B + nchunks - 1) / nchunks;
@@ -369,7 +383,8 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
         const int nb = std::min(per, B - b0);
         const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
         SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf + r0 * C, conf_h + r0 * C, nr * C * 4, cudaMemcpyHostToDevice, c->s_h2d));
-        SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc + r0 * 4, loc_h + r0 * 4, nr * 16, cudaMemcpyHostToDevice, c->s_h2d));
+        // the mining kernel reads loc only for the positive rows (~50 per image): page-locked loc is read in place
+        if (!loc_alias) SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc + r0 * 4, loc_h + r0 * 4, nr * 16, cudaMemcpyHostToDevice, c->s_h2d));
         SSD_CHECK_CUDA(cudaEventRecord(c->ev_in[k], c->s_h2d));
         SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_in[k], 0));
         void* ws = (char*)c->ws_loss + (size_t)k * c->ws_loss_bytes;
@@ -378,7 +393,7 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
         rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, gl, gc, ws, c->ws_loss_bytes, c->s_main);
         if (rc) return rc;
         if (k == 0) SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
-        rc = ssdhead_mine(c->loc + r0 * 4, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
+        rc = ssdhead_mine((loc_alias ? loc_alias : c->loc) + r0 * 4, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
                           c->best_prior, c->npos + b0, c->npos + B, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
                           c->chunk_sums + 2 * k, c->losses, gl, gc, nullptr, nullptr, ws, c->ws_loss_bytes, c->s_main);
         if (rc) return rc;
@@ -416,8 +431,13 @@ int ssdhead_ctx_detect_host(ssdhead_ctx* c, const float* loc_h, const float* con
         c->last_detect_B = B;
     }
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf, conf_h, nr * c->C * 4, cudaMemcpyHostToDevice, c->s_main));
-    SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc, loc_h, nr * 16, cudaMemcpyHostToDevice, c->s_main));
-    const int rc = ssdhead_detect(c->loc, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k, nullptr, 0,
+    // The sweep decodes only the few hundred boxes per image it actually visits, so the offsets need not cross PCIe in
+    // full (16 % of the input bytes): page-locked host memory is mapped into the device's address space (UVA) and the
+    // kernel reads those rows in place.  Pageable or unaligned buffers are copied as before.
+    const float* loc_alias = mapped_host_alias(loc_h);
+    const float* loc_dev = loc_alias ? loc_alias : c->loc;
+    if (loc_dev == c->loc) SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc, loc_h, nr * 16, cudaMemcpyHostToDevice, c->s_main));
+    const int rc = ssdhead_detect(loc_dev, c->conf, c->pri_cxcywh, B, c->P, c->C, min_score, iou_thr, c->top_k, nullptr, 0,
                                   c->det_boxes, c->det_prob, c->det_cls, c->det_prior, c->det_cnt,
                                   c->ws_detect, c->ws_detect_bytes, c->s_main);
     if (rc) return rc;
