@@ -105,3 +105,35 @@ def test_detect_host_matches_device_path_and_survives_batch_changes():
             assert np.array_equal(op[b, :k], out["prob"][b, :k].cpu().numpy())
             assert np.array_equal(ob[b, :k], out["boxes"][b, :k].cpu().numpy())
     ctx.close()
+
+
+def test_host_paths_with_pageable_buffers_equal_pinned_ones():
+    """Page-locked `loc` is read in place by the kernels (UVA alias); ordinary numpy arrays take the copy path.  Both
+    must give the same losses, gradients and detections, bit for bit."""
+    import numpy as np
+    from objectdetection_ssd_b200.ctx import SSDHeadContext, pinned_empty, pinned_free
+    B = 5
+    pri, loc, conf, gb, gc, gx, gcl, off = _inputs(23, B)
+    ctx = SSDHeadContext(pri.numpy(), max_batch=B)
+    hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    hl[:] = loc
+    hc[:] = conf
+    g1l, g1c = np.empty_like(loc), np.empty_like(conf)
+    g2l, g2c = np.empty_like(loc), np.empty_like(conf)
+    a = ctx.loss_host(hl, hc, gx, gcl, off, g1l, g1c)                                   # pinned inputs
+    b = ctx.loss_host(np.ascontiguousarray(loc), np.ascontiguousarray(conf), gx, gcl, off, g2l, g2c)   # pageable inputs
+    assert a == b and np.array_equal(g1l, g2l) and np.array_equal(g1c, g2c)
+    outs = []
+    for l_, c_ in ((hl, hc), (np.ascontiguousarray(loc), np.ascontiguousarray(conf))):
+        ob, op = np.empty((B, 200, 4), np.float32), np.empty((B, 200), np.float32)
+        oc, oi, on = np.empty((B, 200), np.int32), np.empty((B, 200), np.int32), np.empty((B,), np.int32)
+        ctx.detect_host(l_, c_, ob, op, oc, oi, on, 0.05, 0.45)
+        outs.append((ob, op, oc, oi, on))
+    for i in range(B):
+        k = int(outs[0][4][i])
+        assert k == int(outs[1][4][i])
+        for x, y in zip(outs[0][:4], outs[1][:4]):
+            assert np.array_equal(x[i, :k], y[i, :k])
+    pinned_free(hl)
+    pinned_free(hc)
+    ctx.close()
