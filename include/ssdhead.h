@@ -354,7 +354,9 @@ int ssdhead_ctx_xchg_error(ssdhead_ctx* ctx);
 /* ssd() with host buffers: losses_host[2] = (loc_loss, conf_loss); grads nullable as a pair.
  * Copies, kernels and copies back are pipelined in image chunks on the context's streams; pass
  * page-locked buffers (ssdhead_host_alloc) so the copies are asynchronous - a page-locked `loc` is not copied at
- * all, the kernels read the few rows they need in place.  Blocks until done. */
+ * all (the kernels read the few rows they need in place), and page-locked gradient buffers are zeroed by host threads
+ * and receive only their non-zero rows from the GPU (environment SSDHEAD_E2E_SPARSE=0 restores the dense copy back).
+ * Blocks until done. */
 int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host,
                                    const float* gt_xyxy_host, const float* gt_cls_host, const int32_t* gt_off_host,
                                    int B, int neg_ratio, float pos_iou,

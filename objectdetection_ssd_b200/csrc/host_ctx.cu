@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -379,38 +381,81 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     const int nchunks = std::min(8, std::max(1, B / 8));
     const int per = (B + nchunks - 1) / nchunks;
     int used = 0;
+
+    // The gradient is sparse (about 4 Npos of the B x P rows): when the caller's gradient buffers are page-locked, the
+    // dense zero background never crosses PCIe.  Host threads zero the buffers chunk by chunk while the inputs stream
+    // in, the streaming kernel runs without its zero-fill, and the mining kernel stores its few hundred rows per image
+    // straight into the host buffers through their UVA aliases.  Same bits in the caller's buffers, ~220 MB less D2H.
+    static const int sparse_ok = getenv("SSDHEAD_E2E_SPARSE") ? atoi(getenv("SSDHEAD_E2E_SPARSE")) : 1;
+    float* gl_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_loc_h)) : nullptr;
+    float* gc_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_conf_h)) : nullptr;
+    const bool sparse = gl_alias && gc_alias;
+    std::vector<std::thread> zero_threads;
+    std::atomic<int> zero_done[8];
+    for (auto& z : zero_done) z.store(0);
+    int T = 0;
+    if (sparse) {
+        T = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        for (int ti = 0; ti < T; ++ti) {
+            zero_threads.emplace_back([=, &zero_done]() {
+                for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+                    const int nb = std::min(per, B - b0);
+                    const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
+                    auto zero_part = [&](float* base, size_t floats) {
+                        const size_t part = (floats / T + 15) & ~(size_t)15;
+                        const size_t lo = std::min(floats, part * ti), hi = std::min(floats, lo + part);
+                        if (hi > lo) std::memset(base + lo, 0, (hi - lo) * sizeof(float));
+                    };
+                    zero_part(grad_conf_h + r0 * C, nr * C);
+                    zero_part(grad_loc_h + r0 * 4, nr * 4);
+                    zero_done[k].fetch_add(1, std::memory_order_release);
+                }
+            });
+        }
+    }
+    auto join_all = [&]() { for (auto& th : zero_threads) if (th.joinable()) th.join(); };
+#define CTX_HOST_CHECK(expr) do { const int _rc = (expr); if (_rc) { join_all(); return _rc; } } while (0)
+
+    // all input copies first (they depend on nothing), then the kernels chunk by chunk
     for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
         const int nb = std::min(per, B - b0);
         const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
-        SSD_CHECK_CUDA(cudaMemcpyAsync(c->conf + r0 * C, conf_h + r0 * C, nr * C * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        CTX_HOST_CHECK((int)cudaMemcpyAsync(c->conf + r0 * C, conf_h + r0 * C, nr * C * 4, cudaMemcpyHostToDevice, c->s_h2d));
         // the mining kernel reads loc only for the positive rows (~50 per image): page-locked loc is read in place
-        if (!loc_alias) SSD_CHECK_CUDA(cudaMemcpyAsync(c->loc + r0 * 4, loc_h + r0 * 4, nr * 16, cudaMemcpyHostToDevice, c->s_h2d));
-        SSD_CHECK_CUDA(cudaEventRecord(c->ev_in[k], c->s_h2d));
-        SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_in[k], 0));
+        if (!loc_alias) CTX_HOST_CHECK((int)cudaMemcpyAsync(c->loc + r0 * 4, loc_h + r0 * 4, nr * 16, cudaMemcpyHostToDevice, c->s_h2d));
+        CTX_HOST_CHECK((int)cudaEventRecord(c->ev_in[k], c->s_h2d));
+    }
+    for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+        const int nb = std::min(per, B - b0);
+        const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
+        CTX_HOST_CHECK((int)cudaStreamWaitEvent(c->s_main, c->ev_in[k], 0));
         void* ws = (char*)c->ws_loss + (size_t)k * c->ws_loss_bytes;
-        float* gl = grads ? c->grad_loc + r0 * 4 : nullptr;
-        float* gc = grads ? c->grad_conf + r0 * C : nullptr;
-        rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, gl, gc, ws, c->ws_loss_bytes, c->s_main);
-        if (rc) return rc;
-        if (k == 0) SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
+        float* gl = grads ? (sparse ? gl_alias + r0 * 4 : c->grad_loc + r0 * 4) : nullptr;
+        float* gc = grads ? (sparse ? gc_alias + r0 * C : c->grad_conf + r0 * C) : nullptr;
+        rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, sparse ? nullptr : gl, sparse ? nullptr : gc, ws, c->ws_loss_bytes, c->s_main);
+        CTX_HOST_CHECK(rc);
+        if (k == 0) CTX_HOST_CHECK((int)cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
+        if (sparse) while (zero_done[k].load(std::memory_order_acquire) < T) std::this_thread::yield();   // chunk k's slices are zero
         rc = ssdhead_mine((loc_alias ? loc_alias : c->loc) + r0 * 4, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
                           c->best_prior, c->npos + b0, c->npos + B, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
                           c->chunk_sums + 2 * k, c->losses, gl, gc, nullptr, nullptr, ws, c->ws_loss_bytes, c->s_main);
-        if (rc) return rc;
-        if (grads) {
-            SSD_CHECK_CUDA(cudaEventRecord(c->ev_out[k], c->s_main));
-            SSD_CHECK_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_out[k], 0));
-            SSD_CHECK_CUDA(cudaMemcpyAsync(grad_conf_h + r0 * C, gc, nr * C * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-            SSD_CHECK_CUDA(cudaMemcpyAsync(grad_loc_h + r0 * 4, gl, nr * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+        CTX_HOST_CHECK(rc);
+        if (grads && !sparse) {
+            CTX_HOST_CHECK((int)cudaEventRecord(c->ev_out[k], c->s_main));
+            CTX_HOST_CHECK((int)cudaStreamWaitEvent(c->s_d2h, c->ev_out[k], 0));
+            CTX_HOST_CHECK((int)cudaMemcpyAsync(grad_conf_h + r0 * C, gc, nr * C * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            CTX_HOST_CHECK((int)cudaMemcpyAsync(grad_loc_h + r0 * 4, gl, nr * 16, cudaMemcpyDeviceToHost, c->s_d2h));
         }
         used = k + 1;
     }
+    join_all();
+#undef CTX_HOST_CHECK
     sum_chunks_kernel<<<1, 1, 0, c->s_main>>>(c->chunk_sums, used, c->npos + B, c->sums, c->losses);
     count_launch();
     SSD_LAUNCH_CHECK();
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->h_losses, c->losses, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->s_main));
     SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_main));
-    if (grads) SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_d2h));
+    if (grads && !sparse) SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_d2h));
     losses_h[0] = c->h_losses[0];
     losses_h[1] = c->h_losses[1];
     return 0;
