@@ -6,6 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "common.cuh"
@@ -34,7 +37,52 @@ __global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nch
 }
 }  // namespace ssdhead
 
+// A few host threads that live as long as the context: they zero the caller's gradient buffers while the inputs of a
+// host-buffer loss call stream in (spawning threads per call would cost ~0.1 ms of every call).
+struct ZeroPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void(int)> job;          // job(thread index); valid while a generation is running
+    unsigned generation = 0;
+    std::atomic<int> finished{0};
+    bool stop = false;
+
+    int size() const { return (int)threads.size(); }
+    void start(int n) {
+        for (int ti = 0; ti < n; ++ti)
+            threads.emplace_back([this, ti]() {
+                unsigned seen = 0;
+                for (;;) {
+                    std::function<void(int)> j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        j = job;
+                    }
+                    j(ti);
+                    finished.fetch_add(1, std::memory_order_release);
+                }
+            });
+    }
+    void run(std::function<void(int)> j) {                 // returns at once; wait() blocks until every thread is done
+        finished.store(0, std::memory_order_relaxed);
+        { std::lock_guard<std::mutex> lk(m); job = std::move(j); ++generation; }
+        cv.notify_all();
+    }
+    void wait() { while (finished.load(std::memory_order_acquire) < size()) std::this_thread::yield(); }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : threads) if (t.joinable()) t.join();
+        threads.clear();
+    }
+};
+
 struct ssdhead_ctx {
+    ZeroPool pool;
     int device, maxB, P, C, max_sumG, top_k, last_detect_B, last_loss_B;
     // cross-GPU exchange (sharded batches)
     int xchg_R, xchg_rank;
@@ -140,6 +188,7 @@ void ssdhead_host_free(void* p) { if (p) cudaFreeHost(p); }
 void ssdhead_ctx_destroy(ssdhead_ctx* c)
 {
     if (!c) return;
+    c->pool.shutdown();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* bufs[] = {c->pri_cxcywh, c->pri_xyxy, c->gt_xyxy, c->gt_cls, c->gt_off, c->best_prior, c->npos, c->cls_u8,
@@ -390,30 +439,29 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     float* gl_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_loc_h)) : nullptr;
     float* gc_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_conf_h)) : nullptr;
     const bool sparse = gl_alias && gc_alias;
-    std::vector<std::thread> zero_threads;
     std::atomic<int> zero_done[8];
     for (auto& z : zero_done) z.store(0);
     int T = 0;
     if (sparse) {
-        T = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
-        for (int ti = 0; ti < T; ++ti) {
-            zero_threads.emplace_back([=, &zero_done]() {
-                for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
-                    const int nb = std::min(per, B - b0);
-                    const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
-                    auto zero_part = [&](float* base, size_t floats) {
-                        const size_t part = (floats / T + 15) & ~(size_t)15;
-                        const size_t lo = std::min(floats, part * ti), hi = std::min(floats, lo + part);
-                        if (hi > lo) std::memset(base + lo, 0, (hi - lo) * sizeof(float));
-                    };
-                    zero_part(grad_conf_h + r0 * C, nr * C);
-                    zero_part(grad_loc_h + r0 * 4, nr * 4);
-                    zero_done[k].fetch_add(1, std::memory_order_release);
-                }
-            });
-        }
+        if (c->pool.size() == 0)
+            c->pool.start((int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
+        T = c->pool.size();
+        c->pool.run([=, &zero_done](int ti) {
+            for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+                const int nb = std::min(per, B - b0);
+                const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
+                auto zero_part = [&](float* base, size_t floats) {
+                    const size_t part = ((floats + T - 1) / T + 15) & ~(size_t)15;     // T parts cover everything
+                    const size_t lo = std::min(floats, part * ti), hi = std::min(floats, lo + part);
+                    if (hi > lo) std::memset(base + lo, 0, (hi - lo) * sizeof(float));
+                };
+                zero_part(grad_conf_h + r0 * C, nr * C);
+                zero_part(grad_loc_h + r0 * 4, nr * 4);
+                zero_done[k].fetch_add(1, std::memory_order_release);
+            }
+        });
     }
-    auto join_all = [&]() { for (auto& th : zero_threads) if (th.joinable()) th.join(); };
+    auto join_all = [&]() { if (sparse) c->pool.wait(); };     // the job references this frame: never return before it is done
 #define CTX_HOST_CHECK(expr) do { const int _rc = (expr); if (_rc) { join_all(); return _rc; } } while (0)
 
     // all input copies first (they depend on nothing), then the kernels chunk by chunk

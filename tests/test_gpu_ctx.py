@@ -120,7 +120,15 @@ def test_host_paths_with_pageable_buffers_equal_pinned_ones():
     hc[:] = conf
     g1l, g1c = np.empty_like(loc), np.empty_like(conf)
     g2l, g2c = np.empty_like(loc), np.empty_like(conf)
+    # page-locked gradient buffers full of garbage: host threads must zero every element the GPU does not write
+    p1l, p1c = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    p1l[:] = 7.0
+    p1c[:] = -3.0
+    s = ctx.loss_host(hl, hc, gx, gcl, off, p1l, p1c)                                   # sparse return path
     a = ctx.loss_host(hl, hc, gx, gcl, off, g1l, g1c)                                   # pinned inputs
+    assert s == a and np.array_equal(p1l, g1l) and np.array_equal(p1c, g1c)
+    pinned_free(p1l)
+    pinned_free(p1c)
     b = ctx.loss_host(np.ascontiguousarray(loc), np.ascontiguousarray(conf), gx, gcl, off, g2l, g2c)   # pageable inputs
     assert a == b and np.array_equal(g1l, g2l) and np.array_equal(g1c, g2c)
     outs = []
