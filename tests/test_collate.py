@@ -68,3 +68,23 @@ def test_collate_feeds_the_packed_layout_of_synth():
     b = collate_gt(gb, gc, pinned=False)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_pack_gt_c_entry_error_codes():
+    """The C entry point directly: capacity check, bad arguments, empty batch."""
+    import ctypes as C
+    from objectdetection_ssd_b200 import _lib
+    lib = _lib.load()
+    b0 = np.array([[0.1, 0.1, 0.5, 0.5], [0.2, 0.2, 0.9, 0.9]], np.float32)
+    c0 = np.array([3, 7], np.float32)
+    boxes = (C.c_void_p * 1)(b0.ctypes.data)
+    classes = (C.c_void_p * 1)(c0.ctypes.data)
+    counts = np.array([2], np.int32)
+    ob, oc, oo = np.zeros((2, 4), np.float32), np.zeros(2, np.float32), np.zeros(2, np.int32)
+    call = lambda cap, bx=boxes, out_off=oo.ctypes.data: lib.ssdhead_pack_gt(
+        bx, classes, None, counts.ctypes.data, 1, 1, None, ob.ctypes.data, oc.ctypes.data, out_off, cap)
+    assert call(2) == 2 and np.array_equal(ob, b0) and np.array_equal(oo, [0, 2])
+    assert call(1) == _lib.E_WORKSPACE                      # room for one box only
+    assert call(2, out_off=None) == _lib.E_BADARG
+    assert call(2, bx=None) == _lib.E_BADARG
+    assert lib.ssdhead_pack_gt(None, None, None, None, 0, 1, None, None, None, oo.ctypes.data, 0) == 0   # empty batch
