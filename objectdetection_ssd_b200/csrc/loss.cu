@@ -31,6 +31,10 @@
 //                      last CTA -> run-to-run deterministic.
 //   match_finalize_kernel   the forced-match override as a separate small kernel (the NCCL route of a
 //                      sharded batch, or when the batch does not fit a co-resident grid).
+//   *_levels_kernel    the same two kernel bodies reading the head outputs per pyramid level in place (a level
+//                      table in the constant bank instead of the concatenated [B,P,*] tensors).
+//   For batches with many gts per image the streaming kernel also records the best gt of every prior (2 B/row) so the
+//   mining kernel does not walk the image's gts for every positive row.
 //
 // HBM traffic per image: conf in once (733 KB) + CE out/in (2 x 35 KB, L2-resident between the two
 // kernels) + dense gradients out once (873 KB) + ~4*npos sparse rows: the algorithmic minimum.
