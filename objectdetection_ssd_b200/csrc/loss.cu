@@ -666,62 +666,16 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     }
     pdl_trigger();
     pdl_wait();                                              // CE, class bytes, best priors, positive counts are ready
+    __syncthreads();                                         // s_max / s_nsel / gt staging above are visible
     LPHASE(0);
-    int npos_b;
+    // The forced-match inputs are requested first, then the keys are built from the NATURAL classes while those loads
+    // are in flight; the override below patches the few forced priors in shared memory (and in the global class map).
+    int acc0 = 0;
+    unsigned long long bk0 = 0ull;
     if (FIN) {
-        // ---- 0. forced-match override of THIS image (Losses.py:164-167), fused here so that no separate finaliser
-        // kernel sits between the streaming kernel and this one.  The batch-global positive count, which only the
-        // gradient scale needs, is exchanged through a counter the CTAs of this (cooperative) grid wait on later.
-        __shared__ int s_fin_extra, s_fin_npos;
-        const int acc0 = ld_cg_s32(&p.npos_acc[b]);
-        if (t == 0) s_fin_extra = 0;
-        for (int g = t; g < G; g += MN_T) {
-            const int bp = (int)(0xffffffffu - (uint32_t)(ld_cg_u64(&p.best_key[off0 + g]) & 0xffffffffull));
-            p.best_key[off0 + g] = 0ull;                     // leave the workspace zeroed
-            p.best_prior_w[off0 + g] = bp;
-            if (g < MN_GC) s_gbp[g] = bp;
-        }
-        __syncthreads();
-        int extra = 0;
-        for (int g = t; g < G; g += MN_T) {
-            const int bp = g < MN_GC ? s_gbp[g] : p.best_prior_w[off0 + g];
-            bool winner = true;                              // T3: the highest gt index keeps the prior
-            for (int g2 = g + 1; g2 < G; ++g2) winner = winner && ((g2 < MN_GC ? s_gbp[g2] : p.best_prior_w[off0 + g2]) != bp);
-            if (winner) {
-                const int c_new = (int)p.gt_cls[off0 + g];
-                const int c_nat = (int)p.cls_rw[row0 + bp];
-                extra += (c_new != p.bg_class ? 1 : 0) - (c_nat != p.bg_class ? 1 : 0);
-                p.cls_rw[row0 + bp] = (uint8_t)c_new;        // read back below by this same CTA (after the barrier)
-                if (p.obj_u16) p.obj_u16[row0 + bp] = (unsigned short)g;
-            }
-        }
-        if (extra) atomicAdd(&s_fin_extra, extra);
-        __syncthreads();
-        if (t == 0) {
-            const int nb = acc0 + s_fin_extra;
-            s_fin_npos = nb;
-            p.npos_w[b] = nb;
-            p.npos_acc[b] = 0;
-            // one 64-bit atomic carries both the arrival (high word) and the image's positives (low word): whoever sees
-            // gridDim.x arrivals sees the complete batch count in the same word - no fence between two atomics
-            const unsigned long long before = atomicAdd(p.arrive_total, (1ull << 32) | (unsigned long long)(unsigned)nb);
-            if (p.xchg_R > 1 && (unsigned)(before >> 32) == gridDim.x - 1u) {
-                // last image of this GPU: its positive count is complete -> one 64-bit store (seq << 32 | count) into
-                // the exchange buffer of every rank (own included) over NVLink
-                const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)((unsigned)before + (unsigned)nb);
-                for (int q = 0; q < p.xchg_R; ++q)          // the word validates itself (seq in the high half): relaxed, pipelined stores
-                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
-            }
-        }
-        __syncthreads();
-        npos_b = s_fin_npos;
-    } else {
-        if (t < min(G, MN_GC)) s_gbp[t] = p.best_prior[off0 + t];
-        __syncthreads();
-        npos_b = p.npos[b];
+        acc0 = ld_cg_s32(&p.npos_acc[b]);
+        if (t < G) bk0 = ld_cg_u64(&p.best_key[off0 + t]);
     }
-    const int* bprior = FIN ? p.best_prior_w : p.best_prior;
-    LPHASE(1);
     uint32_t kmax = 0u;
     const bool vec_ok = ((P & 3) == 0) && (((row0 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.ce) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.cls_u8) & 3) == 0);
@@ -759,9 +713,66 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     }
     kmax = __reduce_max_sync(FULL, kmax);
     if (lane == 0) atomicMax(&s_max, kmax);
+    LPHASE(1);
+    int npos_b;
+    if (FIN) {
+        // ---- 0. forced-match override of THIS image (Losses.py:164-167), fused here so that no separate finaliser
+        // kernel sits between the streaming kernel and this one.  The batch-global positive count, which only the
+        // gradient scale needs, is exchanged through a counter the CTAs of this (cooperative) grid wait on later.
+        __shared__ int s_fin_extra, s_fin_npos;
+        if (t == 0) s_fin_extra = 0;
+        for (int g = t; g < G; g += MN_T) {
+            const unsigned long long bkv = g == t ? bk0 : ld_cg_u64(&p.best_key[off0 + g]);
+            const int bp = (int)(0xffffffffu - (uint32_t)(bkv & 0xffffffffull));
+            p.best_key[off0 + g] = 0ull;                     // leave the workspace zeroed
+            p.best_prior_w[off0 + g] = bp;
+            if (g < MN_GC) s_gbp[g] = bp;
+        }
+        __syncthreads();
+        int extra = 0;
+        for (int g = t; g < G; g += MN_T) {
+            const int bp = g < MN_GC ? s_gbp[g] : p.best_prior_w[off0 + g];
+            bool winner = true;                              // T3: the highest gt index keeps the prior
+            for (int g2 = g + 1; g2 < G; ++g2) winner = winner && ((g2 < MN_GC ? s_gbp[g2] : p.best_prior_w[off0 + g2]) != bp);
+            if (winner) {
+                const int c_new = (int)p.gt_cls[off0 + g];
+                const int c_nat = (int)s_cls[bp];            // the natural class, staged a moment ago
+                extra += (c_new != p.bg_class ? 1 : 0) - (c_nat != p.bg_class ? 1 : 0);
+                p.cls_rw[row0 + bp] = (uint8_t)c_new;
+                s_cls[bp] = (uint8_t)c_new;                  // a prior has one winner: no two threads patch the same entry
+                s_key[bp] = c_new != p.bg_class ? 0u : (__float_as_uint(p.ce[row0 + bp]) & 0x7fffffffu);
+                if (p.obj_u16) p.obj_u16[row0 + bp] = (unsigned short)g;
+            }
+        }
+        if (extra) atomicAdd(&s_fin_extra, extra);
+        __syncthreads();
+        if (t == 0) {
+            const int nb = acc0 + s_fin_extra;
+            s_fin_npos = nb;
+            p.npos_w[b] = nb;
+            p.npos_acc[b] = 0;
+            // one 64-bit atomic carries both the arrival (high word) and the image's positives (low word): whoever sees
+            // gridDim.x arrivals sees the complete batch count in the same word - no fence between two atomics
+            const unsigned long long before = atomicAdd(p.arrive_total, (1ull << 32) | (unsigned long long)(unsigned)nb);
+            if (p.xchg_R > 1 && (unsigned)(before >> 32) == gridDim.x - 1u) {
+                // last image of this GPU: its positive count is complete -> one 64-bit store (seq << 32 | count) into
+                // the exchange buffer of every rank (own included) over NVLink
+                const unsigned long long word = ((unsigned long long)p.xchg_seq << 32) | (unsigned)((unsigned)before + (unsigned)nb);
+                for (int q = 0; q < p.xchg_R; ++q)          // the word validates itself (seq in the high half): relaxed, pipelined stores
+                    st_relaxed_sys_u64(p.xchg_peers[q] + xchg_slot(p.xchg_seq, 0, p.xchg_rank), word);
+            }
+        }
+        __syncthreads();
+        npos_b = s_fin_npos;
+    } else {
+        if (t < min(G, MN_GC)) s_gbp[t] = p.best_prior[off0 + t];
+        __syncthreads();
+        npos_b = p.npos[b];
+    }
+    const int* bprior = FIN ? p.best_prior_w : p.best_prior;
     __syncthreads();
-    kmax = s_max;
-    LPHASE(2);
+    kmax = s_max;                                            // (may be the key of a prior a forced match made positive:
+    LPHASE(2);                                               //  it only scales the histogram bins)
 
     // ---- 2. the k largest keys, ties to the lower prior index (T4): mark them with bit 31 ----
     const long long kk = (long long)p.neg_ratio * (long long)npos_b;

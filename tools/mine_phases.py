@@ -21,7 +21,7 @@ sums = torch.empty(2, dtype=torch.float64, device="cuda"); losses = torch.empty(
 gl = torch.empty_like(sets[0][0]); gcf = torch.empty_like(sets[0][1])
 st = torch.cuda.current_stream().cuda_stream
 lib = _lib.load()
-names = ["finalise", "keys", "select+list", "wait total", "grad rows", "publish"]
+names = ["keys (natural classes)", "finalise + patch", "select+list", "wait total", "grad rows", "publish"]
 for it in range(5):
     l, c = sets[it % 3]
     ctx.loss_dev(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
