@@ -88,3 +88,21 @@ def test_pack_gt_c_entry_error_codes():
     assert call(2, out_off=None) == _lib.E_BADARG
     assert call(2, bx=None) == _lib.E_BADARG
     assert lib.ssdhead_pack_gt(None, None, None, None, 0, 1, None, None, None, oo.ctypes.data, 0) == 0   # empty batch
+
+
+def test_collate_property_random_ragged_batches():
+    """Hypothesis: any ragged batch (1..20 images, 1..30 boxes, random difficult flags with at least one easy box) packs
+    exactly as the reference's ops do."""
+    from hypothesis import given, settings, strategies as st
+    from objectdetection_ssd_b200.collate import collate_gt
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 20), st.booleans(), st.booleans())
+    def check(seed, B, keep_difficult, pixels):
+        boxes, classes, diff, wh = _ragged(seed, B, lo=1, hi=30, pixels=pixels)
+        rb, rc, ro = O.collate_gt(boxes, classes, diff, keep_difficult, wh if pixels else None)
+        gb, gc, go = collate_gt(boxes, classes, diff, keep_difficult, wh if pixels else None, pinned=False)
+        assert np.array_equal(go, ro.numpy()) and np.array_equal(gc, rc.numpy())
+        assert np.array_equal(gb.view(np.uint32), rb.numpy().view(np.uint32))
+
+    check()

@@ -50,3 +50,28 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert lib.ssdhead_ce_stream(None, 4, 8732, 21, None, None, None, None, 0, None) == -1
     assert lib.ssdhead_iou_matrix(None, -1, None, 3, None, None) == -1
     assert lib.ssdhead_ctx_multibox_loss_dev(None, None, None, None, None, None, 1, 1, 3, 0.5, None, None, None, None, None) == -1
+
+
+def test_levels_struct_layout_matches_the_header(tmp_path):
+    """ctypes `Levels` must have the layout a C compiler gives `ssdhead_levels` (offsets and size), else the per-level
+    entry points would read garbage."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from objectdetection_ssd_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "ssdhead.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(ssdhead_levels), offsetof(ssdhead_levels, num_levels),\n'
+        '  offsetof(ssdhead_levels, count), offsetof(ssdhead_levels, conf), offsetof(ssdhead_levels, loc),\n'
+        '  offsetof(ssdhead_levels, grad_conf), offsetof(ssdhead_levels, grad_loc), SSDHEAD_MAX_LEVELS); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    L = _lib.Levels
+    want = [C.sizeof(L), L.num_levels.offset, L.count.offset, L.conf.offset, L.loc.offset, L.grad_conf.offset,
+            L.grad_loc.offset, _lib.MAX_LEVELS]
+    assert got == want, (got, want)
