@@ -82,3 +82,26 @@ def test_subsampling_matches_strided_indexing():
     from objectdetection_ssd_b200.Util import subsampling
     x = torch.arange(4 * 6 * 5).view(4, 6, 5)
     assert torch.equal(subsampling(x, [2, None, 3]), x[::2, :, ::3])
+
+
+def test_head_levels_are_views_of_the_reference_layout():
+    """Model.py:212-235 restated (permute(0,2,3,1).contiguous().view per conv map, cat over the six levels): the
+    per-level tensors `head_levels` hands to the kernels are exactly the pieces of that concatenation, in the same
+    prior order, and for channels_last conv outputs they are views (no copy)."""
+    from objectdetection_ssd_b200.Losses import head_levels
+    g = torch.Generator().manual_seed(3)
+    bs = 2
+    grids = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))
+    loc_maps = [torch.randn(bs, a * 4, hw, hw, generator=g) for hw, a in grids]
+    conf_maps = [torch.randn(bs, a * 21, hw, hw, generator=g) for hw, a in grids]
+    ref_loc = torch.cat([m.permute(0, 2, 3, 1).contiguous().view(bs, -1, 4) for m in loc_maps], dim=1)
+    ref_conf = torch.cat([m.permute(0, 2, 3, 1).contiguous().view(bs, -1, 21) for m in conf_maps], dim=1)
+    assert ref_loc.shape == (bs, 8732, 4) and ref_conf.shape == (bs, 8732, 21)
+    locs, confs = head_levels(loc_maps, conf_maps)
+    assert [int(t.shape[1]) for t in confs] == [5776, 2166, 600, 150, 36, 4]
+    assert torch.equal(torch.cat(locs, 1), ref_loc) and torch.equal(torch.cat(confs, 1), ref_conf)
+    cl = [m.contiguous(memory_format=torch.channels_last) for m in conf_maps]
+    _, confs_cl = head_levels(loc_maps, cl)
+    assert torch.equal(torch.cat(confs_cl, 1), ref_conf)
+    # 1x1 maps have ambiguous strides; every other NHWC conv output is consumed in place
+    assert all(v.data_ptr() == m.data_ptr() and v.is_contiguous() for v, m in zip(confs_cl[:5], cl[:5]))
