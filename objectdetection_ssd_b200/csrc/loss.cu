@@ -46,8 +46,15 @@ namespace ssdhead {
 #ifdef SSDHEAD_PHASE_TIMES      // developer build: SM clock at the phase boundaries of the first image's mining CTA
 __device__ long long g_phase_loss[16];
 #define LPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_loss[i] = clock64(); } while (0)
+__device__ long long g_cta[1024][4];     // per mining CTA: clocks from its wait to (a) the selection done, (b) gradient rows done, (c) end; [3] = nsel
+__device__ unsigned long long g_gt[8];    // global-timer marks: [0] last streaming CTA done, [1]/[2] first/last mining CTA past its wait, [3] last mining CTA done
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long v; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v)); return v; }
+#define GMARK_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_gt[i], gtimer()); } while (0)
+#define GMARK_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_gt[i], gtimer()); } while (0)
 #else
 #define LPHASE(i) do { } while (0)
+#define GMARK_MAX(i) do { } while (0)
+#define GMARK_MIN(i) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -518,6 +525,8 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
             }
         }
     }
+    __syncthreads();
+    GMARK_MAX(0);
 }
 
 template <int C, bool ZERO_FILL, bool MATCH>
@@ -668,6 +677,10 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     pdl_wait();                                              // CE, class bytes, best priors, positive counts are ready
     __syncthreads();                                         // s_max / s_nsel / gt staging above are visible
     LPHASE(0);
+    GMARK_MIN(1); GMARK_MAX(2);
+#ifdef SSDHEAD_PHASE_TIMES
+    const long long cta_t0 = clock64();
+#endif
     // The forced-match inputs are requested first, then the keys are built from the NATURAL classes while those loads
     // are in flight; the override below patches the few forced priors in shared memory (and in the global class map).
     int acc0 = 0;
@@ -919,6 +932,9 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     // ---- 4. the selected rows only: conf gradient, and for positives the L1 term + loc gradient ----
     LPHASE(3);
     const uint32_t nsel = s_nsel;
+#ifdef SSDHEAD_PHASE_TIMES
+    if (t == 0 && b < 1024) { g_cta[b][0] = clock64() - cta_t0; g_cta[b][3] = nsel; }
+#endif
     int npos_total;
     if (FIN) {
         // every CTA of the grid is co-resident (cooperative launch) and published its count long ago (step 0);
@@ -1074,6 +1090,9 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         }
     }
 
+#ifdef SSDHEAD_PHASE_TIMES
+    if (t == 0 && b < 1024) g_cta[b][1] = clock64() - cta_t0;
+#endif
     LPHASE(5);
     // ---- 5. loss sums: per-image partial -> the last CTA reduces all partials in a fixed order ----
     acc_l1 = warp_sum(acc_l1);
@@ -1144,6 +1163,10 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             }
         }
     }
+    GMARK_MAX(3);
+#ifdef SSDHEAD_PHASE_TIMES
+    if (t == 0 && b < 1024) g_cta[b][2] = clock64() - cta_t0;
+#endif
 }
 
 
@@ -1715,6 +1738,12 @@ int ssdhead_scale_grads(float* grad_loc, size_t n_loc, float* grad_conf, size_t 
 
 #ifdef SSDHEAD_PHASE_TIMES
 int ssdhead_debug_phases_loss(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, ssdhead::g_phase_loss, sizeof(long long) * 16); }
+int ssdhead_debug_cta(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, ssdhead::g_cta, sizeof(long long) * 4 * n); }
+int ssdhead_debug_gmarks(unsigned long long* out8, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(out8, ssdhead::g_gt, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0ull, ~0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}; rc |= (int)cudaMemcpyToSymbol(ssdhead::g_gt, z, sizeof(z)); }
+    return rc;
+}
 #endif
 
 }  // extern "C"
