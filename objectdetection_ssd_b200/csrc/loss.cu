@@ -693,25 +693,38 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     const bool vec_ok = ((P & 3) == 0) && (((row0 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.ce) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.cls_u8) & 3) == 0);
     if (vec_ok) {
-        // 16-byte CE loads + 4-byte class loads, several in flight per thread
         const float4* ce4 = reinterpret_cast<const float4*>(p.ce + row0);
         const uchar4* cl4 = reinterpret_cast<const uchar4*>(p.cls_u8 + row0);
         const int nvec = P >> 2;
-#pragma unroll 4
-        for (int v = t; v < nvec; v += MN_T) {
-            const float4 e = ce4[v];
-            const uchar4 c = cl4[v];
-            const float ev[4] = {e.x, e.y, e.z, e.w};
-            const uint8_t cv[4] = {c.x, c.y, c.z, c.w};
-            uint32_t kv[4];
+        // 16-byte CE loads + 4-byte class loads; KU of each are issued per thread before the first is used
+        // (SSD300: 2183 vectors / 512 threads -> the whole image in one round of loads)
+        constexpr int KU = 5;
+        for (int v0 = t; v0 < nvec; v0 += KU * MN_T) {
+            float4 e5[KU];
+            uchar4 c5[KU];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool pos = (int)cv[q] != p.bg_class;
-                kv[q] = pos ? 0u : (__float_as_uint(ev[q]) & 0x7fffffffu);
-                kmax = max(kmax, kv[q]);
+            for (int u = 0; u < KU; ++u) {
+                const int v = v0 + u * MN_T;
+                if (v < nvec) { e5[u] = ce4[v]; c5[u] = cl4[v]; }
             }
-            reinterpret_cast<uint4*>(s_key)[v] = make_uint4(kv[0], kv[1], kv[2], kv[3]);
-            reinterpret_cast<uchar4*>(s_cls)[v] = c;
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int v = v0 + u * MN_T;
+                if (v >= nvec) break;
+                const float4 e = e5[u];
+                const uchar4 c = c5[u];
+                const float ev[4] = {e.x, e.y, e.z, e.w};
+                const uint8_t cv[4] = {c.x, c.y, c.z, c.w};
+                uint32_t kv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool pos = (int)cv[q] != p.bg_class;
+                    kv[q] = pos ? 0u : (__float_as_uint(ev[q]) & 0x7fffffffu);
+                    kmax = max(kmax, kv[q]);
+                }
+                reinterpret_cast<uint4*>(s_key)[v] = make_uint4(kv[0], kv[1], kv[2], kv[3]);
+                reinterpret_cast<uchar4*>(s_cls)[v] = c;
+            }
         }
     } else {
         for (int j = t; j < P; j += MN_T) {
@@ -1018,7 +1031,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             pc = p.pri_cxcywh[j];
             l = *loc_row(j);
         }
-        if (pos) {
+        if (!GRADS && pos) {
             // the streaming kernel scored every row against the background class; a positive row gets its
             // true-class CE here, from the row it re-reads anyway (same code -> same bits as a direct evaluation)
             const float ce = row_cross_entropy<C>(x, c);
@@ -1029,9 +1042,21 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             float m = x[0];
 #pragma unroll
             for (int q = 1; q < C; ++q) m = fmaxf(m, x[q]);
-            float s = 0.0f;
+            float s = 0.0f, xc = 0.0f;
 #pragma unroll
-            for (int q = 0; q < C; ++q) { x[q] = expf(__fsub_rn(x[q], m)); s = __fadd_rn(s, x[q]); }
+            for (int q = 0; q < C; ++q) {
+                const float d = __fsub_rn(x[q], m);
+                if (q == c) xc = d;
+                x[q] = expf(d);
+                s = __fadd_rn(s, x[q]);
+            }
+            if (pos) {
+                // max, exponentials and their sum (same order) are exactly row_cross_entropy's: the true-class CE of a
+                // positive row falls out of the softmax its gradient needs anyway
+                const float ce = __fadd_rn(__fsub_rn(logf(s), xc), 0.0f);
+                acc_ce += (double)ce;
+                if (p.ce_tap) p.ce_tap[row0 + j] = ce;
+            }
             const float inv = __fdiv_rn(1.0f, s);
             if (staged) {
 #pragma unroll
