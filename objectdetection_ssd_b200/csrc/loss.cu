@@ -1327,9 +1327,16 @@ static int launch_mine_fin(MineParams prm, cudaStream_t st)
 
 static float* ws_ce(void* ws, int B) { return (float*)((char*)ws + 16 + round_up((size_t)B * 2 * sizeof(double), 16)); }
 static unsigned short* ws_obj(void* ws, int B, int P) { return (unsigned short*)((char*)ws_ce(ws, B) + round_up((size_t)B * P * sizeof(float), 16)); }
-// the walk over an image's gts in the mining kernel costs G x ~30 instructions per positive row: from this average G on
-// the streaming kernel records the best gt of every prior (2 bytes per row) and the walk disappears
-static bool use_obj_map(int B, int sumG) { return sumG >= 16 * B && sumG <= 65535; }
+// The walk over an image's gts in the mining kernel costs G x ~25 instructions per positive row, on the latency chain
+// of the step's last kernel; the streaming kernel can record the best gt of every prior instead (2 bytes per row, +1 %
+// of its traffic) and the walk disappears.  Measured at 1-10 gts per image: 112.4 -> 111.5 us per step at B=256 with the
+// map, 671 -> 565 us at 100 gts per image - so the map is used whenever a gt index fits its 16 bits
+// (SSDHEAD_OBJ_MAP_MIN=<average gts per image> restores a threshold for experiments).
+static bool use_obj_map(int B, int sumG)
+{
+    static const int min_avg = getenv("SSDHEAD_OBJ_MAP_MIN") ? atoi(getenv("SSDHEAD_OBJ_MAP_MIN")) : 0;
+    return sumG >= min_avg * B && sumG <= 65535;
+}
 
 }  // namespace ssdhead
 
