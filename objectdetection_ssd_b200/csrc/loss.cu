@@ -46,7 +46,8 @@ namespace ssdhead {
 #ifdef SSDHEAD_PHASE_TIMES      // developer build: SM clock at the phase boundaries of the first image's mining CTA
 __device__ long long g_phase_loss[16];
 #define LPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_loss[i] = clock64(); } while (0)
-__device__ long long g_cta[1024][4];     // per mining CTA: clocks from its wait to (a) the selection done, (b) gradient rows done, (c) end; [3] = nsel
+__device__ long long g_cta[1024][12];    // per mining CTA: clocks from its wait to [0] selection done, [1] gradient rows done, [2] end; [3] = nsel;
+                                          // [4] batch total known; row-loop trips 0/1: [5],[6] warp 0 done, [7],[8] last warp done, [9],[10] warp 0's conf part done
 __device__ unsigned long long g_gt[8];    // global-timer marks: [0] last streaming CTA done, [1]/[2] first/last mining CTA past its wait, [3] last mining CTA done
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long v; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v)); return v; }
 #define GMARK_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_gt[i], gtimer()); } while (0)
@@ -978,6 +979,9 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         npos_total = *p.npos_norm;
     }
     LPHASE(4);
+#ifdef SSDHEAD_PHASE_TIMES
+    if (t == 0 && b < 1024) { g_cta[b][4] = clock64() - cta_t0; for (int q = 5; q < 11; ++q) g_cta[b][q] = 0; }
+#endif
     const float nrm = (float)npos_total;
     const float gs_conf = __fdiv_rn(1.0f, nrm);
     const float gs_loc = __fdiv_rn(1.0f, __fmul_rn(4.0f, nrm));
@@ -1084,6 +1088,9 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             }
             __syncwarp();
         }
+#ifdef SSDHEAD_PHASE_TIMES
+        if (lane == 0 && warp == 0 && b < 1024 && base < 2 * MN_T) g_cta[b][9 + base / MN_T] = clock64() - cta_t0;
+#endif
         if (pos) {
             // which gt: the forced one (T3: highest index wins) or the natural argmax (T1)
             const float pa = box_area(pb);
@@ -1113,6 +1120,11 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 *gloc_row(j) = gl;
             }
         }
+#ifdef SSDHEAD_PHASE_TIMES
+        __syncwarp();
+        if (lane == 0 && (warp == 0 || warp == MN_W - 1) && b < 1024 && base < 2 * MN_T)
+            g_cta[b][5 + (warp ? 2 : 0) + base / MN_T] = clock64() - cta_t0;
+#endif
     }
 
 #ifdef SSDHEAD_PHASE_TIMES
@@ -1770,7 +1782,7 @@ int ssdhead_scale_grads(float* grad_loc, size_t n_loc, float* grad_conf, size_t 
 
 #ifdef SSDHEAD_PHASE_TIMES
 int ssdhead_debug_phases_loss(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, ssdhead::g_phase_loss, sizeof(long long) * 16); }
-int ssdhead_debug_cta(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, ssdhead::g_cta, sizeof(long long) * 4 * n); }
+int ssdhead_debug_cta(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, ssdhead::g_cta, sizeof(long long) * 12 * n); }
 int ssdhead_debug_gmarks(unsigned long long* out8, int reset) {
     int rc = (int)cudaMemcpyFromSymbol(out8, ssdhead::g_gt, sizeof(unsigned long long) * 8);
     if (reset) { unsigned long long z[8] = {0ull, ~0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}; rc |= (int)cudaMemcpyToSymbol(ssdhead::g_gt, z, sizeof(z)); }

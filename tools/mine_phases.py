@@ -38,13 +38,15 @@ for it in range(5):
     print("   global timer: stream end -> first mining CTA past wait %.2f us, -> last CTA past wait %.2f us, mining (first start -> last end) %.2f us" % ((g[1] - g[0]) / 1e3, (g[2] - g[0]) / 1e3, (g[3] - g[1]) / 1e3))
     print(it, " ".join(f"{names[i]}={(ph[i + 1] - ph[i]) / 1965.0:.2f}us" for i in range(6)), f"total={(ph[6] - ph[0]) / 1965.0:.2f}us")
 import numpy as _np
-buf = (_ct.c_longlong * (4 * B))()
+buf = (_ct.c_longlong * (12 * B))()
 lib.ssdhead_debug_cta(buf, B)
-a = _np.array(list(buf), dtype=_np.float64).reshape(B, 4)
+a = _np.array(list(buf), dtype=_np.float64).reshape(B, 12)
 us = a[:, :3] / 1965.0
 order = _np.argsort(us[:, 2])
 print("per-CTA time from its wait to its end (us): min %.1f  median %.1f  p90 %.1f  max %.1f" % (us[:, 2].min(), _np.median(us[:, 2]), _np.percentile(us[:, 2], 90), us[:, 2].max()))
 print("  slowest CTAs: " + ", ".join("b=%d nsel=%d sel=%.1f rows=%.1f end=%.1f" % (i, a[i, 3], us[i, 0], us[i, 1], us[i, 2]) for i in order[-5:]))
+print("  slowest CTAs, us from the CTA's start: " + "; ".join("b=%d nsel=%d total-known=%.1f trip0[w0 conf %.1f, w0 end %.1f, w15 end %.1f] trip1[w0 conf %.1f, w0 end %.1f, w15 end %.1f] rows=%.1f" % (
+    i, a[i, 3], a[i, 4] / 1965, a[i, 9] / 1965, a[i, 5] / 1965, a[i, 7] / 1965, a[i, 10] / 1965, a[i, 6] / 1965, a[i, 8] / 1965, us[i, 1]) for i in order[-6:]))
 print("  fastest CTAs: " + ", ".join("b=%d nsel=%d sel=%.1f rows=%.1f end=%.1f" % (i, a[i, 3], us[i, 0], us[i, 1], us[i, 2]) for i in order[:3]))
 print("  corr(nsel, end) = %.2f; mean end for b < 108 (2 CTAs/SM partner of b+148): %.1f, 108 <= b < 148 (alone): %.1f, b >= 148: %.1f" % (
     _np.corrcoef(a[:, 3], us[:, 2])[0, 1], us[:108, 2].mean(), us[108:148, 2].mean() if B > 148 else float("nan"), us[148:, 2].mean() if B > 148 else float("nan")))
