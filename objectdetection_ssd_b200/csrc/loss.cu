@@ -633,6 +633,9 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     __shared__ uint32_t s_warp[MN_W + 1];
     __shared__ uint32_t s_sel[3];
     __shared__ uint32_t s_nsel, s_ncand, s_max;
+    // positives are listed from the END of s_list downwards, mined rows from its start upwards (together at most P
+    // entries): the box part of the positive rows runs as its own pass (step 4a)
+    __shared__ uint32_t s_npl;
     __shared__ uint32_t s_ckey[MN_CAND], s_cidx[MN_CAND];
     __shared__ float4 s_gbox[MN_GC];
     __shared__ float s_garea[MN_GC];
@@ -668,7 +671,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     };
 
     // ---- 1. keys: CE bits for negatives, 0 for positives (Losses.py:188-190); class bytes; gts ----
-    if (t == 0) { s_nsel = 0u; s_ncand = 0u; s_max = 0u; }
+    if (t == 0) { s_nsel = 0u; s_ncand = 0u; s_max = 0u; s_npl = 0u; }
     if (t < min(G, MN_GC)) {
         const float4 bx = p.gt_xyxy[off0 + t];               // inputs of the step: may be read before the wait
         s_gbox[t] = bx;
@@ -844,7 +847,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                     const bool pos = (int)s_cls[j] != p.bg_class;
                     const int bin = (int)__fmul_rn(__uint_as_float(key), scale);
                     if (pos) {
-                        s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
+                        s_list[P - 1 - (int)atomicAdd(&s_npl, 1u)] = (uint16_t)j;
                     } else if (bin > bq) {
                         acc_ce += (double)__uint_as_float(key);
                         if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
@@ -938,14 +941,16 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 acc_ce += (double)__uint_as_float(key & 0x7fffffffu);
                 if (p.mined_mask) atomicOr(&p.mined_mask[(size_t)b * ((P + 31) / 32) + (j >> 5)], 1u << (j & 31));
             }
-            if (pos || (GRADS && mined)) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
+            if (pos) s_list[P - 1 - (int)atomicAdd(&s_npl, 1u)] = (uint16_t)j;
+            else if (GRADS && mined) s_list[atomicAdd(&s_nsel, 1u)] = (uint16_t)j;
         }
     }
     __syncthreads();
 
     // ---- 4. the selected rows only: conf gradient, and for positives the L1 term + loc gradient ----
     LPHASE(3);
-    const uint32_t nsel = s_nsel;
+    const uint32_t npl = s_npl;                  // positives, listed from the end
+    const uint32_t nsel = s_nsel + npl;
 #ifdef SSDHEAD_PHASE_TIMES
     if (t == 0 && b < 1024) { g_cta[b][0] = clock64() - cta_t0; g_cta[b][3] = nsel; }
 #endif
@@ -990,6 +995,46 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     // flat, coalesced loads of the 32 x 21 logits, thread-per-row arithmetic in place, flat coalesced stores - about
     // seven times fewer L2 transactions on the latency chain every CTA of the step waits for.  The staging area is the
     // key + histogram region, dead since the selection.
+    // ---- 4a. the box part of the positive rows (target encoding, L1 term, loc gradient): its own pass, one thread per
+    // positive, handed out from the LAST thread downwards.  The conf trip below is a serial chain of about a thousand
+    // instructions per warp and its rows are packed into the first warps, so in most images the last warps are free to
+    // do this meanwhile, and neither loop carries the other's registers (measured: 112.0 -> 105.6 us per step at B=256,
+    // 36.9 -> 34.3 at B=32, no spills left in the gradient kernel; same bits).
+    auto box_pass = [&]() {      // (kept as a lambda: this is the form whose code generation was measured and tested)
+        for (uint32_t i = (uint32_t)(MN_T - 1 - t); i < npl; i += MN_T) {
+            const int j = (int)s_list[P - 1 - (int)i];
+            const float4 pb = p.pri_xyxy[j];
+            const float4 pc = p.pri_cxcywh[j];
+            const float4 l = *loc_row(j);
+            const float pa = box_area(pb);
+            int obj = -1, ng = 0;
+            float nb = 0.0f;
+            if (FIN && p.obj_u16) obj = (int)p.obj_u16[row0 + j];   // recorded by the match: no walk over the image's gts
+            else for (int g = 0; g < G; ++g) {
+                float4 gb; float ga; int bp;
+                if (g < MN_GC) { gb = s_gbox[g]; ga = s_garea[g]; bp = s_gbp[g]; }
+                else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = bprior[off0 + g]; }
+                if (bp == j) obj = g;
+                const float v = iou_sparse(gb, ga, pb, pa);
+                if (v > nb) { nb = v; ng = g; }
+            }
+            if (obj < 0) obj = ng;
+            const float4 gbox = obj < MN_GC ? s_gbox[obj] : p.gt_xyxy[off0 + obj];
+            const float4 tgt = encode_box(xyxy_to_cxcywh(gbox), pc);
+            const float dx = __fsub_rn(l.x, tgt.x), dy = __fsub_rn(l.y, tgt.y);
+            const float dz = __fsub_rn(l.z, tgt.z), dw = __fsub_rn(l.w, tgt.w);
+            acc_l1 += (double)fabsf(dx) + (double)fabsf(dy) + (double)fabsf(dz) + (double)fabsf(dw);
+            if (GRADS) {
+                float4 gl;
+                gl.x = dx > 0.f ? gs_loc : (dx < 0.f ? -gs_loc : 0.f);
+                gl.y = dy > 0.f ? gs_loc : (dy < 0.f ? -gs_loc : 0.f);
+                gl.z = dz > 0.f ? gs_loc : (dz < 0.f ? -gs_loc : 0.f);
+                gl.w = dw > 0.f ? gs_loc : (dw < 0.f ? -gs_loc : 0.f);
+                *gloc_row(j) = gl;
+            }
+        }
+    };
+    box_pass();
     const bool staged = GRADS && (size_t)P * 4 + (size_t)MN_BINS * 4 >= (size_t)MN_W * 32 * C * 4;
     float* wstage = reinterpret_cast<float*>(smem_raw) + warp * (32 * C);
     for (uint32_t base = 0; base < nsel; base += MN_T) {
@@ -997,7 +1042,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         const bool valid = idx < nsel;
         const uint32_t wbase = base + (uint32_t)warp * 32u;
         const int nrw = wbase < nsel ? (int)min(32u, nsel - wbase) : 0;
-        const int j = valid ? (int)s_list[idx] : 0;
+        const int j = valid ? (int)(idx < npl ? s_list[P - 1 - (int)idx] : s_list[idx - npl]) : 0;   // positives first
         const float* my_crow = LEVELS ? conf_row(j) : nullptr;      // per-level tensors: locate the row once, pass pointers
         float* my_grow = (LEVELS && GRADS) ? gconf_row(j) : nullptr;
         if (staged) {
@@ -1019,7 +1064,6 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         const int c = valid ? (int)s_cls[j] : p.bg_class;
         const bool pos = c != p.bg_class;
         float x[C];
-        float4 pb, pc, l;
         if (valid && (GRADS || pos)) {
             if (staged) {
 #pragma unroll
@@ -1029,11 +1073,6 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #pragma unroll
                 for (int q = 0; q < C; ++q) x[q] = __ldg(row + q);
             }
-        }
-        if (pos) {                                   // issue every independent load before the first use
-            pb = p.pri_xyxy[j];
-            pc = p.pri_cxcywh[j];
-            l = *loc_row(j);
         }
         if (!GRADS && pos) {
             // the streaming kernel scored every row against the background class; a positive row gets its
@@ -1091,35 +1130,6 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #ifdef SSDHEAD_PHASE_TIMES
         if (lane == 0 && warp == 0 && b < 1024 && base < 2 * MN_T) g_cta[b][9 + base / MN_T] = clock64() - cta_t0;
 #endif
-        if (pos) {
-            // which gt: the forced one (T3: highest index wins) or the natural argmax (T1)
-            const float pa = box_area(pb);
-            int obj = -1, ng = 0;
-            float nb = 0.0f;
-            if (FIN && p.obj_u16) obj = (int)p.obj_u16[row0 + j];   // recorded by the match: no walk over the image's gts
-            else for (int g = 0; g < G; ++g) {
-                float4 gb; float ga; int bp;
-                if (g < MN_GC) { gb = s_gbox[g]; ga = s_garea[g]; bp = s_gbp[g]; }
-                else { gb = p.gt_xyxy[off0 + g]; ga = box_area(gb); bp = bprior[off0 + g]; }
-                if (bp == j) obj = g;
-                const float v = iou_sparse(gb, ga, pb, pa);
-                if (v > nb) { nb = v; ng = g; }
-            }
-            if (obj < 0) obj = ng;
-            const float4 gbox = obj < MN_GC ? s_gbox[obj] : p.gt_xyxy[off0 + obj];
-            const float4 tgt = encode_box(xyxy_to_cxcywh(gbox), pc);
-            const float dx = __fsub_rn(l.x, tgt.x), dy = __fsub_rn(l.y, tgt.y);
-            const float dz = __fsub_rn(l.z, tgt.z), dw = __fsub_rn(l.w, tgt.w);
-            acc_l1 += (double)fabsf(dx) + (double)fabsf(dy) + (double)fabsf(dz) + (double)fabsf(dw);
-            if (GRADS) {
-                float4 gl;
-                gl.x = dx > 0.f ? gs_loc : (dx < 0.f ? -gs_loc : 0.f);
-                gl.y = dy > 0.f ? gs_loc : (dy < 0.f ? -gs_loc : 0.f);
-                gl.z = dz > 0.f ? gs_loc : (dz < 0.f ? -gs_loc : 0.f);
-                gl.w = dw > 0.f ? gs_loc : (dw < 0.f ? -gs_loc : 0.f);
-                *gloc_row(j) = gl;
-            }
-        }
 #ifdef SSDHEAD_PHASE_TIMES
         __syncwarp();
         if (lane == 0 && (warp == 0 || warp == MN_W - 1) && b < 1024 && base < 2 * MN_T)
