@@ -81,21 +81,66 @@ def _box_op(name, a, b=None):
     return out
 
 
+class _BoxOpFn(torch.autograd.Function):
+    """The reference's box functions are plain torch expressions and therefore differentiable; the kernels are not
+    seen by autograd, so when an input requires grad the (elementwise, closed-form) backward is supplied here.  It is
+    off the hot path: the loss kernels produce their own gradients."""
+
+    @staticmethod
+    def forward(ctx, name, a, b):
+        out = _box_op(name, a, b)
+        ctx.name = name
+        ctx.save_for_backward(a.detach(), b.detach() if b is not None else None, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, out = ctx.saved_tensors
+        dev = out.device
+        g = g.to(dev)
+        ga = gb = None
+        if ctx.name == "ssdhead_cxcywh_to_xyxy":            # [c - wh/2, c + wh/2]
+            ga = torch.cat([g[:, :2] + g[:, 2:], (g[:, 2:] - g[:, :2]) / 2], 1)
+        elif ctx.name == "ssdhead_decode":                    # [g_c * p_wh / 10 + p_c, exp(g_wh / 5) * p_wh]
+            pb = b.to(dev).reshape(-1, 4)
+            ga = torch.cat([g[:, :2] * pb[:, 2:] / 10, g[:, 2:] * out[:, 2:] / 5], 1)
+            if ctx.needs_input_grad[2]:
+                aa = a.to(dev).reshape(-1, 4)
+                gb = torch.cat([g[:, :2], g[:, :2] * aa[:, :2] / 10 + g[:, 2:] * out[:, 2:] / pb[:, 2:]], 1)
+        elif ctx.name == "ssdhead_encode":                    # [(c - p_c) / (p_wh / 10), log(wh / p_wh) * 5]
+            aa, pb = a.to(dev).reshape(-1, 4), b.to(dev).reshape(-1, 4)
+            ga = torch.cat([g[:, :2] * 10 / pb[:, 2:], g[:, 2:] * 5 / aa[:, 2:]], 1)
+            if ctx.needs_input_grad[2]:
+                gb = torch.cat([-g[:, :2] * 10 / pb[:, 2:], -g[:, :2] * out[:, :2] / pb[:, 2:] - g[:, 2:] * 5 / pb[:, 2:]], 1)
+        if ga is not None:
+            ga = ga.reshape(a.shape).to(a.device)
+        if gb is not None:
+            gb = gb.reshape(b.shape).to(b.device)
+        return None, ga, gb
+
+
+def _box_fn(name, a, b=None):
+    ts = [t for t in (a, b) if isinstance(t, torch.Tensor)]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return _BoxOpFn.apply(name, torch.as_tensor(a), None if b is None else torch.as_tensor(b))
+    return _box_op(name, a, b)
+
+
 def xywh_to_xyxy(box):
-    return _box_op("ssdhead_cxcywh_to_xyxy", box)
+    return _box_fn("ssdhead_cxcywh_to_xyxy", box)
 
 
 def xyxy_to_xywh(anchors):
-    # the reference goes through numpy and hands back a CPU tensor (Util.py:58-63)
+    # the reference goes through numpy and hands back a CPU tensor (Util.py:58-63): not differentiable there either
     return _box_op("ssdhead_xyxy_to_cxcywh", anchors).cpu()
 
 
 def gcxgcy_to_cxcy(gcxgcy, priors_cxcy):
-    return _box_op("ssdhead_decode", gcxgcy, priors_cxcy)
+    return _box_fn("ssdhead_decode", gcxgcy, priors_cxcy)
 
 
 def get_offsets_coords(cxcy, priors_cxcy):
-    return _box_op("ssdhead_encode", cxcy, priors_cxcy)
+    return _box_fn("ssdhead_encode", cxcy, priors_cxcy)
 
 
 def _pair_matrix(name, set_1, set_2):

@@ -23,13 +23,15 @@ def _as_f32(a):
 
 
 def collate_gt(boxes: Sequence, classes: Sequence, difficult: Optional[Sequence] = None, keep_difficult: bool = True,
-               img_wh=None, pinned: bool = True):
+               img_wh=None, pinned: bool = True, out=None):
     """Ragged per-image gt -> (boxes [sumG,4] f32, classes [sumG] f32, offsets int32 [B+1]) as numpy arrays.
 
     ``boxes[i]`` is ``[n_i,4]`` xyxy (pixels when ``img_wh`` [B,2] is given, else already fractional), ``classes[i]``
     ``[n_i]`` class ids, ``difficult[i]`` ``[n_i]`` flags.  With ``pinned`` the arrays live in page-locked memory
-    (``ssdhead_host_alloc``) when a CUDA device is present.  Raises ``IndexError`` for an image left without a box,
-    as the reference does (``Losses.py:153``)."""
+    (``ssdhead_host_alloc``) when a CUDA device is present; every returned array keeps that allocation alive on its
+    own, so the result may be unpacked, sliced and the tuple dropped.  ``out``: a ``pinned.Staging`` to pack into
+    (the per-step upload path of ``ssd()`` recycles its blocks).  Raises ``IndexError`` for an image left without a
+    box, as the reference does (``Losses.py:153``)."""
     lib = _lib.load()
     B = len(boxes)
     if len(classes) != B or (difficult is not None and len(difficult) != B):
@@ -50,7 +52,13 @@ def collate_gt(boxes: Sequence, classes: Sequence, difficult: Optional[Sequence]
     def ptr_array(arrs):
         return (C.c_void_p * max(B, 1))(*[a.ctypes.data if a.size else None for a in arrs])
 
-    out_b, out_c, out_o, owner = _alloc(lib, cap, B, pinned)
+    if out is not None:
+        if out.capacity < cap or out.B != B:
+            raise ValueError("collate_gt: staging block too small for this batch")
+        out_b, out_c, out_o = out.boxes, out.classes, out.offsets
+        cap = out.capacity
+    else:
+        out_b, out_c, out_o = _alloc(cap, B, pinned)
     rc = lib.ssdhead_pack_gt(ptr_array(bx), ptr_array(cl), ptr_array(df) if df is not None else None,
                              counts.ctypes.data, B, 1 if keep_difficult else 0,
                              wh.ctypes.data if wh is not None else None,
@@ -60,41 +68,16 @@ def collate_gt(boxes: Sequence, classes: Sequence, difficult: Optional[Sequence]
     if rc < 0:
         _lib.check(rc, "ssdhead_pack_gt")
     n = int(rc)
-    res = (out_b[:n], out_c[:n], out_o)
-    for r in res:                      # keep the page-locked allocation alive as long as any view is
-        r.flags.writeable = True
-    return _Packed(res, owner)
+    return out_b[:n], out_c[:n], out_o
 
 
-class _Packed(tuple):
-    """(boxes, classes, offsets) - a tuple that also owns the page-locked allocation behind the arrays."""
-
-    def __new__(cls, arrays, owner):
-        self = super().__new__(cls, arrays)
-        self._owner = owner
-        return self
-
-
-class _PinnedBlock:
-    def __init__(self, lib, nbytes):
-        self.lib = lib
-        self.ptr = lib.ssdhead_host_alloc(max(nbytes, 16))
-
-    def __del__(self):
-        if getattr(self, "ptr", None):
-            self.lib.ssdhead_host_free(self.ptr)
-            self.ptr = None
-
-
-def _alloc(lib, cap, B, pinned):
-    nb, nc, no = cap * 16, cap * 4, (B + 1) * 4
+def _alloc(cap, B, pinned):
+    """Three arrays for `cap` boxes; page-locked (one block, each array owning it) when a CUDA device is present."""
     if pinned:
-        blk = _PinnedBlock(lib, nb + nc + no + 64)
-        if blk.ptr:
-            def view(off, count, dt):
-                buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(blk.ptr + off)
-                return np.frombuffer(buf, dtype=dt, count=count)
-            o1 = (nb + 15) // 16 * 16
-            o2 = o1 + (nc + 15) // 16 * 16
-            return view(0, cap * 4, np.float32).reshape(cap, 4), view(o1, cap, np.float32), view(o2, B + 1, np.int32), blk
-    return np.empty((cap, 4), np.float32), np.empty((cap,), np.float32), np.empty((B + 1,), np.int32), None
+        try:
+            from .pinned import Staging
+            s = Staging(cap, B)
+            return s.boxes, s.classes, s.offsets
+        except RuntimeError:
+            pass                                  # no CUDA device / no page-locked memory: ordinary host arrays
+    return np.empty((cap, 4), np.float32), np.empty((cap,), np.float32), np.empty((B + 1,), np.int32)

@@ -956,8 +956,8 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
 #endif
     int npos_total;
     if (FIN) {
-        // every CTA of the grid is co-resident (cooperative launch) and published its count long ago (step 0);
-        // the bounded wait can only trip if the launch contract is violated, and then degrades instead of hanging
+        // every CTA of the grid is co-resident (cooperative launch) and published its count long ago (step 0); a bounded
+        // wait that expires is reported (trap on one GPU, err_flag for a peer that never arrived), never papered over
         __shared__ int s_total;
         if (t == 0) {
             unsigned spins = 0;
@@ -973,8 +973,12 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 if (spins >= (1u << 27)) *p.err_flag = 1;
                 s_total = tot;
             } else {
+                // The launch is cooperative, so every CTA of the grid is resident and has published its count microseconds
+                // ago.  The spin is still bounded (~2 s) so that a broken launch contract cannot hang the GPU - but it
+                // never continues with a partial count: it traps, and the host sees a launch failure.
                 unsigned long long w;
-                while ((unsigned)((w = ld_relaxed_gpu_u64(p.arrive_total)) >> 32) < gridDim.x && ++spins < (1u << 22)) __nanosleep(64);
+                while ((unsigned)((w = ld_relaxed_gpu_u64(p.arrive_total)) >> 32) < gridDim.x && ++spins < (1u << 25)) __nanosleep(64);
+                if ((unsigned)(w >> 32) < gridDim.x) __trap();
                 s_total = (int)(unsigned)w;
             }
         }

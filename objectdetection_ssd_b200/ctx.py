@@ -15,27 +15,13 @@ import numpy as np
 from . import _lib
 
 
-def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
-    """Page-locked host array (cudaHostAlloc through the library) so copies are asynchronous."""
-    lib = _lib.load()
-    dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    ptr = lib.ssdhead_host_alloc(max(n, 16))
-    if not ptr:
-        raise RuntimeError("ssdhead_host_alloc failed")
-    buf = (C.c_uint8 * max(n, 16)).from_address(ptr)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[arr.__array_interface__["data"][0]] = (ptr, buf)
-    return arr
-
-
-_PINNED = {}
+from .pinned import pinned_empty       # noqa: E402,F401  (page-locked host array that owns its allocation)
 
 
 def pinned_free(arr: np.ndarray) -> None:
-    ent = _PINNED.pop(arr.__array_interface__["data"][0], None)
-    if ent is not None:
-        _lib.load().ssdhead_host_free(ent[0])
+    """Kept for callers of the first ABI revision: page-locked arrays now release their allocation when the last view of
+    them is collected, so there is nothing to do here."""
+    return None
 
 
 def _p(a):

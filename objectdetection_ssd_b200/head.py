@@ -40,6 +40,9 @@ def require_cuda(dev) -> torch.device:
     return dev
 
 
+_staging_pool = None     # pinned.StagingPool, created with the first host-list batch
+
+
 class PackedGT:
     """Ragged gt lists packed once: boxes [sumG,4] f32, classes [sumG] f32, offsets int32 [B+1]
     (host-side equivalent of Losses.py:129-130; no per-image synchronisation)."""
@@ -59,13 +62,27 @@ class PackedGT:
         self.off_host = off
         on_host = all(b.device.type == "cpu" for b in boxes) and all(c.device.type == "cpu" for c in classes)
         if on_host and torch.cuda.is_available():
-            # host lists (what a DataLoader hands over): one native pass into page-locked memory, one copy per array
+            global _staging_pool
+            if _staging_pool is None:
+                from .pinned import StagingPool
+                _staging_pool = StagingPool()
+            # host lists (what a DataLoader hands over): one native pass into a recycled page-locked block, ONE copy of
+            # the block to the device.  No cudaHostAlloc / cudaFreeHost per step; the block returns to the pool behind
+            # an event recorded after the copy, so it is never rewritten while the DMA engine may still read it.
             from .collate import collate_gt
-            self._staging = collate_gt(boxes, classes)           # keeps the pinned block alive until the copies ran
-            hb, hc, ho = self._staging
-            self.boxes = torch.from_numpy(hb).to(dev, non_blocking=True)
-            self.classes = torch.from_numpy(hc).to(dev, non_blocking=True)
-            self.off = torch.from_numpy(ho).to(dev, non_blocking=True)
+            from .pinned import gt_layout
+            st = _staging_pool.acquire(self.sumG, self.B)
+            collate_gt(boxes, classes, out=st)
+            blk = torch.empty(st.nbytes, dtype=torch.uint8, device=dev)
+            blk.copy_(torch.from_numpy(st.raw), non_blocking=True)
+            if st.event is None:
+                st.event = torch.cuda.Event()
+            st.event.record(torch.cuda.current_stream(dev))
+            _staging_pool.release(st, st.event)
+            o0, o1, o2, _ = gt_layout(st.capacity, self.B)
+            self.boxes = blk[o0:o0 + self.sumG * 16].view(torch.float32).view(self.sumG, 4)
+            self.classes = blk[o1:o1 + self.sumG * 4].view(torch.float32)
+            self.off = blk[o2:o2 + (self.B + 1) * 4].view(torch.int32)
             return
         self.boxes = torch.cat([b.reshape(-1, 4) for b in boxes]).to(device=dev, dtype=torch.float32).contiguous()
         self.classes = torch.cat([c.reshape(-1) for c in classes]).to(device=dev, dtype=torch.float32).contiguous()
@@ -92,13 +109,15 @@ class MultiboxHead:
         if need == 0:
             raise RuntimeError("ssdhead: unsupported shape for this entry point "
                                f"(B={B}, P={self.P}, C={self.C})")
-        key = (B, n)
+        # Every kernel leaves every counter it used zeroed again and writes the other regions before it reads them, so
+        # a buffer that was zero-filled once stays valid when only the gt count `n` changes (it does on every training
+        # step).  A change of the batch size is re-zeroed anyway - it is rare and keeps the header's contract
+        # (include/ssdhead.h, "re-zero a buffer before reusing it with another shape") to the letter.
+        key = B
         cur, last = self._ws.get(which, (None, None))
         if cur is None or cur.numel() < need:
-            cur = torch.zeros(need + 4096, dtype=torch.uint8, device=self.dev)
+            cur = torch.zeros(max(need, 2 * (cur.numel() if cur is not None else 0)) + 4096, dtype=torch.uint8, device=self.dev)
         elif last != key:
-            # the kernels leave their counters zeroed, but the layout of the counters depends on (B, n): a buffer
-            # last used with another shape must be zero-filled again (include/ssdhead.h, "zero-filled before first use")
             cur.zero_()
         self._ws[which] = (cur, key)
         return cur
@@ -275,14 +294,15 @@ class _MultiboxLossFn(torch.autograd.Function):
     gradients; backward rescales them on the device only if the upstream gradients are not 1."""
 
     @staticmethod
-    def forward(ctx, loc, conf, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, group):
-        need = loc.requires_grad or conf.requires_grad
+    def forward(ctx, loc, conf, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, group, need):
+        # `need` is decided by the caller: inside forward() grad mode is always off and ctx.needs_input_grad is set even
+        # under torch.no_grad(), so a validation loop would otherwise pay for 0.23 GB of dense gradients per step
         out = head.loss(loc, conf, gt, with_grads=need, neg_ratio=neg_ratio, pos_iou=pos_iou, group=group)
         ctx.head = head
         ctx.src = (loc.device, conf.device, loc.dtype, conf.dtype)
         ctx.grads = (out["grad_loc"], out["grad_conf"])
-        losses = out["losses"]
-        return losses[0].clone(), losses[1].clone()
+        a, b = out["losses"].unbind(0)          # views of a tensor made in this call: no copy kernels
+        return a, b
 
     @staticmethod
     def backward(ctx, g_loc_loss, g_conf_loss):
@@ -297,7 +317,7 @@ class _MultiboxLossFn(torch.autograd.Function):
                             (g_conf_loss if g_conf_loss is not None else z).to(head.dev, torch.float32).reshape(())])
         head.scale_grads(gl, gc, gout)
         ld, cd, lt, ct = ctx.src
-        return gl.to(device=ld, dtype=lt), gc.to(device=cd, dtype=ct), None, None, None, None, None
+        return gl.to(device=ld, dtype=lt), gc.to(device=cd, dtype=ct), None, None, None, None, None, None
 
 
 def multibox_loss(head: MultiboxHead, loc: torch.Tensor, conf: torch.Tensor,
@@ -305,7 +325,8 @@ def multibox_loss(head: MultiboxHead, loc: torch.Tensor, conf: torch.Tensor,
                   neg_ratio: int = NEG_RATIO, pos_iou: float = POS_IOU, group=None):
     """(loc_loss, conf_loss) as 0-dim tensors with grad_fn - the return of ``ssd()`` (Losses.py:134)."""
     gt = PackedGT(gt_boxes, gt_classes, head.dev)
-    return _MultiboxLossFn.apply(loc, conf, head, gt, neg_ratio, pos_iou, group)
+    need = torch.is_grad_enabled() and (loc.requires_grad or conf.requires_grad)
+    return _MultiboxLossFn.apply(loc, conf, head, gt, neg_ratio, pos_iou, group, need)
 
 
 def _detect(head: MultiboxHead, a: torch.Tensor, b: torch.Tensor, min_score: float, iou_thr: float, top_k: int,
@@ -353,15 +374,14 @@ class _MultiboxLossLevelsFn(torch.autograd.Function):
     level in the same layout, so autograd continues straight into each conv (the permute is a view)."""
 
     @staticmethod
-    def forward(ctx, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, L, *tensors):
+    def forward(ctx, head: MultiboxHead, gt: PackedGT, neg_ratio, pos_iou, L, need, *tensors):
         locs, confs = tensors[:L], tensors[L:]
-        need = any(t.requires_grad for t in tensors)
         out = head.loss_levels(locs, confs, gt, with_grads=need, neg_ratio=neg_ratio, pos_iou=pos_iou)
         ctx.head = head
         ctx.meta = [(t.shape, t.device, t.dtype) for t in tensors]
         ctx.grads = (out["grad_loc"], out["grad_conf"]) if need else None
-        losses = out["losses"]
-        return losses[0].clone(), losses[1].clone()
+        a, b = out["losses"].unbind(0)
+        return a, b
 
     @staticmethod
     def backward(ctx, g_loc_loss, g_conf_loss):
@@ -376,7 +396,7 @@ class _MultiboxLossLevelsFn(torch.autograd.Function):
         for gl, gc in zip(gls, gcs):
             head.scale_grads(gl, gc, gout)
         outs = [g.reshape(shape).to(device=dev, dtype=dt) for g, (shape, dev, dt) in zip(list(gls) + list(gcs), ctx.meta)]
-        return (None, None, None, None, None, *outs)
+        return (None, None, None, None, None, None, *outs)
 
 
 def multibox_loss_levels(head: MultiboxHead, loc_levels, conf_levels, gt_boxes, gt_classes,
@@ -384,7 +404,8 @@ def multibox_loss_levels(head: MultiboxHead, loc_levels, conf_levels, gt_boxes, 
     """(loc_loss, conf_loss) from per-level head tensors - ``ssd()`` without Model.py:212-235's permute/cat copies."""
     gt = PackedGT(gt_boxes, gt_classes, head.dev)
     L = len(conf_levels)
-    return _MultiboxLossLevelsFn.apply(head, gt, neg_ratio, pos_iou, L, *loc_levels, *conf_levels)
+    need = torch.is_grad_enabled() and any(t.requires_grad for t in list(loc_levels) + list(conf_levels))
+    return _MultiboxLossLevelsFn.apply(head, gt, neg_ratio, pos_iou, L, need, *loc_levels, *conf_levels)
 
 
 def detect_levels(head: MultiboxHead, loc_levels, conf_levels, min_score=0.2, iou_thr=0.45, top_k=200, img_wh=None,

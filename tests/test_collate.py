@@ -106,3 +106,32 @@ def test_collate_property_random_ragged_batches():
         assert np.array_equal(gb.view(np.uint32), rb.numpy().view(np.uint32))
 
     check()
+
+
+def test_collate_result_survives_unpacking_and_gc():
+    """the arrays must keep their (page-locked) allocation alive on their own - unpack the result,
+    drop everything else, collect, allocate more of the same kind, and the contents must still be there."""
+    import gc
+    from objectdetection_ssd_b200.collate import collate_gt
+    boxes, classes, diff, wh = _ragged(11, 17)
+    rb, rc, ro = O.collate_gt(boxes, classes, diff, True, None)
+    gb, gc_, go = collate_gt(boxes, classes, diff, True, None)          # tuple dropped at once
+    gc.collect()
+    junk = [collate_gt(boxes, classes, diff, True, None) for _ in range(8)]   # would reuse a freed block
+    for j in junk:
+        j[0][...] = -1.0
+    del junk
+    gc.collect()
+    assert np.array_equal(gb, rb.numpy()) and np.array_equal(gc_, rc.numpy()) and np.array_equal(go, ro.numpy())
+    tail = gb[3:]                                                        # a slice alone keeps the block alive too
+    del gb, gc_, go
+    gc.collect()
+    assert np.array_equal(tail, rb.numpy()[3:])
+
+
+def test_gt_staging_layout_is_16_byte_aligned():
+    from objectdetection_ssd_b200.pinned import gt_layout
+    for cap, B in ((1, 1), (63, 7), (2048, 256), (12800, 128)):
+        o0, o1, o2, total = gt_layout(cap, B)
+        assert o0 == 0 and o1 % 16 == 0 and o2 % 16 == 0 and total % 16 == 0
+        assert o1 >= cap * 16 and o2 - o1 >= cap * 4 and total - o2 >= (B + 1) * 4

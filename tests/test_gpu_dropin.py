@@ -110,3 +110,63 @@ def test_stress_prior_table_by_overwriting_module_global():
         assert abs(l2.item() - ref["conf_loss"].item()) <= 1e-5 * ref["conf_loss"].item()
     finally:
         Losses.ancs_xywh = old
+
+
+def test_pinned_collate_arrays_own_their_block_and_staging_pool_is_recycled():
+    """ADVICE r1: (high) arrays returned by collate_gt keep their page-locked block alive after the tuple is gone;
+    (medium) ssd() with host lists recycles staging blocks instead of cudaHostAlloc / cudaFreeHost per call, and a
+    block is not rewritten before the copy that read it has run."""
+    import gc
+    import numpy as np
+    from objectdetection_ssd_b200 import head as HD
+    from objectdetection_ssd_b200.collate import collate_gt
+    from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
+    pri = H.priors()
+    _, _, tb, tc = H.train_inputs(61, 9, pri.shape[0])
+    gb, gcl, go = collate_gt(tb, tc)
+    want = (np.concatenate([b.numpy() for b in tb]), np.concatenate([c.numpy() for c in tc]))
+    gc.collect()
+    junk = [collate_gt(tb, tc) for _ in range(16)]
+    for j in junk:
+        j[0][...] = -7.0
+    del junk
+    gc.collect()
+    assert np.array_equal(gb, want[0]) and np.array_equal(gcl, want[1]) and go[-1] == want[0].shape[0]
+    # staging pool: many ragged batches back to back on one stream; every packed gt must hold its own batch
+    head = MultiboxHead(pri, "cuda")
+    packed, wants = [], []
+    for s in range(40):
+        _, _, b, c = H.train_inputs(100 + s, 5 + s % 4, pri.shape[0])
+        packed.append(PackedGT(b, c, head.dev))
+        wants.append((torch.cat(b), torch.cat(c)))
+    torch.cuda.synchronize()
+    for g, (wb, wc) in zip(packed, wants):
+        assert torch.equal(g.boxes.cpu(), wb) and torch.equal(g.classes.cpu(), wc)
+        assert g.off.cpu().tolist() == g.off_host
+    assert HD._staging_pool is not None and len(HD._staging_pool.free) <= 32
+
+
+def test_util_box_functions_are_differentiable_like_the_reference():
+    """Util.py:86-102 are plain torch expressions in the reference, so autograd flows through them."""
+    from objectdetection_ssd_b200 import Util
+    pri = H.priors()[:300]
+    g = (torch.randn(300, 4, generator=torch.Generator().manual_seed(3)) * 0.5)
+    w = torch.randn(300, 4, generator=torch.Generator().manual_seed(4))
+    a = g.clone().requires_grad_(True)
+    (Util.gcxgcy_to_cxcy(a, pri).cpu() * w).sum().backward()
+    r = g.clone().requires_grad_(True)
+    (O.decode(r, pri) * w).sum().backward()
+    assert torch.allclose(a.grad, r.grad, rtol=1e-5, atol=1e-7)
+    boxes = O.xyxy_to_cxcywh(O.cxcywh_to_xyxy(H.priors()[100:400])).clone()
+    a = boxes.clone().requires_grad_(True)
+    (Util.get_offsets_coords(a, pri).cpu() * w).sum().backward()
+    r = boxes.clone().requires_grad_(True)
+    (O.encode(r, pri) * w).sum().backward()
+    assert torch.allclose(a.grad, r.grad, rtol=1e-5, atol=1e-6)
+    a = boxes.clone().requires_grad_(True)
+    (Util.xywh_to_xyxy(a).cpu() * w).sum().backward()
+    r = boxes.clone().requires_grad_(True)
+    (O.cxcywh_to_xyxy(r) * w).sum().backward()
+    assert torch.allclose(a.grad, r.grad, rtol=1e-6, atol=1e-7)
+    with torch.no_grad():
+        assert not Util.gcxgcy_to_cxcy(a, pri).requires_grad
