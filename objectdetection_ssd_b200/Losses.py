@@ -127,8 +127,15 @@ def inference_batch(loc, conf, top_k=200, min_score=0.2, iou_threshold=0.45, img
 
 
 def _image_size(phase, index):
-    """(w, h) of the image file the reference looks up through the dataset lists (Losses.py:87, Util.py:226-228)."""
-    return _U.get_img_sz(_U.all_images[phase][index])       # forwarded to the reference's Util (dataset side)
+    """(w, h) by which ``inference`` scales its boxes (Losses.py:87-89).  The reference looks the file up through the
+    dataset lists, ``get_img_sz(all_images[phase][index])``; that still works when those lists are available (they are
+    the out-of-scope dataset side, forwarded from the reference's own Util).  So that the drop-in also works WITHOUT
+    them, ``index`` may be the image path itself or a ``(w, h)`` pair."""
+    if isinstance(index, (tuple, list)) and len(index) == 2:
+        return float(index[0]), float(index[1])
+    if isinstance(index, (str, bytes)) or hasattr(index, "__fspath__"):
+        return _U.get_img_sz(index)
+    return _U.get_img_sz(_U.all_images[phase][index])
 
 
 def inference(l_, c_, index, top_k=200, phase='train', toDraw=True, min_score=0.2, iou_threshold=0.45):

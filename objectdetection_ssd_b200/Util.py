@@ -239,6 +239,14 @@ def get_map(det_boxes, det_classes, det_scores, gt_boxes, gt_classes):
     return {c: out[c] for c in range(20)}
 
 
+def get_img_sz(img_path):
+    """(width, height) of an image file (Util.py:226-228).  Local, so ``inference(..., toDraw=False)`` needs nothing of
+    the reference's dataset side beyond the path itself."""
+    from PIL import Image
+    with Image.open(img_path) as im:
+        return im.size
+
+
 def subsampling(x, step):
     """Strided sub-sampling used by Model.py for the fc6/fc7 surgery (Util.py:555-560); plain indexing."""
     for d, s in enumerate(step):

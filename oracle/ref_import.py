@@ -21,7 +21,18 @@ import sys
 import types
 import warnings
 
-REFERENCE_DIR = os.environ.get("SSD_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_dir() -> str:
+    # /root/reference exists in the build container only; on the GPU box the byte-for-byte copy made by
+    # oracle/fetch_ref.py (git-ignored oracle/_ref/) is used
+    if os.path.isfile("/root/reference/Losses.py"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_DIR = os.environ.get("SSD_REFERENCE_DIR") or _default_dir()
 
 
 def available() -> bool:

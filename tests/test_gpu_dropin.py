@@ -170,3 +170,20 @@ def test_util_box_functions_are_differentiable_like_the_reference():
     assert torch.allclose(a.grad, r.grad, rtol=1e-6, atol=1e-7)
     with torch.no_grad():
         assert not Util.gcxgcy_to_cxcy(a, pri).requires_grad
+
+
+def test_inference_standalone_image_size_lookup(tmp_path):
+    """inference(toDraw=False) without the reference's dataset lists: `index` as the image path (local get_img_sz,
+    Util.py:226-228) or as a (w, h) pair - boxes scaled by (w, h, w, h) as Losses.py:87-89 does."""
+    from PIL import Image
+    from objectdetection_ssd_b200 import Losses, Util
+    path = tmp_path / "img.png"
+    Image.new("RGB", (500, 375)).save(path)
+    assert tuple(Util.get_img_sz(str(path))) == (500, 375)
+    pri = H.priors()
+    loc, conf = H.detect_inputs(47, 1, pri.shape[0], bg_bias=8.0)
+    b1, c1, p1 = Losses.inference(loc[0].cuda(), conf[0].cuda(), str(path), toDraw=False, min_score=0.05)
+    b2, c2, p2 = Losses.inference(loc[0].cuda(), conf[0].cuda(), (500, 375), toDraw=False, min_score=0.05)
+    b0, c0, p0 = Losses.inference(loc[0].cuda(), conf[0].cuda(), (1, 1), toDraw=False, min_score=0.05)
+    assert b1.shape[0] > 0 and torch.equal(b1, b2) and torch.equal(c1, c2) and torch.equal(p1, p0)
+    assert torch.equal(b1.cpu(), b0.cpu() * torch.tensor([500., 375., 500., 375.]))
