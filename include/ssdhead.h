@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SSDHEAD_ABI_VERSION 1
+#define SSDHEAD_ABI_VERSION 2   /* 2: sparse gradient return (ssdhead_mine_sparse, ssdhead_ctx_multibox_loss_host_sparse) */
 
 #define SSDHEAD_E_BADARG      (-1)  /* null pointer / negative size */
 #define SSDHEAD_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for */
@@ -181,6 +181,24 @@ int ssdhead_mine(const float* loc_dev, const float* conf_dev,
                  double* sums_dev, float* losses_dev,
                  float* grad_loc_dev, float* grad_conf_dev,
                  uint32_t* mined_mask_dev, float* ce_dev,
+                 void* ws_dev, size_t ws_bytes, void* stream);
+/* ssdhead_mine with the gradients returned as PACKED ROWS instead of dense [B,P,*] tensors.  The gradient of this loss
+ * is sparse - only positives and mined negatives (about 4 * Npos of the P rows of an image) carry one, Losses.py:177-197
+ * - so a caller that scatters rows itself (or keeps its gradient buffers in host memory) needs no dense tensor at all.
+ * Image b owns slots [b*row_cap, (b+1)*row_cap):  row_cnt[2b] = number of rows of the image (if it exceeds row_cap only
+ * the first row_cap were stored - check it), row_cnt[2b+1] = how many of them are positives; slot s: row_idx = prior
+ * index inside the image, grad_conf_rows [.,C] = (softmax - onehot)/N; the positives come first and also own
+ * grad_loc_rows [.,4] = sign(loc - enc)/(4N).  The order of the rows inside an image is unspecified (the set is
+ * deterministic).  Pair with ssdhead_ce_stream called WITHOUT gradient pointers (no zero background is needed). */
+int ssdhead_mine_sparse(const float* loc_dev, const float* conf_dev,
+                 const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                 const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                 const int32_t* best_prior_dev, const int32_t* npos_dev, const int32_t* npos_norm_dev,
+                 const uint8_t* cls_u8_dev,
+                 int B, int P, int C, int neg_ratio, float pos_iou,
+                 double* sums_dev, float* losses_dev,
+                 int row_cap, int32_t* row_cnt_dev /*[B,2]*/, int32_t* row_idx_dev /*[B,row_cap]*/,
+                 float* grad_conf_rows_dev /*[B,row_cap,C]*/, float* grad_loc_rows_dev /*[B,row_cap,4]*/,
                  void* ws_dev, size_t ws_bytes, void* stream);
 int ssdhead_multibox_loss(const float* loc_dev, const float* conf_dev,
                           const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
@@ -361,6 +379,19 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* ctx, const float* loc_host, cons
                                    const float* gt_xyxy_host, const float* gt_cls_host, const int32_t* gt_off_host,
                                    int B, int neg_ratio, float pos_iou,
                                    float* losses_host, float* grad_loc_host, float* grad_conf_host);
+/* ssd() with host buffers and the gradients returned as packed rows (layout: ssdhead_mine_sparse).  Nothing dense is
+ * zeroed, copied or written on either side: page-locked output buffers receive their rows straight from the mining
+ * kernel (about 100 bytes per row over PCIe); pageable ones go through device staging.  This is the cheap way to hand
+ * the loss gradients to a host-side consumer: ~5 MB instead of 223 MB at batch 256.
+ * After ssdhead_ctx_xchg_import BOTH host entry points treat the batch as one shard of a batch spread over R GPUs:
+ * the positive count and the loss sums cross GPUs through the exchange buffers (NVLink peer stores from two
+ * single-thread kernels), losses and gradients carry the global normalisation of Losses.py:182,197, and all ranks
+ * must call in lock step. */
+int ssdhead_ctx_multibox_loss_host_sparse(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host,
+                                          const float* gt_xyxy_host, const float* gt_cls_host, const int32_t* gt_off_host,
+                                          int B, int neg_ratio, float pos_iou, float* losses_host,
+                                          int row_cap, int32_t* row_cnt_host /*[B,2]*/, int32_t* row_idx_host /*[B,row_cap]*/,
+                                          float* grad_conf_rows_host /*[B,row_cap,C]*/, float* grad_loc_rows_host /*[B,row_cap,4]*/);
 /* inference() over a batch with host buffers; outputs as ssdhead_detect. */
 int ssdhead_ctx_detect_host(ssdhead_ctx* ctx, const float* loc_host, const float* conf_host, int B,
                             float min_score, float iou_thr,

@@ -13,6 +13,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libssdhead.so")
 
+ABI_VERSION = 2
 WS_MATCH, WS_LOSS, WS_DETECT, WS_NMS = 0, 1, 2, 3
 E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN, E_STATE = -1, -2, -3, -4, -5
 
@@ -47,6 +48,8 @@ SIGNATURES = {
     "ssdhead_ctx_xchg_error": (_i, [_vp]),
     "ssdhead_mine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                           _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_mine_sparse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_finish_loss": (_i, [_vp, _vp, _vp, _vp]),
     "ssdhead_scale_grads": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "ssdhead_detect": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -61,6 +64,7 @@ SIGNATURES = {
     "ssdhead_ctx_multibox_loss_begin": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, C.POINTER(_vp), _vp]),
     "ssdhead_ctx_multibox_loss_end": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "ssdhead_ctx_multibox_loss_host_sparse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_detect_host": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_pack_gt": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "ssdhead_multibox_step_levels": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
@@ -97,7 +101,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.ssdhead_abi_version() != 1:
+    if lib.ssdhead_abi_version() != ABI_VERSION:
         raise RuntimeError("libssdhead.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

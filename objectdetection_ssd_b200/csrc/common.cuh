@@ -202,6 +202,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     return v;
 }
 
+// Cross-GPU exchange buffer of a sharded batch: every rank owns XCHG_WORDS 64-bit words that its PEERS write into over
+// NVLink (and it polls locally).  Slots are double-buffered by the parity of the step sequence number.
+constexpr int XCHG_MAX_R = 16;
+constexpr int XCHG_WORDS = 2 * 4 * XCHG_MAX_R;     // parity x {npos, sum_l1, sum_ce, sums_flag} x rank
+__host__ __device__ __forceinline__ int xchg_slot(unsigned seq, int what, int rank) { return ((int)(seq & 1u) * 4 + what) * XCHG_MAX_R + rank; }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);

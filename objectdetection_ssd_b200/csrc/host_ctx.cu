@@ -11,6 +11,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#ifdef __linux__
+#include <sched.h>
+#endif
 #include "common.cuh"
 
 using namespace ssdhead;
@@ -35,17 +38,69 @@ __global__ void sum_chunks_kernel(const double* __restrict__ chunk_sums, int nch
     losses[0] = (float)(a / (4.0 * N));
     losses[1] = (float)(c / N);
 }
+
+// Sharded batches through the host-buffer entry points: the same exchange buffers the fused mining kernel uses
+// (common.cuh), driven by two single-thread kernels.  xchg_npos_kernel: this rank's positive count goes to every rank,
+// the global count comes back - before any chunk is mined (it scales the gradients, Losses.py:182,197).
+struct XchgArgs {
+    int R, rank;
+    unsigned int seq;
+    unsigned long long* const* peers;
+    unsigned long long* local;
+    int* err_flag;
+};
+__global__ void xchg_npos_kernel(const int* __restrict__ npos_local, int* __restrict__ npos_global, const XchgArgs x)
+{
+    const unsigned long long word = ((unsigned long long)x.seq << 32) | (unsigned)(*npos_local);
+    for (int q = 0; q < x.R; ++q) st_relaxed_sys_u64(x.peers[q] + xchg_slot(x.seq, 0, x.rank), word);   // self-validating word
+    unsigned spins = 0;
+    int tot = 0;
+    for (int q = 0; q < x.R; ++q) {
+        unsigned long long w;
+        while ((unsigned)((w = ld_acquire_sys_u64(x.local + xchg_slot(x.seq, 0, q))) >> 32) != x.seq && ++spins < (1u << 27)) __nanosleep(64);
+        tot += (int)(unsigned)w;
+    }
+    if (spins >= (1u << 27)) *x.err_flag = 1;
+    *npos_global = tot;
+}
+// The chunk sums of this rank -> global sums (added in rank order on every rank: identical bits everywhere) -> losses.
+__global__ void sum_chunks_xchg_kernel(const double* __restrict__ chunk_sums, int nchunks, const int* __restrict__ npos_norm,
+                                       double* __restrict__ sums, float* __restrict__ losses, const XchgArgs x)
+{
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < nchunks; ++i) { a += chunk_sums[2 * i]; c += chunk_sums[2 * i + 1]; }
+    for (int q = 0; q < x.R; ++q) {
+        st_relaxed_sys_u64(x.peers[q] + xchg_slot(x.seq, 1, x.rank), (unsigned long long)__double_as_longlong(a));
+        st_relaxed_sys_u64(x.peers[q] + xchg_slot(x.seq, 2, x.rank), (unsigned long long)__double_as_longlong(c));
+    }
+    __threadfence_system();                      // values before flags
+    for (int q = 0; q < x.R; ++q) st_relaxed_sys_u64(x.peers[q] + xchg_slot(x.seq, 3, x.rank), (unsigned long long)x.seq);
+    unsigned spins = 0;
+    a = 0.0; c = 0.0;
+    for (int q = 0; q < x.R; ++q) {
+        while ((unsigned)ld_acquire_sys_u64(x.local + xchg_slot(x.seq, 3, q)) != x.seq && ++spins < (1u << 27)) __nanosleep(64);
+        a += __longlong_as_double((long long)ld_relaxed_sys_u64(x.local + xchg_slot(x.seq, 1, q)));
+        c += __longlong_as_double((long long)ld_relaxed_sys_u64(x.local + xchg_slot(x.seq, 2, q)));
+    }
+    if (spins >= (1u << 27)) *x.err_flag = 1;
+    sums[0] = a; sums[1] = c;
+    const double N = (double)(*npos_norm);
+    losses[0] = (float)(a / (4.0 * N));
+    losses[1] = (float)(c / N);
+}
 }  // namespace ssdhead
 
-// A few host threads that live as long as the context: they zero the caller's gradient buffers while the inputs of a
-// host-buffer loss call stream in (spawning threads per call would cost ~0.1 ms of every call).
+// A few host threads that live as long as the context: they zero the caller's DENSE gradient buffers while the inputs
+// of a host-buffer loss call stream in (spawning threads per call would cost ~0.1 ms of every call).  All waiting is
+// on condition variables: a rank that waits burns no core (eight ranks share the host's cores).
 struct ZeroPool {
     std::vector<std::thread> threads;
     std::mutex m;
-    std::condition_variable cv;
+    std::condition_variable cv, cv_done;
     std::function<void(int)> job;          // job(thread index); valid while a generation is running
     unsigned generation = 0;
-    std::atomic<int> finished{0};
+    int finished = 0;
+    int chunk_done[16] = {};               // threads that finished chunk k of the current generation
     bool stop = false;
 
     int size() const { return (int)threads.size(); }
@@ -63,16 +118,33 @@ struct ZeroPool {
                         j = job;
                     }
                     j(ti);
-                    finished.fetch_add(1, std::memory_order_release);
+                    { std::lock_guard<std::mutex> lk(m); ++finished; }
+                    cv_done.notify_all();
                 }
             });
     }
     void run(std::function<void(int)> j) {                 // returns at once; wait() blocks until every thread is done
-        finished.store(0, std::memory_order_relaxed);
-        { std::lock_guard<std::mutex> lk(m); job = std::move(j); ++generation; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            finished = 0;
+            for (int& c : chunk_done) c = 0;
+            job = std::move(j);
+            ++generation;
+        }
         cv.notify_all();
     }
-    void wait() { while (finished.load(std::memory_order_acquire) < size()) std::this_thread::yield(); }
+    void mark_chunk(int k) {                                // called by a worker when its part of chunk k is zero
+        { std::lock_guard<std::mutex> lk(m); ++chunk_done[k]; }
+        cv_done.notify_all();
+    }
+    void wait_chunk(int k) {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return chunk_done[k] >= size(); });
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return finished >= size(); });
+    }
     void shutdown() {
         { std::lock_guard<std::mutex> lk(m); stop = true; }
         cv.notify_all();
@@ -80,6 +152,22 @@ struct ZeroPool {
         threads.clear();
     }
 };
+
+// Zeroing threads of one context: the host's cores are shared by all ranks of the box (one process per GPU), so the
+// pool takes its share of what this process may run on - (affinity-mask cores / LOCAL_WORLD_SIZE) / 2, between 1 and 8
+// (memset throughput saturates near 8 threads beside the DMA traffic).  SSDHEAD_ZERO_THREADS overrides.
+static int zero_pool_threads()
+{
+    if (const char* e = getenv("SSDHEAD_ZERO_THREADS")) return std::max(1, std::min(64, atoi(e)));
+    unsigned cores = std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = (unsigned)CPU_COUNT(&set);
+#endif
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return (int)std::min(8u, std::max(1u, cores / (unsigned)ranks / 2u));
+}
 
 struct ssdhead_ctx {
     ZeroPool pool;
@@ -112,6 +200,12 @@ struct ssdhead_ctx {
     int32_t *det_cls, *det_prior, *det_cnt;
     // pinned scratch for small results
     float* h_losses;
+    // host-buffer path of a sharded batch: global positive count (device int)
+    int32_t* npos_global;
+    // sparse gradient return into pageable host buffers: device staging (grown on demand)
+    int32_t *sp_cnt, *sp_idx;
+    float *sp_conf, *sp_loc;
+    size_t sp_rows;                                     // capacity of the staging in rows (B * row_cap)
 };
 
 // Device-visible alias of a page-locked host buffer (UVA maps cudaHostAlloc / cudaHostRegister memory), or null for
@@ -200,6 +294,8 @@ void ssdhead_ctx_destroy(ssdhead_ctx* c)
     if (c->xchg_local) cudaFree(c->xchg_local);
     if (c->xchg_peers_dev) cudaFree(c->xchg_peers_dev);
     if (c->err_flag) cudaFree(c->err_flag);
+    void* more[] = {c->npos_global, c->sp_cnt, c->sp_idx, c->sp_conf, c->sp_loc};
+    for (void* b : more) if (b) cudaFree(b);
     cudaStream_t st[] = {c->s_main, c->s_aux, c->s_h2d, c->s_d2h};
     for (cudaStream_t s : st) if (s) cudaStreamDestroy(s);
     cudaEvent_t ev[] = {c->ev_fork, c->ev_join, c->ev_gt, c->ev_done};
@@ -278,6 +374,7 @@ int ssdhead_ctx_create(ssdhead_ctx** out, int device, int maxB, int P, int C, in
         CTX_CUDA(cudaMalloc(&c->xchg_peers_dev, 16 * sizeof(void*)));
         CTX_CUDA(cudaMalloc(&c->err_flag, sizeof(int)));
         CTX_CUDA(cudaMemset(c->err_flag, 0, sizeof(int)));
+        CTX_CUDA(cudaMalloc(&c->npos_global, sizeof(int32_t)));
         c->xchg_R = 1;
     }
     *out = c;
@@ -397,15 +494,21 @@ int ssdhead_ctx_xchg_error(ssdhead_ctx* c)
 
 // ssd() on HOST buffers (pass page-locked memory, e.g. ssdhead_host_alloc, for asynchronous copies).
 // gt goes first and the match starts at once; conf/loc travel in image chunks, each chunk is streamed
-// (CE) and mined as soon as it lands while the next one is in flight, and its gradient slice returns on a
-// third stream: H2D, kernels and D2H overlap.  Blocks until the results are in host memory.
-int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const float* conf_h,
-                                   const float* gt_xyxy_h, const float* gt_cls_h, const int32_t* gt_off_h,
-                                   int B, int neg_ratio, float pos_iou,
-                                   float* losses_h, float* grad_loc_h, float* grad_conf_h)
+// (CE) and mined as soon as it lands while the next one is in flight.  Gradients come back either DENSE (the caller's
+// [B,P,*] host tensors) or SPARSE (packed rows, ssdhead_ctx_multibox_loss_host_sparse).  After ssdhead_ctx_xchg_import
+// the batch is one shard of a batch spread over R GPUs: the positive count and the loss sums cross GPUs through the
+// exchange buffers (two single-thread kernels, NVLink peer stores), so losses and gradients carry the GLOBAL
+// normalisation of Losses.py:182,197; all ranks must call in lock step.  Blocks until the results are in host memory.
+static int loss_host_impl(ssdhead_ctx* c, const float* loc_h, const float* conf_h,
+                          const float* gt_xyxy_h, const float* gt_cls_h, const int32_t* gt_off_h,
+                          int B, int neg_ratio, float pos_iou, float* losses_h,
+                          float* grad_loc_h, float* grad_conf_h,
+                          int row_cap, int32_t* row_cnt_h, int32_t* row_idx_h, float* gconf_rows_h, float* gloc_rows_h)
 {
     if (!c || !loc_h || !conf_h || !gt_off_h || !losses_h) return SSDHEAD_E_BADARG;
     if ((grad_loc_h == nullptr) != (grad_conf_h == nullptr)) return SSDHEAD_E_BADARG;
+    const bool rows = row_cnt_h != nullptr;                   // sparse gradient return
+    if (rows && (row_cap <= 0 || !row_idx_h || !gconf_rows_h || !gloc_rows_h || grad_loc_h)) return SSDHEAD_E_BADARG;
     if (B <= 0 || B > c->maxB) return SSDHEAD_E_STATE;
     const int sumG = gt_off_h[B];
     if (sumG < 0 || sumG > c->max_sumG || (sumG > 0 && (!gt_xyxy_h || !gt_cls_h))) return SSDHEAD_E_STATE;
@@ -423,6 +526,17 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     int rc = ssdhead_match(c->gt_xyxy, c->gt_cls, c->gt_off, c->pri_xyxy, B, P, C, sumG, pos_iou,
                            c->best_prior, c->npos, c->cls_u8, nullptr, nullptr, c->ws_match, c->ws_match_bytes, c->s_aux);
     if (rc) return rc;
+    const bool sharded = c->xchg_R > 1;
+    XchgArgs xa = {};
+    const int32_t* npos_norm = c->npos + B;
+    if (sharded) {
+        xa.R = c->xchg_R; xa.rank = c->xchg_rank; xa.seq = ++c->xchg_seq;
+        xa.peers = (unsigned long long* const*)c->xchg_peers_dev; xa.local = (unsigned long long*)c->xchg_local; xa.err_flag = c->err_flag;
+        xchg_npos_kernel<<<1, 1, 0, c->s_aux>>>(c->npos + B, c->npos_global, xa);
+        count_launch();
+        SSD_LAUNCH_CHECK();
+        npos_norm = c->npos_global;
+    }
     SSD_CHECK_CUDA(cudaEventRecord(c->ev_join, c->s_aux));
 
     const float* loc_alias = mapped_host_alias(loc_h);
@@ -431,22 +545,20 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     const int per = (B + nchunks - 1) / nchunks;
     int used = 0;
 
-    // The gradient is sparse (about 4 Npos of the B x P rows): when the caller's gradient buffers are page-locked, the
-    // dense zero background never crosses PCIe.  Host threads zero the buffers chunk by chunk while the inputs stream
-    // in, the streaming kernel runs without its zero-fill, and the mining kernel stores its few hundred rows per image
-    // straight into the host buffers through their UVA aliases.  Same bits in the caller's buffers, ~220 MB less D2H.
+    // DENSE return.  The gradient is sparse (about 4 Npos of the B x P rows): when the caller's gradient buffers are
+    // page-locked, the dense zero background never crosses PCIe.  Host threads zero the buffers chunk by chunk while the
+    // inputs stream in, the streaming kernel runs without its zero-fill, and the mining kernel stores its few hundred
+    // rows per image straight into the host buffers through their UVA aliases.  Same bits in the caller's buffers.
     static const int sparse_ok = getenv("SSDHEAD_E2E_SPARSE") ? atoi(getenv("SSDHEAD_E2E_SPARSE")) : 1;
     float* gl_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_loc_h)) : nullptr;
     float* gc_alias = (grads && sparse_ok) ? const_cast<float*>(mapped_host_alias(grad_conf_h)) : nullptr;
     const bool sparse = gl_alias && gc_alias;
-    std::atomic<int> zero_done[8];
-    for (auto& z : zero_done) z.store(0);
     int T = 0;
     if (sparse) {
-        if (c->pool.size() == 0)
-            c->pool.start((int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
+        if (c->pool.size() == 0) c->pool.start(zero_pool_threads());
         T = c->pool.size();
-        c->pool.run([=, &zero_done](int ti) {
+        ZeroPool* pool = &c->pool;
+        c->pool.run([=](int ti) {
             for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
                 const int nb = std::min(per, B - b0);
                 const size_t r0 = (size_t)b0 * P, nr = (size_t)nb * P;
@@ -457,11 +569,36 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
                 };
                 zero_part(grad_conf_h + r0 * C, nr * C);
                 zero_part(grad_loc_h + r0 * 4, nr * 4);
-                zero_done[k].fetch_add(1, std::memory_order_release);
+                pool->mark_chunk(k);
             }
         });
     }
-    auto join_all = [&]() { if (sparse) c->pool.wait(); };     // the job references this frame: never return before it is done
+    // ROW return: packed rows; page-locked output buffers are written in place by the mining kernel, pageable ones
+    // through device staging copied back at the end.  No zero background exists on either side.
+    int32_t* rc_dev = nullptr; int32_t* ri_dev = nullptr; float* rgc_dev = nullptr; float* rgl_dev = nullptr;
+    bool rows_staged = false;
+    if (rows) {
+        rc_dev = (int32_t*)mapped_host_alias((const float*)row_cnt_h);
+        ri_dev = (int32_t*)mapped_host_alias((const float*)row_idx_h);
+        rgc_dev = const_cast<float*>(mapped_host_alias(gconf_rows_h));
+        rgl_dev = const_cast<float*>(mapped_host_alias(gloc_rows_h));
+        if (!rc_dev || !ri_dev || !rgc_dev || !rgl_dev) {
+            const size_t need_rows = (size_t)B * row_cap;
+            if (c->sp_rows < need_rows) {
+                void* old[] = {c->sp_cnt, c->sp_idx, c->sp_conf, c->sp_loc};
+                for (void* o : old) if (o) cudaFree(o);
+                c->sp_cnt = nullptr; c->sp_idx = nullptr; c->sp_conf = nullptr; c->sp_loc = nullptr; c->sp_rows = 0;
+                SSD_CHECK_CUDA(cudaMalloc(&c->sp_cnt, (size_t)c->maxB * 2 * 4));
+                SSD_CHECK_CUDA(cudaMalloc(&c->sp_idx, need_rows * 4));
+                SSD_CHECK_CUDA(cudaMalloc(&c->sp_conf, need_rows * C * 4));
+                SSD_CHECK_CUDA(cudaMalloc(&c->sp_loc, need_rows * 16));
+                c->sp_rows = need_rows;
+            }
+            rc_dev = c->sp_cnt; ri_dev = c->sp_idx; rgc_dev = c->sp_conf; rgl_dev = c->sp_loc;
+            rows_staged = true;
+        }
+    }
+    auto join_all = [&]() { if (sparse) c->pool.wait(); };     // the job references the caller's buffers: never return before it is done
 #define CTX_HOST_CHECK(expr) do { const int _rc = (expr); if (_rc) { join_all(); return _rc; } } while (0)
 
     // all input copies first (they depend on nothing), then the kernels chunk by chunk
@@ -480,13 +617,21 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
         void* ws = (char*)c->ws_loss + (size_t)k * c->ws_loss_bytes;
         float* gl = grads ? (sparse ? gl_alias + r0 * 4 : c->grad_loc + r0 * 4) : nullptr;
         float* gc = grads ? (sparse ? gc_alias + r0 * C : c->grad_conf + r0 * C) : nullptr;
-        rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, sparse ? nullptr : gl, sparse ? nullptr : gc, ws, c->ws_loss_bytes, c->s_main);
+        rc = ssdhead_ce_stream(c->conf + r0 * C, nb, P, C, nullptr, (sparse || rows) ? nullptr : gl, (sparse || rows) ? nullptr : gc, ws, c->ws_loss_bytes, c->s_main);
         CTX_HOST_CHECK(rc);
         if (k == 0) CTX_HOST_CHECK((int)cudaStreamWaitEvent(c->s_main, c->ev_join, 0));
-        if (sparse) while (zero_done[k].load(std::memory_order_acquire) < T) std::this_thread::yield();   // chunk k's slices are zero
-        rc = ssdhead_mine((loc_alias ? loc_alias : c->loc) + r0 * 4, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
-                          c->best_prior, c->npos + b0, c->npos + B, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
-                          c->chunk_sums + 2 * k, c->losses, gl, gc, nullptr, nullptr, ws, c->ws_loss_bytes, c->s_main);
+        if (sparse) c->pool.wait_chunk(k);                       // chunk k's slices are zero (condition variable, no spinning)
+        const float* loc_k = (loc_alias ? loc_alias : c->loc) + r0 * 4;
+        if (rows)
+            rc = ssdhead_mine_sparse(loc_k, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
+                                     c->best_prior, c->npos + b0, npos_norm, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
+                                     c->chunk_sums + 2 * k, c->losses, row_cap, rc_dev + 2 * (size_t)b0, ri_dev + (size_t)b0 * row_cap,
+                                     rgc_dev + (size_t)b0 * row_cap * C, rgl_dev + (size_t)b0 * row_cap * 4,
+                                     ws, c->ws_loss_bytes, c->s_main);
+        else
+            rc = ssdhead_mine(loc_k, c->conf + r0 * C, c->gt_xyxy, c->gt_cls, c->gt_off + b0, c->pri_xyxy, c->pri_cxcywh,
+                              c->best_prior, c->npos + b0, npos_norm, c->cls_u8 + r0, nb, P, C, neg_ratio, pos_iou,
+                              c->chunk_sums + 2 * k, c->losses, gl, gc, nullptr, nullptr, ws, c->ws_loss_bytes, c->s_main);
         CTX_HOST_CHECK(rc);
         if (grads && !sparse) {
             CTX_HOST_CHECK((int)cudaEventRecord(c->ev_out[k], c->s_main));
@@ -498,15 +643,43 @@ int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const flo
     }
     join_all();
 #undef CTX_HOST_CHECK
-    sum_chunks_kernel<<<1, 1, 0, c->s_main>>>(c->chunk_sums, used, c->npos + B, c->sums, c->losses);
+    if (sharded) sum_chunks_xchg_kernel<<<1, 1, 0, c->s_main>>>(c->chunk_sums, used, npos_norm, c->sums, c->losses, xa);
+    else sum_chunks_kernel<<<1, 1, 0, c->s_main>>>(c->chunk_sums, used, npos_norm, c->sums, c->losses);
     count_launch();
     SSD_LAUNCH_CHECK();
     SSD_CHECK_CUDA(cudaMemcpyAsync(c->h_losses, c->losses, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->s_main));
+    if (rows_staged) {
+        const size_t nrows = (size_t)B * row_cap;
+        SSD_CHECK_CUDA(cudaMemcpyAsync(row_cnt_h, rc_dev, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost, c->s_main));
+        SSD_CHECK_CUDA(cudaMemcpyAsync(row_idx_h, ri_dev, nrows * 4, cudaMemcpyDeviceToHost, c->s_main));
+        SSD_CHECK_CUDA(cudaMemcpyAsync(gconf_rows_h, rgc_dev, nrows * C * 4, cudaMemcpyDeviceToHost, c->s_main));
+        SSD_CHECK_CUDA(cudaMemcpyAsync(gloc_rows_h, rgl_dev, nrows * 16, cudaMemcpyDeviceToHost, c->s_main));
+    }
     SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_main));
     if (grads && !sparse) SSD_CHECK_CUDA(cudaStreamSynchronize(c->s_d2h));
     losses_h[0] = c->h_losses[0];
     losses_h[1] = c->h_losses[1];
     return 0;
+}
+
+int ssdhead_ctx_multibox_loss_host(ssdhead_ctx* c, const float* loc_h, const float* conf_h,
+                                   const float* gt_xyxy_h, const float* gt_cls_h, const int32_t* gt_off_h,
+                                   int B, int neg_ratio, float pos_iou,
+                                   float* losses_h, float* grad_loc_h, float* grad_conf_h)
+{
+    return loss_host_impl(c, loc_h, conf_h, gt_xyxy_h, gt_cls_h, gt_off_h, B, neg_ratio, pos_iou, losses_h,
+                          grad_loc_h, grad_conf_h, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ssdhead_ctx_multibox_loss_host_sparse(ssdhead_ctx* c, const float* loc_h, const float* conf_h,
+                                          const float* gt_xyxy_h, const float* gt_cls_h, const int32_t* gt_off_h,
+                                          int B, int neg_ratio, float pos_iou, float* losses_h,
+                                          int row_cap, int32_t* row_cnt_h, int32_t* row_idx_h,
+                                          float* grad_conf_rows_h, float* grad_loc_rows_h)
+{
+    if (!row_cnt_h) return SSDHEAD_E_BADARG;
+    return loss_host_impl(c, loc_h, conf_h, gt_xyxy_h, gt_cls_h, gt_off_h, B, neg_ratio, pos_iou, losses_h,
+                          nullptr, nullptr, row_cap, row_cnt_h, row_idx_h, grad_conf_rows_h, grad_loc_rows_h);
 }
 
 // inference() over a batch on HOST buffers: copies in, ssdhead_detect, detections out.  Blocks.

@@ -593,11 +593,16 @@ struct MineParams {
     unsigned long long* const* xchg_peers;   // [R] device table: peer-mapped exchange buffers, indexed by rank
     unsigned long long* xchg_local;          // this rank's buffer
     int* err_flag;                  // set to 1 if a bounded wait expired
+    // sparse gradient return (SPARSE = true; ssdhead_mine_sparse): the rows that carry a gradient, packed per image
+    // instead of scattered into dense [B,P,*] tensors.  Slot s of image b: sp_idx[b*cap+s] = prior, sp_conf[(b*cap+s)*C..]
+    // its conf-gradient row; the first sp_cnt[2b+1] slots are the positives and also own sp_loc[(b*cap+s)*4..].
+    float* sp_conf;
+    float* sp_loc;
+    int* sp_idx;
+    int* sp_cnt;                    // [B][2]: rows of the image (may exceed cap: then only cap were stored), positives
+    int sp_cap;
 };
 
-constexpr int XCHG_MAX_R = 16;
-constexpr int XCHG_WORDS = 2 * 4 * XCHG_MAX_R;     // parity x {npos, sum_l1, sum_ce, sums_flag} x rank
-__device__ __forceinline__ int xchg_slot(unsigned seq, int what, int rank) { return ((int)(seq & 1u) * 4 + what) * XCHG_MAX_R + rank; }
 
 // exclusive prefix sum over the MN_T threads of the CTA; *total receives the block sum
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[MN_W+1]*/, uint32_t* total)
@@ -622,7 +627,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 constexpr int MN_GC = 64;        // gt boxes staged in shared memory
 constexpr int MN_CAND = 512;     // boundary-bin candidates ranked directly (one per thread)
 
-template <int C, bool GRADS, bool FIN, bool LEVELS>
+template <int C, bool GRADS, bool FIN, bool LEVELS, bool SPARSE = false>
 __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* __restrict__ lvp)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -951,6 +956,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     LPHASE(3);
     const uint32_t npl = s_npl;                  // positives, listed from the end
     const uint32_t nsel = s_nsel + npl;
+    if (SPARSE && t == 0) { p.sp_cnt[2 * b] = (int)nsel; p.sp_cnt[2 * b + 1] = (int)npl; }
 #ifdef SSDHEAD_PHASE_TIMES
     if (t == 0 && b < 1024) { g_cta[b][0] = clock64() - cta_t0; g_cta[b][3] = nsel; }
 #endif
@@ -1034,7 +1040,8 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 gl.y = dy > 0.f ? gs_loc : (dy < 0.f ? -gs_loc : 0.f);
                 gl.z = dz > 0.f ? gs_loc : (dz < 0.f ? -gs_loc : 0.f);
                 gl.w = dw > 0.f ? gs_loc : (dw < 0.f ? -gs_loc : 0.f);
-                *gloc_row(j) = gl;
+                if (SPARSE) { if (i < (uint32_t)p.sp_cap) reinterpret_cast<float4*>(p.sp_loc)[(size_t)b * p.sp_cap + i] = gl; }
+                else *gloc_row(j) = gl;
             }
         }
     };
@@ -1049,6 +1056,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         const int j = valid ? (int)(idx < npl ? s_list[P - 1 - (int)idx] : s_list[idx - npl]) : 0;   // positives first
         const float* my_crow = LEVELS ? conf_row(j) : nullptr;      // per-level tensors: locate the row once, pass pointers
         float* my_grow = (LEVELS && GRADS) ? gconf_row(j) : nullptr;
+        if (SPARSE && valid && idx < (uint32_t)p.sp_cap) p.sp_idx[(size_t)b * p.sp_cap + idx] = j;
         if (staged) {
             // element e = lane + 32 i of the warp's 32 x C block belongs to row e / C, whose index lane e / C holds;
             // all loads are issued before the first shared-memory store (which the compiler must assume may alias)
@@ -1110,10 +1118,12 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
                 for (int q = 0; q < C; ++q)
                     wstage[lane * C + q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
             } else {
-                float* grow = LEVELS ? my_grow : gconf_row(j);
+                float* grow = SPARSE ? p.sp_conf + ((size_t)b * p.sp_cap + idx) * C : (LEVELS ? my_grow : gconf_row(j));
+                if (!SPARSE || idx < (uint32_t)p.sp_cap) {
 #pragma unroll
-                for (int q = 0; q < C; ++q)
-                    grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
+                    for (int q = 0; q < C; ++q)
+                        grow[q] = __fmul_rn(__fsub_rn(__fmul_rn(x[q], inv), q == c ? 1.0f : 0.0f), gs_conf);
+                }
             }
         }
         if (staged) {
@@ -1125,6 +1135,12 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
             for (int i = 0; i < C; ++i) {
                 const int e = lane + 32 * i, r = e / C, q = e - r * C;
                 float* rp;
+                if (SPARSE) {
+                    // the warp's 32 slots are contiguous in the packed output: one flat, fully coalesced block
+                    rp = p.sp_conf + ((size_t)b * p.sp_cap + (wbase + (uint32_t)r)) * C;
+                    if (r < nrw && wbase + (uint32_t)r < (uint32_t)p.sp_cap) rp[q] = v[i];
+                    continue;
+                }
                 if (LEVELS) rp = reinterpret_cast<float*>(__shfl_sync(FULL, (unsigned long long)my_grow, r));
                 else rp = gconf_row(__shfl_sync(FULL, j, r));
                 if (r < nrw) rp[q] = v[i];
@@ -1228,6 +1244,14 @@ mine_kernel(const MineParams p)
     mine_body<C, GRADS, FIN, false>(p, nullptr);
 }
 
+// the mining kernel with the gradient rows returned PACKED (ssdhead_mine_sparse): no dense [B,P,*] gradient tensor exists
+template <int C>
+__global__ void __launch_bounds__(MN_T, 2)
+mine_sparse_kernel(const MineParams p)
+{
+    mine_body<C, true, false, false, true>(p, nullptr);
+}
+
 // the same kernel on per-level head tensors (ssdhead_multibox_step_levels)
 template <int C, bool GRADS, bool FIN>
 __global__ void __launch_bounds__(MN_T, 2)
@@ -1304,6 +1328,17 @@ template <int C, bool GRADS>
 static int launch_mine(const MineParams& prm, cudaStream_t st)
 {
     auto kmn = mine_kernel<C, GRADS, false>;
+    const size_t smem_mn = mine_smem_bytes(prm.P);
+    SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
+    SSD_CHECK_CUDA(launch_pdl(4, kmn, dim3(prm.B), dim3(MN_T), smem_mn, st, prm));
+    count_launch();
+    return 0;
+}
+
+template <int C>
+static int launch_mine_sparse(const MineParams& prm, cudaStream_t st)
+{
+    auto kmn = mine_sparse_kernel<C>;
     const size_t smem_mn = mine_smem_bytes(prm.P);
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kmn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn));
     SSD_CHECK_CUDA(launch_pdl(4, kmn, dim3(prm.B), dim3(MN_T), smem_mn, st, prm));
@@ -1657,30 +1692,33 @@ int ssdhead_multibox_step_levels_sharded(const ssdhead_levels* levels,
 
 size_t ssdhead_xchg_bytes(void) { return (size_t)XCHG_WORDS * 8; }
 
-int ssdhead_mine(const float* loc, const float* conf,
+static int mine_impl(const float* loc, const float* conf,
                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
                  const float* pri_xyxy, const float* pri_cxcywh,
                  const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
                  int B, int P, int C, int neg_ratio, float pos_iou,
                  double* sums, float* losses, float* grad_loc, float* grad_conf,
                  uint32_t* mined_mask, float* ce,
-                 void* ws, size_t ws_bytes, void* stream)
+                 void* ws, size_t ws_bytes, void* stream,
+                 int sp_cap, int32_t* sp_cnt, int32_t* sp_idx, float* sp_conf, float* sp_loc)
 {
     if (B < 0 || P <= 0 || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!loc || !conf || !gt_off || !pri_xyxy || !pri_cxcywh || !npos || !npos_norm || !cls_u8 || !sums || !losses || !ws)
         return SSDHEAD_E_BADARG;
     if ((grad_loc == nullptr) != (grad_conf == nullptr)) return SSDHEAD_E_BADARG;
+    const bool sparse = sp_cnt != nullptr;
+    if (sparse && (sp_cap <= 0 || !sp_idx || !sp_conf || !sp_loc || grad_loc)) return SSDHEAD_E_BADARG;
     if (C != 21) return SSDHEAD_E_UNSUPPORTED;
     if (B == 0) return 0;
     if (!aligned16(loc) || !aligned16(pri_xyxy) || !aligned16(pri_cxcywh) || (gt_xyxy && !aligned16(gt_xyxy)) ||
-        (grad_loc && !aligned16(grad_loc)) || !aligned16(ws))
+        (grad_loc && !aligned16(grad_loc)) || !aligned16(ws) || (sparse && !aligned16(sp_loc)))
         return SSDHEAD_E_ALIGN;
     const size_t need = loss_workspace_bytes(B, P, C);
     if (need == 0) return SSDHEAD_E_UNSUPPORTED;
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 
-    MineParams prm;
+    MineParams prm = {};
     prm.loc = loc; prm.conf = conf; prm.cls_u8 = cls_u8;
     prm.gt_xyxy = (const float4*)gt_xyxy; prm.gt_cls = gt_cls; prm.gt_off = gt_off;
     prm.pri_xyxy = (const float4*)pri_xyxy; prm.pri_cxcywh = (const float4*)pri_cxcywh;
@@ -1692,12 +1730,39 @@ int ssdhead_mine(const float* loc, const float* conf,
     prm.partials = (double*)((char*)ws + 16);
     prm.ce = ce ? ce : ws_ce(ws, B);
     prm.ce_tap = ce;
-    prm.obj_u16 = nullptr;
-    prm.cls_rw = nullptr; prm.best_prior_w = nullptr; prm.npos_w = nullptr; prm.best_key = nullptr; prm.npos_acc = nullptr;
-    prm.arrive_total = nullptr;
-    prm.xchg_R = 0; prm.xchg_rank = 0; prm.xchg_seq = 0; prm.xchg_peers = nullptr; prm.xchg_local = nullptr; prm.err_flag = nullptr;
+    prm.sp_cap = sp_cap; prm.sp_cnt = sp_cnt; prm.sp_idx = sp_idx; prm.sp_conf = sp_conf; prm.sp_loc = sp_loc;
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
+    if (sparse) return launch_mine_sparse<21>(prm, st);
     return grad_loc ? launch_mine<21, true>(prm, st) : launch_mine<21, false>(prm, st);
+}
+
+int ssdhead_mine(const float* loc, const float* conf,
+                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                 const float* pri_xyxy, const float* pri_cxcywh,
+                 const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
+                 int B, int P, int C, int neg_ratio, float pos_iou,
+                 double* sums, float* losses, float* grad_loc, float* grad_conf,
+                 uint32_t* mined_mask, float* ce,
+                 void* ws, size_t ws_bytes, void* stream)
+{
+    return mine_impl(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, best_prior, npos, npos_norm, cls_u8,
+                     B, P, C, neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, mined_mask, ce, ws, ws_bytes, stream,
+                     0, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ssdhead_mine_sparse(const float* loc, const float* conf,
+                 const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                 const float* pri_xyxy, const float* pri_cxcywh,
+                 const int32_t* best_prior, const int32_t* npos, const int32_t* npos_norm, const uint8_t* cls_u8,
+                 int B, int P, int C, int neg_ratio, float pos_iou,
+                 double* sums, float* losses,
+                 int row_cap, int32_t* row_cnt, int32_t* row_idx, float* grad_conf_rows, float* grad_loc_rows,
+                 void* ws, size_t ws_bytes, void* stream)
+{
+    if (!row_cnt) return SSDHEAD_E_BADARG;
+    return mine_impl(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, best_prior, npos, npos_norm, cls_u8,
+                     B, P, C, neg_ratio, pos_iou, sums, losses, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes, stream,
+                     row_cap, row_cnt, row_idx, grad_conf_rows, grad_loc_rows);
 }
 
 // The whole training-head step of ONE GPU in two kernels: the streaming CE kernel with the fused natural match,
@@ -1728,7 +1793,7 @@ static int multibox_step_impl(const float* loc, const float* conf,
     int* npos_acc = (int*)w;                                          w += round_up((size_t)B * 4, 16);
     unsigned int* image_counter = (unsigned int*)w;
 
-    MineParams prm;
+    MineParams prm = {};
     prm.loc = loc; prm.conf = conf; prm.cls_u8 = cls_u8;
     prm.gt_xyxy = (const float4*)gt_xyxy; prm.gt_cls = gt_cls; prm.gt_off = gt_off;
     prm.pri_xyxy = (const float4*)pri_xyxy; prm.pri_cxcywh = (const float4*)pri_cxcywh;

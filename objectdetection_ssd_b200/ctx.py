@@ -24,6 +24,41 @@ def pinned_free(arr: np.ndarray) -> None:
     return None
 
 
+class SparseRows:
+    """Output buffers of ``loss_host_sparse`` (layout: ``ssdhead_mine_sparse`` in include/ssdhead.h), page-locked by
+    default so the mining kernel writes its rows straight into them.  ``cnt[b] = (rows, positives)`` of image b;
+    ``idx[b, s]`` = prior of slot s; ``grad_conf[b, s]`` its conf-gradient row; ``grad_loc[b, s]`` for s < positives."""
+
+    def __init__(self, B: int, cap: int = 1024, C_: int = 21, pinned: bool = True):
+        alloc = pinned_empty if pinned else (lambda shape, dt=np.float32: np.empty(shape, dt))
+        self.B, self.cap, self.C = int(B), int(cap), int(C_)
+        self.cnt = alloc((B, 2), np.int32)
+        self.idx = alloc((B, cap), np.int32)
+        self.grad_conf = alloc((B, cap, C_), np.float32)
+        self.grad_loc = alloc((B, cap, 4), np.float32)
+        self.cnt[...] = 0
+
+    def scatter(self, P: int, B: int = None):
+        """Dense (grad_loc [B,P,4], grad_conf [B,P,C]) numpy arrays rebuilt from the rows (tests / small batches)."""
+        B = self.B if B is None else B
+        gl = np.zeros((B, P, 4), np.float32)
+        gc = np.zeros((B, P, self.C), np.float32)
+        for b in range(B):
+            n, npos = int(self.cnt[b, 0]), int(self.cnt[b, 1])
+            if n > self.cap:
+                raise RuntimeError(f"image {b} produced {n} gradient rows, the buffers hold {self.cap}")
+            gc[b, self.idx[b, :n]] = self.grad_conf[b, :n]
+            gl[b, self.idx[b, :npos]] = self.grad_loc[b, :npos]
+        return gl, gc
+
+    def nbytes_used(self, B: int = None) -> int:
+        """Bytes the device actually wrote (rows + indices + counts) - what crossed PCIe."""
+        B = self.B if B is None else B
+        n = int(np.minimum(self.cnt[:B, 0], self.cap).sum())
+        npos = int(self.cnt[:B, 1].sum())
+        return n * (self.C * 4 + 4) + npos * 16 + B * 8
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -61,6 +96,20 @@ class SSDHeadContext:
         _lib.check(self.lib.ssdhead_ctx_multibox_loss_host(
             self._h, _p(loc), _p(conf), _p(gt_xyxy), _p(gt_cls), _p(gt_off), B, int(neg_ratio), float(pos_iou),
             _p(losses), _p(grad_loc), _p(grad_conf)), "ssdhead_ctx_multibox_loss_host")
+        return float(losses[0]), float(losses[1])
+
+    def loss_host_sparse(self, loc, conf, gt_xyxy, gt_cls, gt_off, rows: "SparseRows",
+                         neg_ratio: int = 3, pos_iou: float = 0.5):
+        """ssd() on host arrays with the gradients returned as packed rows in ``rows`` (``SparseRows``): nothing dense
+        is zeroed or copied.  Returns (loc_loss, conf_loss)."""
+        B = int(loc.shape[0])
+        if B > rows.B:
+            raise ValueError(f"SparseRows holds {rows.B} images, the batch has {B}")
+        losses = np.zeros(2, np.float32)
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_host_sparse(
+            self._h, _p(loc), _p(conf), _p(gt_xyxy), _p(gt_cls), _p(gt_off), B, int(neg_ratio), float(pos_iou),
+            _p(losses), rows.cap, _p(rows.cnt), _p(rows.idx), _p(rows.grad_conf), _p(rows.grad_loc)),
+            "ssdhead_ctx_multibox_loss_host_sparse")
         return float(losses[0]), float(losses[1])
 
     def detect_host(self, loc, conf, out_boxes, out_prob, out_cls, out_prior, out_cnt,

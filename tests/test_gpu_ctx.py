@@ -145,3 +145,42 @@ def test_host_paths_with_pageable_buffers_equal_pinned_ones():
     pinned_free(hl)
     pinned_free(hc)
     ctx.close()
+
+
+@pytest.mark.parametrize("B,pinned_rows", [(5, True), (32, True), (32, False)])
+def test_loss_host_sparse_rows_equal_the_dense_gradients(B, pinned_rows):
+    """ssdhead_ctx_multibox_loss_host_sparse: the packed rows, scattered, are bit-identical to the dense gradient buffers
+    of ssdhead_ctx_multibox_loss_host; positives come first and own the loc rows; a too small row_cap is reported
+    through the counts (rows beyond it are dropped, nothing is written out of bounds)."""
+    from objectdetection_ssd_b200.ctx import SSDHeadContext, SparseRows, pinned_empty
+    pri, loc, conf, gb, gc, gx, gcl, off = _inputs(23, B)
+    P = pri.shape[0]
+    ctx = SSDHeadContext(pri.numpy(), max_batch=B)
+    hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    hl[:] = loc
+    hc[:] = conf
+    gl, gcf = pinned_empty(loc.shape), pinned_empty(conf.shape)
+    l1, l2 = ctx.loss_host(hl, hc, gx, gcl, off, gl, gcf)
+    rows = SparseRows(B, cap=1024, pinned=pinned_rows)
+    rows.idx[...] = -1
+    s1, s2 = ctx.loss_host_sparse(hl, hc, gx, gcl, off, rows)
+    assert (s1, s2) == (l1, l2)
+    sgl, sgc = rows.scatter(P)
+    assert np.array_equal(sgl, gl) and np.array_equal(sgc, gcf)
+    for b in range(B):
+        n, npos = rows.cnt[b]
+        assert n == int((gcf[b] != 0).any(-1).sum()) and npos == int((gl[b] != 0).any(-1).sum())
+        assert len(set(rows.idx[b, :n].tolist())) == n
+        assert not pinned_rows or (rows.idx[b, n:] == -1).all()      # in-place rows: nothing is written past the count
+    assert rows.nbytes_used() < 0.1 * (gl.nbytes + gcf.nbytes)
+    # a cap below the largest image: counts still report the true number, the stored rows are a subset
+    small = int(rows.cnt[:, 0].max()) - 3
+    r2 = SparseRows(B, cap=small, pinned=pinned_rows)
+    r2.idx[...] = -1
+    ctx.loss_host_sparse(hl, hc, gx, gcl, off, r2)
+    assert np.array_equal(r2.cnt, rows.cnt)
+    b = int(rows.cnt[:, 0].argmax())
+    assert set(r2.idx[b].tolist()) <= set(rows.idx[b, :rows.cnt[b, 0]].tolist())
+    with pytest.raises(RuntimeError):
+        r2.scatter(P)
+    ctx.close()
