@@ -2,20 +2,27 @@
 """bench.py - SSD multibox head path on B200: images/sec and fraction of the HBM roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload train|detect] [--batch B]
+                    [--workload train|detect|stress] [--batch B] [--collective peer|nccl] [--no-others]
 
 One "step" = one pass of the hot path over one batch of synthetic head outputs:
-  train  (default)  match + hard-negative-mined CE + L1 loss, forward AND gradients
+  train  (default)  match + hard-negative-mined CE + L1 loss, forward AND gradients, SSD300 (8732 priors, 1-10 gt/image)
                     (BASELINE.json configs[1]/[3]; default batch 256 per GPU = north_star's target size)
-  detect            decode + conf 0.01 threshold + per-class NMS + global top-200 (configs[2], batch 64)
-Under torchrun (N > 1) every rank owns `--batch` images (weak scaling); the batch-global positive
-count and the loss sums are all-reduced over NCCL exactly as a sharded ssd() call does.
-Rank 0 prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference
-(oracle/, torch-CPU ops, all host threads) on a bounded sample of the same workload.
+  detect            decode + conf 0.01 threshold + per-class NMS + global top-200 (configs[2]; default batch 64,
+                    `--batch 256` = north_star's target size)
+  stress            configs[4]: SSD512-style 24 564 priors, 100 gt boxes per image, batch 128 per GPU - the match + loss
+                    step is the timed step, the detect step of the same shape is reported next to it
+Under torchrun (N > 1) every rank owns `--batch` images (weak scaling); the batch-global positive count and the loss
+sums cross GPUs exactly as a sharded ssd() call needs them (Losses.py:182,197), and after the timed loop one extra
+sharded step in which every rank feeds rank 0's shard is compared bit for bit with the single-GPU step of that shard
+(`sharded_check`; a mismatch ends the run with a non-zero exit code).
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference's own CPU implementation (the unmodified
+`Losses.ssd` / `Losses.inference` from oracle/_ref when it travelled with the tree, else the oracle port) on all host
+cores, on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -28,15 +35,23 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-ALGO_BYTES = {  # SURVEY.md 8(d), fp32, P = 8732
-    "train": 1_746_400,      # loc + conf in, dense grad_loc + grad_conf out
-    "train_fwd": 873_200,
-    "detect": 878_800,
-}
-# algorithmic bytes per image of the dominant kernel alone (DESIGN.md "Kernels"): ce_stream_kernel reads conf
-# (8732*84) and writes CE (8732*4), one class byte per prior and the dense gradient background (8732*100)
-CE_STREAM_BYTES = 8732 * (84 + 4 + 1 + 100)
 L2_BYTES = 126 * 1024 * 1024
+C = 21
+
+
+def algo_bytes(P: int, what: str) -> int:
+    """algorithmic bytes per image, fp32."""
+    if what == "train":          # loc + conf in, dense grad_loc + grad_conf out
+        return 2 * P * 25 * 4
+    if what == "train_fwd":
+        return P * 25 * 4
+    return P * 25 * 4 + 200 * 28   # detect: loc + conf in, <= 200 x 28 B out
+
+
+def ce_stream_bytes(P: int) -> int:
+    """Dominant kernel alone: conf in (84 B/prior), CE (4) + class byte (1) + dense gradient background
+    (100) out."""
+    return P * (84 + 4 + 1 + 100)
 
 
 def peaks():
@@ -47,8 +62,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def source_hash() -> str:
+    """Hash of the kernel sources the shipped libssdhead.so was built from (profiles/traffic.json records the same)."""
+    from objectdetection_ssd_b200 import build
+    return build.source_hash()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
-    """SM clock + throttle reasons through NVML while the timed region runs."""
+    """SM clock + throttle reasons through NVML while the timed region runs (polled every millisecond)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -70,19 +98,21 @@ class ClockSampler:
                  "hw_power_brake": 0x80}
         while not self._stop.is_set():
             try:
+                timed = self._timed.is_set()
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((self._timed.is_set(), mhz))
-                if self._timed.is_set():
+                timed = timed or self._timed.is_set()       # a sample that straddles the start still saw the load
+                self.samples.append((timed, mhz))
+                if timed:
                     for k, bit in names.items():
                         if r & bit:
                             self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.001)
 
     def start(self):
         if self.nv:
@@ -96,118 +126,186 @@ class ClockSampler:
         self._stop.set()
         if self._thr:
             self._thr.join(timeout=1.0)
-        timed = [m for t, m in self.samples if t] or [m for _, m in self.samples]
+        timed = [m for t, m in self.samples if t]
         return {"sm_mhz": float(np.median(timed)) if timed else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples_in_timed_region": len([1 for t, _ in self.samples if t])}
+                "reasons": sorted(self.reasons), "samples_in_timed_region": len(timed)}
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+WORKLOADS = {
+    # name: (prior spec, default batch per GPU, gt per image lo..hi, seed)
+    "train": ("ssd300", 256, 1, 10, 1),
+    "detect": ("ssd300", 64, 0, 0, 3),
+    "stress": ("ssd512", 128, 100, 100, 4),
+}
+
+
+def prior_table(kind: str):
+    from objectdetection_ssd_b200 import priors as PR
+    return PR.make_priors(PR.SSD300_SPEC if kind == "ssd300" else PR.SSD512_SPEC)
+
+
+def workload_config(args, world):
+    kind, _, glo, ghi, _ = WORKLOADS[args.workload]
+    P = 8732 if kind == "ssd300" else 24564
+    l2 = "inputs rotate through >= 2 x 126 MB of distinct device buffers (larger than L2)"
+    if args.workload == "detect":
+        return {"workload": "SSD300 inference post-processing: decode + conf 0.01 threshold + per-class NMS (iou 0.45) + "
+                            "global top-200; background-logit bias +6 (~1.1k candidates/class)",
+                "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_priors": P, "num_classes": C,
+                "parallelism": f"image-sharded x{world}, no collective", "l2": l2}
+    name = ("SSD300-VGG16 VOC head, 8732 priors, 21 classes: match + hard-negative-mined CE + L1 loss, forward and "
+            "gradients (north_star target size: batch 256 per GPU)" if args.workload == "train" else
+            "stress (BASELINE.json configs[4]): SSD512-style 24 564 priors, 100 gt boxes per image, 21 classes: match + "
+            "hard-negative-mined CE + L1 loss, forward and gradients; decode + NMS of the same shape reported in `stress_detect`")
+    coll = getattr(args, "collective", "peer")
+    par = "single GPU" if world == 1 else (
+        f"image-sharded x{world}; Npos and the loss sums cross GPUs " +
+        ("through NVLink peer-memory stores inside the mining kernel (--collective peer)" if coll == "peer"
+         else "through two NCCL all-reduces (--collective nccl)"))
+    return {"workload": name, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_priors": P,
+            "num_classes": C, "gt_per_image": f"U{{{glo}..{ghi}}}" if glo != ghi else str(glo), "parallelism": par, "l2": l2}
+
+
+def metric_name(workload):
+    if workload == "detect":
+        return "images/sec, SSD300 decode + NMS (conf 0.01, top-200)"
+    if workload == "stress":
+        return "images/sec, SSD512-style (24 564 priors, 100 gt/image) match + multibox loss fwd+bwd"
+    return "images/sec, SSD300 match + multibox loss fwd+bwd"
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def reference_inputs(workload, B, P):
+def reference_inputs(workload, B):
     from objectdetection_ssd_b200 import synth
-    if workload == "train":
-        gb, gc = synth.make_gt(1, B)
-        loc, conf = synth.make_head(1, B, P)
+    kind, _, glo, ghi, seed = WORKLOADS[workload]
+    P = 8732 if kind == "ssd300" else 24564
+    if workload in ("train", "stress"):
+        gb, gc = synth.make_gt(seed, B, glo, ghi)
+        loc, conf = synth.make_head(seed, B, P)
         return (torch.from_numpy(loc), torch.from_numpy(conf), [torch.from_numpy(b) for b in gb],
                 [torch.from_numpy(c) for c in gc])
-    loc, conf = synth.make_head(3, B, P, loc_scale=0.5, bg_bias=6.0)
+    loc, conf = synth.make_head(seed, B, P, loc_scale=0.5, bg_bias=6.0)
     return torch.from_numpy(loc), torch.from_numpy(conf)
 
 
-def reference_step(workload, data, pri, pxy):
-    """One pass of the reference's CPU algorithm (oracle port, torch-CPU ops) over the sample."""
-    from oracle import ssd_oracle as O
-    if workload == "train":
-        loc, conf, tb, tc = data
-        l = loc.clone().requires_grad_(True)
-        c = conf.clone().requires_grad_(True)
-        a, b = O.ssd_reference_style((l, c), tc, tb, pri, pxy)
-        (a + b).backward()
-        return a.item() + b.item()
-    loc, conf = data
-    n = 0
-    for i in range(loc.shape[0]):
-        n += O.detect_image(loc[i], conf[i], pri, 0.01, 0.45, 200)[0].shape[0]
-    return n
+class ReferenceImpl:
+    """The reference's CPU implementation of the path: the UNMODIFIED Losses.ssd / Losses.inference when the reference
+    sources are importable (oracle/ref_import: /root/reference in the build container, oracle/_ref on the GPU box),
+    else the oracle's port of them (torch-CPU ops, same algorithm)."""
+
+    def __init__(self, workload):
+        from oracle import ssd_oracle as O
+        from oracle import ref_import
+        self.O, self.workload = O, workload
+        kind = WORKLOADS[workload][0]
+        self.pri = O.make_priors() if kind == "ssd300" else O.make_priors(**O.SSD512)
+        self.pxy = O.cxcywh_to_xyxy(self.pri)
+        self.kind, self.R = "port", None
+        if ref_import.available() and os.environ.get("SSD_BENCH_REFERENCE", "1") != "0":
+            try:
+                self.R = ref_import.load()
+                self.ref_import = ref_import
+                self.kind = "reference"
+            except Exception as e:                              # noqa: BLE001 - fall back to the port, say so
+                print(f"bench.py: unmodified reference not importable ({e}); timing the oracle port", file=sys.stderr)
+
+    def step(self, data):
+        if self.workload in ("train", "stress"):
+            loc, conf, tb, tc = data
+            l = loc.clone().requires_grad_(True)
+            c = conf.clone().requires_grad_(True)
+            if self.R is not None:
+                _, RL = self.R
+                with self.ref_import.quiet(), self._priors(RL):
+                    a, b = RL.ssd((l, c), tc, tb)
+                    (a + b).backward()
+            else:
+                a, b = self.O.ssd_reference_style((l, c), tc, tb, self.pri, self.pxy)
+                (a + b).backward()
+            return a.item() + b.item()
+        loc, conf = data
+        n = 0
+        for i in range(loc.shape[0]):
+            if self.R is not None:
+                _, RL = self.R
+                with self.ref_import.quiet(), self._priors(RL):
+                    out = RL.inference(loc[i], conf[i], 0, top_k=200, toDraw=False, min_score=0.01, iou_threshold=0.45)
+                n += len(out[0])
+            else:
+                n += self.O.detect_image(loc[i], conf[i], self.pri, 0.01, 0.45, 200)[0].shape[0]
+        return n
+
+    def _priors(self, RL):
+        """The reference reads its module-global prior tables at call time: swap them only for the 24 564-prior shape."""
+        import contextlib
+        if WORKLOADS[self.workload][0] == "ssd300":
+            return contextlib.nullcontext()
+        return self.ref_import.priors(RL, self.pri)
+
+    def describe(self, B):
+        fn = {"train": "ssd() fwd+bwd", "stress": "ssd() fwd+bwd (24 564 priors, 100 gt/image)",
+              "detect": "inference() looped over the images, bg bias +6, min_score 0.01"}[self.workload]
+        who = "unmodified reference Losses." if self.kind == "reference" else "oracle port of Losses."
+        return f"{who}{fn}, batch {B}"
 
 
 def cpu_baseline(workload, budget_s=20.0):
-    """Bounded CPU sample of the same workload (SURVEY.md 8(d) 'CPU baseline')."""
-    from oracle import ssd_oracle as O
-    pri = O.make_priors()
-    pxy = O.cxcywh_to_xyxy(pri)
-    B = 32 if workload == "train" else 1
-    data = reference_inputs(workload, B, pri.shape[0])
+    """Bounded CPU sample of the same workload (SURVEY.md 8(d) 'CPU baseline'), all host cores."""
+    torch.set_num_threads(host_cores())
+    impl = ReferenceImpl(workload)
+    B = {"train": 32, "stress": 4, "detect": 1}[workload]
+    data = reference_inputs(workload, B)
     t0 = time.perf_counter()
-    reference_step(workload, data, pri, pxy)            # warm-up
-    first = time.perf_counter() - t0
-    best = first
+    impl.step(data)            # warm-up
+    best = time.perf_counter() - t0
     reps = 0
     while reps < 3 and (time.perf_counter() - t0) + best < budget_s:
         t = time.perf_counter()
-        reference_step(workload, data, pri, pxy)
+        impl.step(data)
         best = min(best, time.perf_counter() - t)
         reps += 1
-    what = ("oracle.ssd_reference_style fwd+bwd, batch 32, 1-10 gt/image" if workload == "train"
-            else "oracle.detect_image, 1 image, bg bias +6, min_score 0.01")
-    return {"value": B / best, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{what}; best of {reps + 1} runs, {best * 1e3:.1f} ms/pass"}
+    return {"value": B / best, "unit": "images/s", "cores": torch.get_num_threads(), "kind": impl.kind,
+            "sample": f"{impl.describe(B)}; best of {reps + 1} runs, {best * 1e3:.1f} ms/pass"}
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from oracle import ssd_oracle as O
-    pri = O.make_priors()
-    pxy = O.cxcywh_to_xyxy(pri)
-    B = min(args.batch, 32) if args.workload == "train" else min(args.batch, 2)
-    data = reference_inputs(args.workload, B, pri.shape[0])
-    for _ in range(min(args.warmup, 1)):
-        reference_step(args.workload, data, pri, pxy)
+    # rank 0 runs alone (the other ranks have exited): it may use every core this process is allowed on, whatever
+    # OMP_NUM_THREADS torchrun exported
+    torch.set_num_threads(host_cores())
+    impl = ReferenceImpl(args.workload)
+    # bounded sample: the full batch for the loss (the reference gets FASTER per image with the batch size), a few images
+    # for its per-image detect loop and for the 24 564-prior / 100-gt stress shape
+    B = {"train": args.batch, "stress": min(args.batch, 8), "detect": min(args.batch, 4)}[args.workload]
+    data = reference_inputs(args.workload, B)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        impl.step(data)
     steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
-        reference_step(args.workload, data, pri, pxy)
+        impl.step(data)
     dt = (time.perf_counter() - t0) / steps
     val = B / dt
-    sample = (f"batch {B} of the {args.batch}-image workload per step (bounded sample), {steps} timed steps"
-              f" (requested {args.steps}), torch {torch.__version__} CPU ops")
+    sample = (f"{impl.describe(B)} per step (bounded sample of the {args.batch}-image workload), {steps} timed steps "
+              f"(requested {args.steps}), torch {torch.__version__} CPU ops, {torch.get_num_threads()} threads")
     line = {
-        "impl": "reference", "metric": "images/sec, SSD300 " + ("match + multibox loss fwd+bwd" if args.workload == "train"
-                                                                else "decode + NMS (conf 0.01, top-200)"),
-        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": metric_name(args.workload),
+        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": impl.kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, world):
-    if args.workload == "train":
-        return {"workload": "SSD300-VGG16 VOC head, 8732 priors, 21 classes: match + hard-negative-mined CE + L1 loss, "
-                            "forward and gradients (north_star target size: batch 256 per GPU)",
-                "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_priors": 8732, "num_classes": 21,
-                "gt_per_image": "U{1..10}", "parallelism": (f"image-sharded x{world}; Npos and the loss sums cross GPUs "
-                                + ("through NVLink peer-memory stores inside the mining kernel (--collective peer)"
-                                   if getattr(args, "collective", "peer") == "peer" else "through two NCCL all-reduces (--collective nccl)")
-                                if world > 1 else "single GPU"),
-                "l2": "inputs rotate through >= 2 x 126 MB of distinct device buffers (larger than L2)"}
-    return {"workload": "SSD300 inference post-processing: decode + conf 0.01 threshold + per-class NMS (iou 0.45) + "
-                        "global top-200; background-logit bias +6 (~1.1k candidates/class)",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_priors": 8732, "num_classes": 21,
-            "parallelism": f"image-sharded x{world}, no collective",
-            "l2": "inputs rotate through >= 2 x 126 MB of distinct device buffers (larger than L2)"}
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -234,17 +332,120 @@ class _DevPtrView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def time_train(args, rank, world, dev, sampler):
+class LossRunner:
+    """One rank's training-head step through the context's C entry points: single GPU, peer-memory sharded, or the
+    NCCL route."""
+
+    def __init__(self, pri, B, dev, world, rank, collective, max_total_gt):
+        from objectdetection_ssd_b200.ctx import SSDHeadContext
+        self.pri, self.B, self.dev, self.world, self.rank = pri, B, dev, world, rank
+        self.P = int(pri.shape[0])
+        self.max_total_gt = max_total_gt
+        self.ctx = SSDHeadContext(pri.numpy(), max_batch=B, max_total_gt=max_total_gt, device=dev.index)
+        self.collective = "none"
+        self.npos_norm = torch.zeros(1, dtype=torch.int32, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            self.collective = collective
+            if collective == "peer" and B > 2 * torch.cuda.get_device_properties(dev).multi_processor_count:
+                self.collective = "nccl"     # the in-kernel exchange needs one co-resident CTA per image (B <= 2 x SMs)
+            if self.collective == "peer":
+                # one-off: exchange the CUDA IPC handles of the ranks' exchange buffers; afterwards the step is the same
+                # two kernels as on one GPU, the mining kernel trading Npos and the loss sums with its peers over NVLink
+                handles = [None] * world
+                dist.all_gather_object(handles, self.ctx.xchg_export())
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+                try:
+                    self.ctx.xchg_import(handles, rank)
+                except RuntimeError as e:                  # no peer access between these GPUs: every rank falls back
+                    print(f"bench.py: rank {rank}: peer-memory import failed ({e}); using --collective nccl", file=sys.stderr)
+                    ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    self.ctx.close()
+                    self.ctx = SSDHeadContext(pri.numpy(), max_batch=B, max_total_gt=max_total_gt, device=dev.index)
+                    self.collective = "nccl"
+                dist.barrier()
+
+    def step(self, l, c, tgx, tgc, toff, sumG, sums, losses, gl, gcf, st):
+        ctx, B = self.ctx, self.B
+        if self.world == 1 or self.collective == "peer":
+            ctx.loss_dev(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
+                         sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
+        else:
+            import torch.distributed as dist
+            p = ctx.loss_begin(c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
+                               gl.data_ptr(), gcf.data_ptr(), st)
+            self.npos_norm.copy_(torch.as_tensor(_DevPtrView(p, 1, "<i4"), device=self.dev))
+            dist.all_reduce(self.npos_norm)
+            ctx.loss_end(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B,
+                         self.npos_norm.data_ptr(), sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
+            dist.all_reduce(sums)
+            ctx.finish_loss(sums.data_ptr(), self.npos_norm.data_ptr(), losses.data_ptr(), st)
+
+    def sharded_check(self, workload, st):
+        """Every rank feeds RANK 0's shard: the global positive count is world x Npos_0, the global sums world x sums_0,
+        so the global losses must equal the single-GPU losses of that shard BIT FOR BIT (world is a power of two: the
+        scaling is exact) and every gradient element must be exactly 1/world of the single-GPU one.  The single-GPU
+        step runs on a second context without the exchange."""
+        from objectdetection_ssd_b200 import synth
+        from objectdetection_ssd_b200.ctx import SSDHeadContext
+        _, _, glo, ghi, seed = WORKLOADS[workload]
+        B, P, dev, world = self.B, self.P, self.dev, self.world
+        gb, gc = synth.make_gt(seed, B, glo, ghi)
+        gx, gcl, off = synth.pack_gt(gb, gc)
+        loc, conf = synth.make_head(seed, B, P)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        tl, tc, tgx, tgc, toff = d(loc), d(conf), d(gx), d(gcl), d(off)
+        sumG = int(off[-1])
+        out = {}
+        for name in ("sharded", "single"):
+            sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            losses = torch.zeros(2, device=dev)
+            gl, gcf = torch.zeros_like(tl), torch.zeros_like(tc)
+            if name == "sharded":
+                for _ in range(2):                             # twice: both parities of the exchange slots
+                    self.step(tl, tc, tgx, tgc, toff, sumG, sums, losses, gl, gcf, st)
+            else:
+                one = SSDHeadContext(self.pri.numpy(), max_batch=B, max_total_gt=self.max_total_gt, device=dev.index)
+                one.loss_dev(tl.data_ptr(), tc.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
+                             sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
+                torch.cuda.synchronize()
+                one.close()
+            torch.cuda.synchronize()
+            out[name] = (sums, losses, gl, gcf)
+        (ss, sl, sgl, sgc), (os_, ol, ogl, ogc) = out["sharded"], out["single"]
+        pow2 = world & (world - 1) == 0
+        ok_loss = bool(torch.equal(sl, ol)) if pow2 else bool(torch.allclose(sl, ol, rtol=1e-6))
+        ok_sums = bool(torch.allclose(ss, os_ * world, rtol=1e-14, atol=0))
+        ok_grad = bool(torch.equal(sgl * world, ogl) and torch.equal(sgc * world, ogc)) if pow2 else \
+            bool(torch.allclose(sgl * world, ogl, rtol=1e-6) and torch.allclose(sgc * world, ogc, rtol=1e-6))
+        ok = ok_loss and ok_sums and ok_grad and not (self.collective == "peer" and self.ctx.xchg_error())
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        import torch.distributed as dist
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return {"ok": bool(int(flag.item())), "this_rank_ok": ok, "loss": sl.tolist(), "expect": ol.tolist(),
+                "grad_rows_checked": int((ogc != 0).any(-1).sum()), "collective": self.collective,
+                "what": f"every rank fed rank 0's shard: global losses == single-GPU losses bit for bit, "
+                        f"gradients x {world} == single-GPU gradients bit for bit, sums x {world} to 1e-14"}
+
+    def close(self):
+        self.ctx.close()
+
+
+def time_loss(args, rank, world, dev, sampler, workload, B, steps, warmup, kernel_alone=True, e2e=True):
+    """The training-head step (match + loss fwd + gradients) of `workload` ('train' or 'stress') at batch B per GPU."""
     from objectdetection_ssd_b200 import _lib, synth, priors as PR
-    from objectdetection_ssd_b200.ctx import SSDHeadContext, pinned_empty
+    from objectdetection_ssd_b200.ctx import SparseRows, pinned_empty
     lib = _lib.load()
-    B = args.batch
-    pri = PR.make_priors()
+    kind, _, glo, ghi, seed = WORKLOADS[workload]
+    pri = prior_table(kind)
     P = pri.shape[0]
-    ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)
-    gb, gc = synth.make_gt(1 + rank, B)
+    run = LossRunner(pri, B, dev, world, rank, getattr(args, "collective", "peer"), max(128 * B, ghi * B))
+    ctx = run.ctx
+    gb, gc = synth.make_gt(seed + rank, B, glo, ghi)
     gx, gcl, off = synth.pack_gt(gb, gc)
-    loc, conf = synth.make_head(1 + rank, B, P)
+    loc, conf = synth.make_head(seed + rank, B, P)
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     tgx, tgc, toff = d(gx), d(gcl), d(off)
     per_set = B * P * 25 * 4
@@ -256,131 +457,117 @@ def time_train(args, rank, world, dev, sampler):
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
     sumG = int(off[-1])
-    npos_norm = torch.zeros(1, dtype=torch.int32, device=dev)
-    collective = "none"
-    if world > 1:
-        import torch.distributed as dist
-        collective = args.collective
-        if collective == "peer" and B > 2 * torch.cuda.get_device_properties(dev).multi_processor_count:
-            collective = "nccl"          # the in-kernel exchange needs one co-resident CTA per image (B <= 2 x SMs)
-        if collective == "peer":
-            # one-off: exchange the CUDA IPC handles of the ranks' exchange buffers; afterwards the step is the same
-            # two kernels as on one GPU, the mining kernel trading Npos and the loss sums with its peers over NVLink
-            handles = [None] * world
-            dist.all_gather_object(handles, ctx.xchg_export())
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
-            try:
-                ctx.xchg_import(handles, rank)
-            except RuntimeError as e:                      # no peer access between these GPUs: every rank falls back
-                print(f"bench.py: rank {rank}: peer-memory import failed ({e}); using --collective nccl", file=sys.stderr)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                ctx.close()
-                ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)   # a context without the exchange
-                collective = "nccl"
-            dist.barrier()
-        args.collective = collective      # what actually ran (reported in config.parallelism)
 
     def step(i):
         l, c = sets[i % nset]
-        if world == 1 or collective == "peer":
-            ctx.loss_dev(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
-                         sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
-        else:
-            p = ctx.loss_begin(c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, sumG,
-                               gl.data_ptr(), gcf.data_ptr(), st)
-            npos_norm.copy_(torch.as_tensor(_DevPtrView(p, 1, "<i4"), device=dev))
-            dist.all_reduce(npos_norm)
-            ctx.loss_end(l.data_ptr(), c.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B,
-                         npos_norm.data_ptr(), sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st)
-            dist.all_reduce(sums)
-            ctx.finish_loss(sums.data_ptr(), npos_norm.data_ptr(), losses.data_ptr(), st)
+        run.step(l, c, tgx, tgc, toff, sumG, sums, losses, gl, gcf, st)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = _lib.launch_count()
     sampler.timed(True)
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     e1.record(stream)
     barrier(world)
     sampler.timed(False)
     launches = _lib.launch_count() - n0
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    loss_val = losses.tolist()
-    if collective == "peer" and ctx.xchg_error():
+    if run.collective == "peer" and ctx.xchg_error():
         raise SystemExit("bench.py: a wait for a peer rank expired inside the sharded step (results invalid)")
-
-    # ---- the dominant kernel alone, CUDA events on its launch stream: the streaming CE kernel with the fused natural
-    # match (ssdhead_ce_match_stream with run_finalizer = 0, on a scratch match workspace) ----
-    ws_bytes = int(lib.ssdhead_workspace_bytes(_lib.WS_LOSS, B, P, 21, 0))
-    ws = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
-    wm = torch.zeros(int(lib.ssdhead_workspace_bytes(_lib.WS_MATCH, B, P, 21, sumG)) + 256, dtype=torch.uint8, device=dev)
-    pri_xyxy = PR.cxcywh_to_xyxy_host(pri).to(dev)
-    cls_u8 = torch.empty(B, P, dtype=torch.uint8, device=dev)
-    bestp = torch.empty(max(sumG, 1), dtype=torch.int32, device=dev)
-    npos_k = torch.empty(B + 1, dtype=torch.int32, device=dev)
-
-    def kern(i):
-        return lib.ssdhead_ce_match_stream(sets[i % nset][1].data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(),
-                                           pri_xyxy.data_ptr(), B, P, 21, sumG, 0.5, None, gl.data_ptr(), gcf.data_ptr(),
-                                           cls_u8.data_ptr(), bestp.data_ptr(), npos_k.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), wm.data_ptr(), wm.numel(), 0, st)
-
-    kn = max(10, min(args.steps, 200))
-    for i in range(3):
-        _lib.check(kern(i), "ssdhead_ce_match_stream")
+    r = dict(ms_total=ms, launches=launches, P=P, algo=algo_bytes(P, "train"), collective=run.collective, kern_ms=None)
+    # losses of set 0 (the data the end-to-end leg uses), for the e2e cross-check
+    step(0)
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    for i in range(kn):
-        kern(i)
-    k1.record(stream)
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / kn
+    r["losses"] = losses.tolist()
 
-    # ---- end to end through the host-buffer C ABI (pinned host tensors in, losses + gradients out) ----
-    hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
-    hl[:] = loc
-    hc[:] = conf
-    hgl, hgc = pinned_empty(loc.shape), pinned_empty(conf.shape)
-    for _ in range(2):
+    if world > 1:
+        r["sharded_check"] = run.sharded_check(workload, st)
+
+    if kernel_alone:
+        # ---- the dominant kernel alone, CUDA events on its launch stream: the streaming CE kernel with the fused
+        # natural match (ssdhead_ce_match_stream with run_finalizer = 0, on a scratch match workspace) ----
+        ws = torch.zeros(int(lib.ssdhead_workspace_bytes(_lib.WS_LOSS, B, P, C, 0)) + 256, dtype=torch.uint8, device=dev)
+        wm = torch.zeros(int(lib.ssdhead_workspace_bytes(_lib.WS_MATCH, B, P, C, sumG)) + 256, dtype=torch.uint8, device=dev)
+        pri_xyxy = PR.cxcywh_to_xyxy_host(pri).to(dev)
+        cls_u8 = torch.empty(B, P, dtype=torch.uint8, device=dev)
+        bestp = torch.empty(max(sumG, 1), dtype=torch.int32, device=dev)
+        npos_k = torch.empty(B + 1, dtype=torch.int32, device=dev)
+
+        def kern(i):
+            return lib.ssdhead_ce_match_stream(sets[i % nset][1].data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(),
+                                               pri_xyxy.data_ptr(), B, P, C, sumG, 0.5, None, gl.data_ptr(), gcf.data_ptr(),
+                                               cls_u8.data_ptr(), bestp.data_ptr(), npos_k.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), wm.data_ptr(), wm.numel(), 0, st)
+
+        kn = max(10, min(steps, 200))
+        for i in range(3):
+            _lib.check(kern(i), "ssdhead_ce_match_stream")
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for i in range(kn):
+            kern(i)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        r.update(kern_ms=k0.elapsed_time(k1) / kn, kernel="ce_stream_kernel<21,true,true>", kernel_bytes=ce_stream_bytes(P) * B)
+
+    if e2e:
+        # ---- end to end through the host-buffer C ABI: pinned host tensors in, losses + gradient ROWS back in host
+        # memory (ssdhead_ctx_multibox_loss_host_sparse).  With N > 1 and the peer exchange it is the SHARDED loss: the
+        # ranks call in lock step and the global normalisation crosses GPUs inside the call. ----
+        hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+        hl[:] = loc
+        hc[:] = conf
+        cap = 1024 if workload == "train" else 8192
+        rows = SparseRows(B, cap=cap)
+        en = max(3, min(steps, 20))
+        for _ in range(2):
+            e2e_loss = ctx.loss_host_sparse(hl, hc, gx, gcl, off, rows)
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(en):
+            e2e_loss = ctx.loss_host_sparse(hl, hc, gx, gcl, off, rows)
+        torch.cuda.synchronize()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
+        if int(rows.cnt[:, 0].max()) > cap:
+            raise SystemExit("bench.py: an image produced more gradient rows than the e2e row buffers hold")
+        sharded_e2e = world > 1 and run.collective == "peer"
+        # conf and gt are copied; loc is read in place from the page-locked host buffer, positive rows only (32-byte
+        # sectors); the rows come back by direct stores into the page-locked row buffers
+        h2d = conf.nbytes + gx.nbytes + gcl.nbytes + off.nbytes + int(rows.cnt[:, 1].sum()) * 32
+        d2h = rows.nbytes_used() + 8
+        want = r["losses"] if (world == 1 or sharded_e2e) else None
+        chk = {"loss": list(e2e_loss), "device_step_loss": want, "copies_declared": True,
+               "ok": None if want is None else bool(abs(e2e_loss[0] - want[0]) <= 1e-5 * abs(want[0]) and
+                                                    abs(e2e_loss[1] - want[1]) <= 1e-5 * abs(want[1]))}
+        # the dense variant (caller's [B,P,*] gradient tensors in host memory), for the record
+        hgl, hgc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+        dn = max(2, min(steps, 5))
         ctx.loss_host(hl, hc, gx, gcl, off, hgl, hgc)
-    en = max(3, min(args.steps, 20))
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(en):
-        ctx.loss_host(hl, hc, gx, gcl, off, hgl, hgc)
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
-    # conf and gt are copied; loc is read in place from the page-locked host buffer, positive rows only (counted as 128
-    # rows of 32-byte sectors per image, an upper bound at 1-10 gts per image)
-    h2d = conf.nbytes + gx.nbytes + gcl.nbytes + off.nbytes + B * 128 * 32
-    # the dense zero background of the gradients never crosses PCIe when the caller's buffers are page-locked: host threads
-    # zero them while the inputs stream in and the mining kernel stores its rows straight into them.
-    # Bytes counted from what arrived: the non-zero rows of the two host gradient tensors + the two losses.
-    if os.environ.get("SSDHEAD_E2E_SPARSE", "1") != "0":
-        d2h = int((hgc != 0).any(-1).sum()) * 84 + int((hgl != 0).any(-1).sum()) * 16 + 8
-    else:
-        d2h = loc.nbytes + conf.nbytes + 8
-    ctx.close()
-    return dict(ms_total=ms, launches=launches, kern_ms=kern_ms, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, losses=loss_val,
-                kernel="ce_stream_kernel<21,true,true>", kernel_bytes=CE_STREAM_BYTES * B, algo=ALGO_BYTES["train"],
-                e2e_steps=en, collective=collective)
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(dn):
+            ctx.loss_host(hl, hc, gx, gcl, off, hgl, hgc)
+        torch.cuda.synchronize()
+        dense_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / dn, world, dev)
+        r.update(e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, e2e_steps=en, e2e_check=chk, e2e_dense_ms=dense_ms,
+                 e2e_sharded=sharded_e2e)
+        if chk["ok"] is False:
+            raise SystemExit(f"bench.py: end-to-end losses {e2e_loss} differ from the device step's {want}")
+    run.close()
+    return r
 
 
-def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
-    from objectdetection_ssd_b200 import _lib, synth, priors as PR
-    from objectdetection_ssd_b200.head import MultiboxHead, detect
+def time_detect(args, rank, world, dev, sampler, B, steps, warmup, workload="detect", e2e=True):
+    from objectdetection_ssd_b200 import _lib, synth
+    from objectdetection_ssd_b200.head import MultiboxHead
     from objectdetection_ssd_b200.ctx import SSDHeadContext, pinned_empty
-    steps = steps or args.steps
-    warmup = warmup if warmup is not None else args.warmup
-    B = args.batch if args.workload == "detect" else 64
-    pri = PR.make_priors()
+    kind = WORKLOADS[workload][0]
+    pri = prior_table(kind)
     P = pri.shape[0]
     head = MultiboxHead(pri, dev)
     loc, conf = synth.make_head(3 + rank, B, P, loc_scale=0.5, bg_bias=6.0)
@@ -395,13 +582,13 @@ def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
                cls=torch.empty(B, top_k, dtype=torch.int32, device=dev),
                prior=torch.empty(B, top_k, dtype=torch.int32, device=dev),
                cnt=torch.empty(B, dtype=torch.int32, device=dev))
-    ws = torch.zeros(int(lib.ssdhead_workspace_bytes(_lib.WS_DETECT, B, P, 21, 0)) + 256, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(int(lib.ssdhead_workspace_bytes(_lib.WS_DETECT, B, P, C, 0)) + 256, dtype=torch.uint8, device=dev)
     pri_dev = head.pri_cxcywh
 
     def step(i):
         # the C ABI directly (what objectdetection_ssd_b200.head.detect calls after allocating its outputs)
         l, c = sets[i % nset]
-        return lib.ssdhead_detect(l.data_ptr(), c.data_ptr(), pri_dev.data_ptr(), B, P, 21, 0.01, 0.45, top_k, None, 0,
+        return lib.ssdhead_detect(l.data_ptr(), c.data_ptr(), pri_dev.data_ptr(), B, P, C, 0.01, 0.45, top_k, None, 0,
                                   out["boxes"].data_ptr(), out["prob"].data_ptr(), out["cls"].data_ptr(),
                                   out["prior"].data_ptr(), out["cnt"].data_ptr(), ws.data_ptr(), ws.numel(), st)
 
@@ -419,38 +606,42 @@ def time_detect(args, rank, world, dev, sampler, steps=None, warmup=None):
     sampler.timed(False)
     launches = _lib.launch_count() - n0
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    # end to end: host buffers in, detections out
-    ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)
-    hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
-    hl[:] = loc
-    hc[:] = conf
-    ob, op = pinned_empty((B, 200, 4)), pinned_empty((B, 200))
-    oc, oi, on = pinned_empty((B, 200), np.int32), pinned_empty((B, 200), np.int32), pinned_empty((B,), np.int32)
-    for _ in range(2):
-        ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
-    en = max(3, min(steps, 20))
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(en):
-        ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
-    ctx.close()
-    # conf is copied; of loc only the rows of the candidates the sweep visits cross PCIe (the kernel reads the page-locked
-    # host buffer in place): counted as 512 rows of 32-byte sectors per image, an upper bound at this workload
-    return dict(ms_total=ms, launches=launches, kern_ms=None, e2e_ms=e2e_ms, h2d=conf.nbytes + B * 512 * 32,
-                d2h=ob.nbytes + op.nbytes + oc.nbytes + oi.nbytes + on.nbytes, B=B, steps=steps,
-                kernel="detect_score_kernel + detect_nms_kernel (whole step)", algo=ALGO_BYTES["detect"], e2e_steps=en,
-                detections=int(out["cnt"].clamp(min=0).sum()))
+    r = dict(ms_total=ms, launches=launches, kern_ms=None, B=B, steps=steps, P=P, algo=algo_bytes(P, "detect"),
+             kernel="detect kernels (whole step)", detections=int(out["cnt"].clamp(min=0).sum()))
+    if e2e:
+        # end to end: host buffers in, detections out
+        ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)
+        hl, hc = pinned_empty(loc.shape), pinned_empty(conf.shape)
+        hl[:] = loc
+        hc[:] = conf
+        ob, op = pinned_empty((B, 200, 4)), pinned_empty((B, 200))
+        oc, oi, on = pinned_empty((B, 200), np.int32), pinned_empty((B, 200), np.int32), pinned_empty((B,), np.int32)
+        for _ in range(2):
+            ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
+        en = max(3, min(steps, 20))
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(en):
+            ctx.detect_host(hl, hc, ob, op, oc, oi, on, 0.01, 0.45)
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / en, world, dev)
+        ctx.close()
+        # conf is copied; of loc only the rows of the candidates the sweep visits cross PCIe (the kernel reads the
+        # page-locked host buffer in place): counted as 512 rows of 32-byte sectors per image, an upper bound here
+        r.update(e2e_ms=e2e_ms, h2d=conf.nbytes + B * 512 * 32,
+                 d2h=ob.nbytes + op.nbytes + oc.nbytes + oi.nbytes + on.nbytes, e2e_steps=en,
+                 e2e_check={"detections_per_image": float(np.clip(on, 0, None).mean()), "copies_declared": True,
+                            "ok": bool((on >= 0).all() and (on <= 200).all())})
+    return r
 
 
 def time_train_levels(rank, dev, B=256, steps=200):
     """Training-head step on the six per-level tensors (NHWC conv outputs viewed as rows) instead of the concatenated
     [B,8732,*] pair - SURVEY.md 8(f) #3 - next to what building that pair costs (the torch.cat of Model.py:234-235)."""
     import ctypes
-    from objectdetection_ssd_b200 import _lib, synth, priors as PR
+    from objectdetection_ssd_b200 import _lib, synth
     from objectdetection_ssd_b200.head import MultiboxHead, PackedGT
     lib = _lib.load()
-    pri = PR.make_priors()
+    pri = prior_table("ssd300")
     P = pri.shape[0]
     head = MultiboxHead(pri, dev)
     gb, gc = synth.make_gt(1 + rank, B)
@@ -488,7 +679,7 @@ def time_train_levels(rank, dev, B=256, steps=200):
     def step(i):
         return lib.ssdhead_multibox_step_levels(
             ctypes.addressof(structs[i % nset]), gt.boxes.data_ptr(), gt.classes.data_ptr(), gt.off.data_ptr(),
-            head.pri_xyxy.data_ptr(), head.pri_cxcywh.data_ptr(), B, P, 21, gt.sumG, 3, 0.5, sums.data_ptr(), losses.data_ptr(),
+            head.pri_xyxy.data_ptr(), head.pri_cxcywh.data_ptr(), B, P, C, gt.sumG, 3, 0.5, sums.data_ptr(), losses.data_ptr(),
             m["cls_u8"].data_ptr(), m["best_prior"].data_ptr(), m["npos"].data_ptr(),
             ws.data_ptr(), ws.numel(), wm.data_ptr(), wm.numel(), st)
 
@@ -512,6 +703,45 @@ def time_train_levels(rank, dev, B=256, steps=200):
     return dict(ms_step=timeit(step), ms_cat=timeit(cat), losses=losses.tolist())
 
 
+def time_dropin(dev, B, steps=100, host_lists=False):
+    """The call a user of the reference makes (train_function.py:82-94): ``Losses.ssd((loc, conf), classes, bboxes)``
+    with ragged gt LISTS and autograd-tracked outputs, then ``(loss1 + loss2).backward()`` - gt packing, output
+    allocation, the autograd node and the gradient hand-over included.  Device-timed (CUDA events) and wall-clock
+    (the Python surface can be launch-bound)."""
+    from objectdetection_ssd_b200 import Losses, synth
+    pri = prior_table("ssd300")
+    P = pri.shape[0]
+    gb, gc = synth.make_gt(1, B)
+    loc, conf = synth.make_head(1, B, P)
+    to = (lambda a: torch.from_numpy(a)) if host_lists else (lambda a: torch.from_numpy(a).to(dev))
+    classes, bboxes = [to(c) for c in gc], [to(b) for b in gb]
+    nset = max(2, -(-2 * L2_BYTES // (B * P * 25 * 4)))
+    sets = [((torch.from_numpy(loc).to(dev) + 0.001 * i).requires_grad_(True),
+             (torch.from_numpy(conf).to(dev) + 0.001 * i).requires_grad_(True)) for i in range(nset)]
+    stream = torch.cuda.current_stream(dev)
+
+    def it(i):
+        l, c = sets[i % nset]
+        l.grad = None
+        c.grad = None
+        l1, l2 = Losses.ssd((l, c), classes, bboxes)
+        (l1 + l2).backward()
+        return l1, l2
+
+    for i in range(5):
+        l1, l2 = it(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(steps):
+        l1, l2 = it(i)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    return dict(ms_device=e0.elapsed_time(e1) / steps, ms_wall=wall, losses=[l1.item(), l2.item()])
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -526,94 +756,142 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     B = args.batch
-    if args.workload == "train":
-        r = time_train(args, rank, world, dev, sampler)
+    if args.workload == "detect":
+        r = time_detect(args, rank, world, dev, sampler, B, args.steps, args.warmup)
     else:
-        r = time_detect(args, rank, world, dev, sampler)
+        r = time_loss(args, rank, world, dev, sampler, args.workload, B, args.steps, args.warmup)
+        args.collective = r["collective"] if world > 1 else args.collective       # what actually ran
     clocks = sampler.stop()
     ms_step = r["ms_total"] / args.steps
     value = B * world / (ms_step * 1e-3)
     e2e_val = B * world / (r["e2e_ms"] * 1e-3)
     step_gbs = r["algo"] * B / (ms_step * 1e-3) / 1e9
+    is_loss = args.workload != "detect"
     line = {
-        "metric": "images/sec, SSD300 " + ("match + multibox loss fwd+bwd" if args.workload == "train"
-                                           else "decode + NMS (conf 0.01, top-200)"),
+        "metric": metric_name(args.workload),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
                 "ms_per_step": r["e2e_ms"], "steps": r["e2e_steps"],
-                "api": "ssdhead_ctx_multibox_loss_host" if args.workload == "train" else "ssdhead_ctx_detect_host",
-                "note": ("pinned host buffers in; losses + dense gradient tensors in the caller's host buffers: conf is copied, "
-                         "loc is read in place (positive rows only), the gradients' zero background is written by host threads "
-                         "while the inputs stream in and the mining kernel stores its ~4 Npos rows straight into the host buffers"
-                         if args.workload == "train" else
-                         "pinned host buffers in, detections back to host: conf is copied, loc is read in place (visited candidates only)")
-                        + "; per-rank call" + (", local normalisation" if world > 1 and args.workload == "train" else "")},
+                "api": "ssdhead_ctx_multibox_loss_host_sparse" if is_loss else "ssdhead_ctx_detect_host",
+                "check": r.get("e2e_check"),
+                "note": ("pinned host buffers in; losses + the gradient ROWS (positives and mined negatives: the only rows "
+                         "of the dense gradient that are not zero) back in pinned host buffers: conf is copied, loc is read in "
+                         "place (positive rows only), the mining kernel stores its ~4 Npos rows per image straight into the "
+                         "host row buffers; "
+                         + ("the ranks call in lock step and the loss is the SHARDED one (global normalisation through the "
+                            "peer exchange)" if r.get("e2e_sharded") else
+                            ("per-rank call" + (", local normalisation (NCCL route: no exchange inside the C call)" if world > 1 else "")))
+                         if is_loss else
+                         "pinned host buffers in, detections back to host: conf is copied, loc is read in place (visited "
+                         "candidates only); per-rank call, no collective")},
         "gpu_launches": int(r["launches"]),
         "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "algorithmic_bytes_per_image": r["algo"], "peak_source": peak_src,
                           "note": "whole step (all kernels of the step) against SURVEY.md 8(d) bytes/image"},
     }
+    if is_loss and "e2e_dense_ms" in r:
+        line["e2e"]["dense_gradient_tensors"] = {
+            "api": "ssdhead_ctx_multibox_loss_host", "value": B * world / (r["e2e_dense_ms"] * 1e-3), "ms_per_step": r["e2e_dense_ms"],
+            "note": "the caller's dense [B,P,*] gradient tensors in host memory: host threads zero them while the inputs "
+                    "stream in, the mining kernel stores its rows into them"}
     if r["kern_ms"] is not None:
         ach = r["kernel_bytes"] / (r["kern_ms"] * 1e-3) / 1e9
-        traffic = None
+        traffic, tnote = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
-            ent = tj.get(f"ce_stream_b{B}")
+            ent = tj.get(f"ce_stream_b{B}" if args.workload == "train" else f"ce_stream_{args.workload}_b{B}")
             if ent:
-                traffic = ent["dram_bytes_per_launch"]
+                if tj.get("source_hash") == source_hash():
+                    traffic = ent["dram_bytes_per_launch"]
+                else:
+                    tnote = ("profiles/traffic.json was captured from other kernel sources than this libssdhead.so "
+                             "(source hash differs): not quoted")
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                             "traffic": traffic, "kernel": r["kernel"], "kernel_us": r["kern_ms"] * 1e3,
                             "algorithmic_bytes_per_launch": r["kernel_bytes"], "peak_source": peak_src}
+        if tnote:
+            line["roofline"]["traffic_note"] = tnote
     else:
         line["roofline"] = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                             "traffic": None, "kernel": r["kernel"],
-                            "note": "whole step: the score kernel is issue-bound at ~22k candidates/image, the sweep kernel latency-bound (one CTA per image); see DESIGN.md",
-                            "peak_source": peak_src}
+                            "note": "whole step: algorithmic bytes of the step / step time", "peak_source": peak_src}
     if "losses" in r:
         line["loss"] = r["losses"]
+    if "sharded_check" in r:
+        line["sharded_check"] = r["sharded_check"]
+    if args.workload == "stress":
+        rd = time_detect(args, rank, world, dev, ClockSampler(local), B, max(5, min(args.steps, 50)), 3, workload="stress", e2e=False)
+        md = rd["ms_total"] / rd["steps"]
+        line["stress_detect"] = {"workload": "decode + conf 0.01 threshold + per-class NMS + top-200, 24 564 priors, bias +6",
+                                 "images_per_s": B * world / (md * 1e-3), "ms_per_step": md,
+                                 "step_roofline_frac": rd["algo"] * B / (md * 1e-3) / 1e9 / peak}
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.workload)
         if args.workload == "train" and not args.no_others:
-            # the other single-GPU configurations of BASELINE.json, short runs, for the record
-            others = []
-            for b2 in (32,):
-                a2 = argparse.Namespace(**vars(args))
-                a2.batch, a2.steps, a2.warmup = b2, 200, 10
-                s2 = ClockSampler(local)
-                r2 = time_train(a2, rank, world, dev, s2)
-                m2 = r2["ms_total"] / a2.steps
-                others.append({"workload": f"train head, batch {b2} (configs[1])", "images_per_s": b2 / (m2 * 1e-3),
-                               "ms_per_step": m2, "step_roofline_frac": ALGO_BYTES['train'] * b2 / (m2 * 1e-3) / 1e9 / peak,
-                               "e2e_images_per_s": b2 / (r2["e2e_ms"] * 1e-3)})
-            a3 = argparse.Namespace(**vars(args))
-            a3.workload, a3.batch = "detect", 64
-            r3 = time_detect(a3, rank, world, dev, ClockSampler(local), steps=20, warmup=3)
-            m3 = r3["ms_total"] / 20
-            others.append({"workload": "detect, batch 64, bias +6 (configs[2])", "images_per_s": 64 / (m3 * 1e-3),
-                           "ms_per_step": m3, "step_roofline_frac": ALGO_BYTES['detect'] * 64 / (m3 * 1e-3) / 1e9 / peak,
-                           "e2e_images_per_s": 64 / (r3["e2e_ms"] * 1e-3)})
-            r4 = time_train_levels(rank, dev)
-            others.append({"workload": "train head, batch 256, from the 6 per-level tensors (ssdhead_multibox_step_levels, "
-                                       "SURVEY 8(f) #3; no concatenated tensor in either direction)",
-                           "images_per_s": 256 / (r4["ms_step"] * 1e-3), "ms_per_step": r4["ms_step"],
-                           "step_roofline_frac": ALGO_BYTES['train'] * 256 / (r4["ms_step"] * 1e-3) / 1e9 / peak,
-                           "torch_cat_of_the_levels_ms": r4["ms_cat"],
-                           "note": "the concatenated layout pays value's step PLUS torch_cat_of_the_levels_ms (Model.py:234-235) "
-                                   "and the same again in backward"})
-            line["others"] = others
+            line["others"] = others(args, rank, dev, local, peak)
     elif rank == 0:
         line["cpu_baseline"] = None
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    if "sharded_check" in r and not r["sharded_check"]["ok"]:
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        raise SystemExit("bench.py: sharded_check FAILED - the sharded step does not reproduce the single-GPU step")
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def others(args, rank, dev, local, peak):
+    """The other single-GPU configurations of BASELINE.json and the reference-facing Python surface, short runs."""
+    out = []
+    a2 = argparse.Namespace(**vars(args))
+    r2 = time_loss(a2, rank, 1, dev, ClockSampler(local), "train", 32, 200, 10, kernel_alone=False)
+    m2 = r2["ms_total"] / 200
+    out.append({"workload": "train head, batch 32 (configs[1])", "images_per_s": 32 / (m2 * 1e-3),
+                "ms_per_step": m2, "step_roofline_frac": r2["algo"] * 32 / (m2 * 1e-3) / 1e9 / peak,
+                "e2e_images_per_s": 32 / (r2["e2e_ms"] * 1e-3)})
+    for b3, n3 in ((64, 100), (256, 50)):
+        r3 = time_detect(args, rank, 1, dev, ClockSampler(local), b3, n3, 5)
+        m3 = r3["ms_total"] / n3
+        out.append({"workload": f"detect, batch {b3}, bias +6 (configs[2]" + (")" if b3 == 64 else ", north_star size)"),
+                    "images_per_s": b3 / (m3 * 1e-3), "ms_per_step": m3,
+                    "step_roofline_frac": r3["algo"] * b3 / (m3 * 1e-3) / 1e9 / peak,
+                    "e2e_images_per_s": b3 / (r3["e2e_ms"] * 1e-3), "gpu_launches_per_step": r3["launches"] / n3})
+    r4 = time_train_levels(rank, dev)
+    out.append({"workload": "train head, batch 256, from the 6 per-level tensors (ssdhead_multibox_step_levels, "
+                            "SURVEY 8(f) #3; no concatenated tensor in either direction)",
+                "images_per_s": 256 / (r4["ms_step"] * 1e-3), "ms_per_step": r4["ms_step"],
+                "step_roofline_frac": algo_bytes(8732, "train") * 256 / (r4["ms_step"] * 1e-3) / 1e9 / peak,
+                "torch_cat_of_the_levels_ms": r4["ms_cat"],
+                "note": "the concatenated layout pays value's step PLUS torch_cat_of_the_levels_ms (Model.py:234-235) "
+                        "and the same again in backward"})
+    for b5, host in ((256, False), (256, True), (32, False)):
+        r5 = time_dropin(dev, b5, steps=100, host_lists=host)
+        out.append({"workload": f"drop-in surface: Losses.ssd((loc, conf), classes, bboxes) + (l1 + l2).backward(), batch {b5}, "
+                                f"{'host' if host else 'device'} gt lists (train_function.py:62-63,82-94)",
+                    "images_per_s": b5 / (max(r5["ms_device"], r5["ms_wall"]) * 1e-3), "ms_per_step_device": r5["ms_device"],
+                    "ms_per_step_wall": r5["ms_wall"],
+                    "note": "includes gt packing + upload, output allocation, the autograd node and scale_grads"})
+    a6 = argparse.Namespace(**vars(args))
+    a6.workload = "stress"
+    r6 = time_loss(a6, rank, 1, dev, ClockSampler(local), "stress", 128, 30, 3, kernel_alone=False, e2e=False)
+    m6 = r6["ms_total"] / 30
+    r7 = time_detect(a6, rank, 1, dev, ClockSampler(local), 128, 30, 3, workload="stress", e2e=False)
+    m7 = r7["ms_total"] / 30
+    out.append({"workload": "stress (configs[4]): 24 564 priors, 100 gt/image, batch 128: match + loss fwd+bwd",
+                "images_per_s": 128 / (m6 * 1e-3), "ms_per_step": m6,
+                "step_roofline_frac": r6["algo"] * 128 / (m6 * 1e-3) / 1e9 / peak})
+    out.append({"workload": "stress (configs[4]): 24 564 priors, batch 128: decode + NMS",
+                "images_per_s": 128 / (m7 * 1e-3), "ms_per_step": m7,
+                "step_roofline_frac": r7["algo"] * 128 / (m7 * 1e-3) / 1e9 / peak})
+    return out
 
 
 def main():
@@ -622,8 +900,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "detect"])
-    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 256 train, 64 detect)")
+    ap.add_argument("--workload", default="train", choices=["train", "detect", "stress"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 256 train, 64 detect, 128 stress)")
     ap.add_argument("--no-others", action="store_true", help="skip the short secondary-configuration runs")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how Npos and the loss sums cross GPUs - 'peer' = stores into peer memory over NVLink "
@@ -631,7 +909,9 @@ def main():
                          "around the mining kernel (3 kernels/step)")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 256 if args.workload == "train" else 64
+        args.batch = WORKLOADS[args.workload][1]
+    if args.workload == "stress" and args.steps == 2000:
+        args.steps = 200
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -42,6 +42,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the kernel sources, the shared headers and the compile flags: identifies what
+    a libssdhead.so was built from.  profiles/traffic.json records it next to the ncu numbers, and bench.py quotes
+    those numbers only for a library built from the same sources."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(PKG_DIR), "include", "ssdhead.h")]
+    for path in deps:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
