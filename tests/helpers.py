@@ -32,3 +32,56 @@ def unpack_mask(mask_i32: torch.Tensor, P: int) -> torch.Tensor:
     m = mask_i32.cpu().numpy().view(np.uint32)
     bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(bool)
     return torch.from_numpy(bits.reshape(m.shape[0], -1)[:, :P])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Boundary proof for the FUSED detect path (own softmax / decode on the device).  CUDA's ex2.approx / expf and ATen's
+# exp differ in the last bits, so a detection may differ from the oracle's - but only for a reason:
+#   (a) its OWN probability is within PROB_ULP ulp of `min_score` (the candidate itself flips; it ranks last in its
+#       class, so nothing else can change because of it);
+#   (b) its class holds a candidate pair whose IoU is within IOU_REL of the NMS threshold (a suppression flips, and the
+#       greedy sweep of THAT class may cascade);
+#   (c) more than top_k survive and it sits at the global cut: its probability is within PROB_ULP ulp of the k-th
+#       largest, or it is at / below the cut while some class has a (b) event (one more or one fewer box kept above
+#       moves the cut).
+# A difference without such an event is a genuine error.  Stated tolerances: the streaming softmax uses
+# ex2.approx.ftz, relative error <= (2 + 1.16 |x - max|) ulp per term (csrc/common.cuh), i.e. <= 16 ulp on a
+# probability at |x - max| <= 10; decoded boxes differ by a few ulp (expf), their IoU by < 1e-5 relative.
+PROB_ULP = 16
+IOU_REL = 1e-5
+
+
+def _ulps(a: float, b: float) -> float:
+    import math
+    m = max(abs(a), abs(b), 1e-30)
+    return abs(a - b) / (2.0 ** (math.floor(math.log2(m)) - 23))
+
+
+def explain_detect_mismatches(loc_i, conf_i, pri, min_score, iou_thr, top_k, ours, ref):
+    """``ours`` / ``ref``: sets of (class, prior) detections of one image.  Returns (n_mismatches, unexplained list)."""
+    import torch.nn.functional as F
+    diff = (ours - ref) | (ref - ours)
+    if not diff:
+        return 0, []
+    probs = F.softmax(conf_i, dim=1)
+    boxes = O.cxcywh_to_xyxy(O.decode(loc_i, pri))
+    iou_fragile = set()
+    for c in {c for c, _ in diff}:
+        cand = torch.nonzero(probs[:, c] >= min_score * (1 - 1e-5)).flatten()
+        if cand.numel() > 1:
+            iou = O.iou_matrix(boxes[cand], boxes[cand])
+            iou.fill_diagonal_(0)
+            if bool(((iou - iou_thr).abs() <= IOU_REL * iou_thr).any()):
+                iou_fragile.add(c)
+    cut = None
+    if len(ref) >= top_k or len(ours) >= top_k:
+        ps = sorted((float(probs[p, c]) for c, p in ref), reverse=True)
+        cut = ps[min(len(ps), top_k) - 1]                       # k-th largest probability the oracle reported
+    unexplained = []
+    for c, p in diff:
+        pr = float(probs[p, c])
+        own = _ulps(pr, min_score) <= PROB_ULP
+        at_cut = cut is not None and (_ulps(pr, cut) <= PROB_ULP or (iou_fragile and pr <= cut * (1 + 1e-5)))
+        if not (own or c in iou_fragile or at_cut):
+            unexplained.append((c, p))
+    return len(diff), unexplained

@@ -82,14 +82,22 @@ def test_losses_inference_surface(monkeypatch):
     monkeypatch.setattr(Losses, "_image_size", lambda phase, index: (500, 375))
     for i in range(2):
         boxes, cls, prob = Losses.inference(loc[i].cuda(), conf[i].cuda(), 0, toDraw=False, min_score=0.01)
-        rb, rc, rp, _ = O.detect_image(loc[i], conf[i], pri, 0.01, 0.45, 200)
-        assert boxes.shape == (rb.shape[0], 4) and cls.dtype == torch.int64
+        rb, rc, rp, ri = O.detect_image(loc[i], conf[i], pri, 0.01, 0.45, 200)
+        assert boxes.shape[1] == 4 and cls.dtype == torch.int64
         scale = torch.tensor([500., 375., 500., 375.])
-        hit = (cls.cpu()[:, None] == rc[None, :]) & ((prob.cpu()[:, None] - rp[None, :]).abs() < 1e-6)
-        assert hit.any(1).float().mean() > 0.98
+        # pair detections by (class, probability): every record of ours has its counterpart in the oracle's output with
+        # the same box, or sits at a boundary (explained below through the prior ids of the batched front end)
+        hit = (cls.cpu()[:, None] == rc[None, :]) & ((prob.cpu()[:, None] - rp[None, :]).abs() <= 1e-5 * rp[None, :])
         j = hit.float().argmax(1)
         ok = hit.any(1)
         assert torch.allclose(boxes.cpu()[ok], (rb * scale)[j[ok]], rtol=1e-5, atol=1e-3)
+        det = Losses.inference_batch(loc[i:i + 1].cuda(), conf[i:i + 1].cuda(), top_k=200, min_score=0.01)
+        k = int(det["cnt"][0])
+        ours = {(int(c), int(p)) for c, p in zip(det["cls"][0, :k].cpu(), det["prior"][0, :k].cpu())}
+        ref = {(int(c), int(p)) for c, p in zip(rc, ri)}
+        assert k == boxes.shape[0] and int((~ok).sum()) <= len(ours ^ ref)
+        n, unexplained = H.explain_detect_mismatches(loc[i], conf[i], pri, 0.01, 0.45, 200, ours, ref)
+        assert not unexplained, f"image {i}: {unexplained[:5]} of {n} differing detections have no boundary proof"
     # nothing above the threshold -> three empty lists (Losses.py:62-63)
     conf0 = torch.zeros(pri.shape[0], 21)
     conf0[:, 20] = 30.0
