@@ -39,8 +39,8 @@ def unpack_mask(mask_i32: torch.Tensor, P: int) -> torch.Tensor:
 # exp differ in the last bits, so a detection may differ from the oracle's - but only for a reason:
 #   (a) its OWN probability is within PROB_ULP ulp of `min_score` (the candidate itself flips; it ranks last in its
 #       class, so nothing else can change because of it);
-#   (b) its class holds a candidate pair whose IoU is within IOU_REL of the NMS threshold (a suppression flips, and the
-#       greedy sweep of THAT class may cascade);
+#   (b) its class holds a pair (box kept by either side, candidate) whose IoU is within IOU_REL of the NMS threshold (a
+#       suppression flips, and the greedy sweep of THAT class may cascade);
 #   (c) more than top_k survive and it sits at the global cut: its probability is within PROB_ULP ulp of the k-th
 #       largest, or it is at / below the cut while some class has a (b) event (one more or one fewer box kept above
 #       moves the cut).
@@ -67,10 +67,12 @@ def explain_detect_mismatches(loc_i, conf_i, pri, min_score, iou_thr, top_k, our
     boxes = O.cxcywh_to_xyxy(O.decode(loc_i, pri))
     iou_fragile = set()
     for c in {c for c, _ in diff}:
+        # only a box that one of the two sides KEPT can suppress anything: pairs (kept box, any candidate of the class)
         cand = torch.nonzero(probs[:, c] >= min_score * (1 - 1e-5)).flatten()
-        if cand.numel() > 1:
-            iou = O.iou_matrix(boxes[cand], boxes[cand])
-            iou.fill_diagonal_(0)
+        kept = torch.tensor(sorted({p for cc, p in (ours | ref) if cc == c}), dtype=torch.long)
+        if cand.numel() > 0 and kept.numel() > 0:
+            iou = O.iou_matrix(boxes[kept], boxes[cand])
+            iou[kept[:, None] == cand[None, :]] = 0
             if bool(((iou - iou_thr).abs() <= IOU_REL * iou_thr).any()):
                 iou_fragile.add(c)
     cut = None
