@@ -61,8 +61,8 @@ def ssd(outputs, tr_classes, tr_bboxs):
     loc, conf = outputs
     head = _head(_dev_of(loc))
     _last.clear()
-    _last.update(head=head, boxes=[b.detach() for b in tr_bboxs], classes=[c.detach() for c in tr_classes])
-    return multibox_loss(head, loc, conf, list(tr_bboxs), list(tr_classes), group=process_group)
+    _last.update(head=head, boxes=tr_bboxs, classes=tr_classes)     # for the obj_forEach_prior___ tap, built on demand
+    return multibox_loss(head, loc, conf, tr_bboxs, tr_classes, group=process_group)
 
 
 def ssd1_(pred_bb_offset, pred_class_score, tr_bbox, tr_class, jaccard=None, indices=None):
@@ -109,8 +109,8 @@ def ssd_levels(outputs, tr_classes, tr_bboxs):
     locs, confs = outputs
     head = _head(_dev_of(confs[0]))
     _last.clear()
-    _last.update(head=head, boxes=[b.detach() for b in tr_bboxs], classes=[c.detach() for c in tr_classes])
-    return multibox_loss_levels(head, list(locs), list(confs), list(tr_bboxs), list(tr_classes))
+    _last.update(head=head, boxes=tr_bboxs, classes=tr_classes)
+    return multibox_loss_levels(head, list(locs), list(confs), tr_bboxs, tr_classes)
 
 
 def inference_batch_levels(loc_levels, conf_levels, top_k=200, min_score=0.2, iou_threshold=0.45, img_wh=None,
@@ -162,6 +162,7 @@ def __getattr__(name):
         if not _last:
             raise AttributeError("obj_forEach_prior___ is only defined after a call to ssd()")
         head = _last["head"]
-        m = head.match(PackedGT(_last["boxes"], _last["classes"], head.dev), want_maps=True)
+        m = head.match(PackedGT([b.detach() for b in _last["boxes"]], [c.detach() for c in _last["classes"]], head.dev),
+                       want_maps=True)
         return m["cls"].to(torch.float32)
     return getattr(_U, name)

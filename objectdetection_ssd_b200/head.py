@@ -12,6 +12,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -45,36 +46,48 @@ _staging_pool = None     # pinned.StagingPool, created with the first host-list 
 
 class PackedGT:
     """Ragged gt lists packed once: boxes [sumG,4] f32, classes [sumG] f32, offsets int32 [B+1]
-    (host-side equivalent of Losses.py:129-130; no per-image synchronisation)."""
+    (host-side equivalent of Losses.py:129-130; no per-image synchronisation).
+
+    This sits on the per-step path of ``ssd()`` (train_function.py:62-63,82), so the per-image Python work is kept to
+    one shape read: the lists are concatenated by ONE ``torch.cat`` each - for host lists straight into a recycled
+    page-locked block that then crosses to the device in one copy, offsets included."""
 
     def __init__(self, boxes: Sequence[torch.Tensor], classes: Sequence[torch.Tensor], dev: torch.device):
-        counts = [int(b.shape[0]) if b.dim() > 0 else 0 for b in boxes]
-        for i, n in enumerate(counts):
-            if n == 0:
-                # the reference fails the same way on an image without objects (Losses.py:153, max over an empty dim)
-                raise IndexError(f"image {i} has no ground-truth box: max() over an empty dimension")
+        try:
+            counts = [b.shape[0] for b in boxes]
+        except IndexError:                       # a 0-dim entry: no box
+            counts = [b.shape[0] if b.dim() > 0 else 0 for b in boxes]
+        if 0 in counts:
+            # the reference fails the same way on an image without objects (Losses.py:153, max over an empty dim)
+            raise IndexError(f"image {counts.index(0)} has no ground-truth box: max() over an empty dimension")
         self.B = len(counts)
-        self.sumG = sum(counts)
+        if len(classes) != self.B:
+            raise ValueError(f"{self.B} box lists but {len(classes)} class lists")
+        offs = np.zeros(self.B + 1, dtype=np.int32)
+        if self.B:
+            np.cumsum(counts, out=offs[1:])
+        self._off_np = offs
+        self.sumG = int(offs[-1])
         self.maxG = max(counts) if counts else 0
-        off = [0]
-        for n in counts:
-            off.append(off[-1] + n)
-        self.off_host = off
-        on_host = all(b.device.type == "cpu" for b in boxes) and all(c.device.type == "cpu" for c in classes)
-        if on_host and torch.cuda.is_available():
+        cuda = torch.cuda.is_available()
+        b0, c0 = (boxes[0], classes[0]) if self.B else (None, None)
+        if cuda and self.B and b0.device.type == "cpu" and c0.device.type == "cpu":
+            # host lists (what a DataLoader hands over): concatenated straight into a recycled page-locked block (no
+            # cudaHostAlloc / cudaFreeHost per step), ONE copy of the block to the device; the block returns to the pool
+            # behind an event recorded after the copy, so it is never rewritten while the DMA engine may still read it
             global _staging_pool
             if _staging_pool is None:
                 from .pinned import StagingPool
                 _staging_pool = StagingPool()
-            # host lists (what a DataLoader hands over): one native pass into a recycled page-locked block, ONE copy of
-            # the block to the device.  No cudaHostAlloc / cudaFreeHost per step; the block returns to the pool behind
-            # an event recorded after the copy, so it is never rewritten while the DMA engine may still read it.
-            from .collate import collate_gt
             from .pinned import gt_layout
             st = _staging_pool.acquire(self.sumG, self.B)
-            collate_gt(boxes, classes, out=st)
+            try:
+                self._fill_staging(st, boxes, classes)
+            except Exception:
+                _staging_pool.release(st, st.event)
+                raise
             blk = torch.empty(st.nbytes, dtype=torch.uint8, device=dev)
-            blk.copy_(torch.from_numpy(st.raw), non_blocking=True)
+            blk.copy_(st.raw_t, non_blocking=True)
             if st.event is None:
                 st.event = torch.cuda.Event()
             st.event.record(torch.cuda.current_stream(dev))
@@ -84,10 +97,40 @@ class PackedGT:
             self.classes = blk[o1:o1 + self.sumG * 4].view(torch.float32)
             self.off = blk[o2:o2 + (self.B + 1) * 4].view(torch.int32)
             return
-        self.boxes = torch.cat([b.reshape(-1, 4) for b in boxes]).to(device=dev, dtype=torch.float32).contiguous()
-        self.classes = torch.cat([c.reshape(-1) for c in classes]).to(device=dev, dtype=torch.float32).contiguous()
-        self.off = torch.tensor(off, dtype=torch.int32).pin_memory().to(dev, non_blocking=True) \
-            if torch.cuda.is_available() else torch.tensor(off, dtype=torch.int32)
+        self.boxes = self._cat(boxes, 4).to(device=dev, dtype=torch.float32)
+        self.classes = self._cat(classes, 0).to(device=dev, dtype=torch.float32)
+        if self.boxes.shape[0] != self.sumG or self.classes.shape[0] != self.sumG:
+            raise ValueError(f"gt lists disagree: {self.boxes.shape[0]} boxes, {self.classes.shape[0]} classes, {self.sumG} expected")
+        self.off = torch.from_numpy(offs).pin_memory().to(dev, non_blocking=True) if cuda else torch.from_numpy(offs)
+
+    @staticmethod
+    def _cat(tensors, width):
+        """One concatenation; tensors of unexpected rank (e.g. a single box given as [4]) are reshaped first."""
+        want = 2 if width else 1
+        if all(t.dim() == want for t in tensors[:1]):
+            try:
+                return torch.cat(list(tensors))
+            except RuntimeError:
+                pass
+        return torch.cat([t.reshape(-1, width) if width else t.reshape(-1) for t in tensors])
+
+    @property
+    def off_host(self):
+        """Offsets as a Python list (tests, debug taps)."""
+        return self._off_np.tolist()
+
+    def _fill_staging(self, st, boxes, classes):
+        if getattr(st, "boxes_t", None) is None:                    # torch views of the pinned arrays, made once per block
+            st.boxes_t = torch.from_numpy(st.boxes)
+            st.classes_t = torch.from_numpy(st.classes)
+            st.offsets_t = torch.from_numpy(st.offsets)
+            st.raw_t = torch.from_numpy(st.raw)
+        n = self.sumG
+        # one concatenation per list, then one small copy into the block (copy_ converts int64 class ids and checks the
+        # shapes: [n,4] boxes, [n] classes)
+        st.boxes_t[:n].copy_(self._cat(boxes, 4))
+        st.classes_t[:n].copy_(self._cat(classes, 0))
+        st.offsets[:] = self._off_np
 
 
 class MultiboxHead:
@@ -102,10 +145,17 @@ class MultiboxHead:
         self.pri_cxcywh = pc.to(self.dev)
         self.pri_xyxy = cxcywh_to_xyxy_host(pc).to(self.dev)     # same fp32 ops as Util.py:93-96
         self._ws = {}
+        self._ws_need = {}
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, which: int, B: int, n: int) -> torch.Tensor:
-        need = int(self.lib.ssdhead_workspace_bytes(which, B, self.P, self.C, n))
+        # sized for n rounded up to a multiple of 1024 (the gt count changes every training step; a larger buffer is
+        # always accepted), so the size query leaves the per-step path
+        nq = (n + 1023) // 1024 * 1024 if n > 0 else 0
+        need = self._ws_need.get((which, B, nq))
+        if need is None:
+            need = int(self.lib.ssdhead_workspace_bytes(which, B, self.P, self.C, nq))
+            self._ws_need[(which, B, nq)] = need
         if need == 0:
             raise RuntimeError("ssdhead: unsupported shape for this entry point "
                                f"(B={B}, P={self.P}, C={self.C})")
@@ -121,6 +171,12 @@ class MultiboxHead:
             cur.zero_()
         self._ws[which] = (cur, key)
         return cur
+
+    def _dense_f32(self, t: torch.Tensor) -> torch.Tensor:
+        """fp32, dense, on this device - without a torch call in the common case."""
+        if t.dtype == torch.float32 and t.device == self.dev and t.is_contiguous():
+            return t
+        return t.detach().to(device=self.dev, dtype=torch.float32).contiguous()
 
     # ------------------------------------------------------------------ match
     def _match_outputs(self, gt: PackedGT, want_maps: bool):
@@ -158,8 +214,8 @@ class MultiboxHead:
         if tuple(loc.shape) != (B, P, 4) or tuple(conf.shape) != (B, P, C) or gt.B != B:
             raise ValueError(f"expected loc [B,{P},4] and conf [B,{P},{C}] with B gt lists, got "
                              f"{tuple(loc.shape)}, {tuple(conf.shape)}, {gt.B}")
-        loc = loc.detach().to(device=self.dev, dtype=torch.float32).contiguous()
-        conf = conf.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        loc = self._dense_f32(loc)
+        conf = self._dense_f32(conf)
         sums = torch.empty(2, dtype=torch.float64, device=self.dev)
         losses = torch.empty(2, dtype=torch.float32, device=self.dev)
         grad_loc = grad_conf = mined = ce = None
@@ -289,6 +345,18 @@ class MultiboxHead:
                    "ssdhead_scale_grads")
 
 
+def _upstream(head, g_loc_loss, g_conf_loss) -> torch.Tensor:
+    """The two upstream gradients as one fp32 [2] device tensor (read by the scale kernel on the device: no sync)."""
+    if g_loc_loss is None or g_conf_loss is None:
+        z = torch.zeros((), dtype=torch.float32, device=head.dev)
+        g_loc_loss = z if g_loc_loss is None else g_loc_loss
+        g_conf_loss = z if g_conf_loss is None else g_conf_loss
+    gout = torch.stack((g_loc_loss.reshape(()), g_conf_loss.reshape(())))
+    if gout.dtype != torch.float32 or gout.device != head.dev:
+        gout = gout.to(head.dev, torch.float32)
+    return gout
+
+
 class _MultiboxLossFn(torch.autograd.Function):
     """Autograd node for ``ssd()``: the forward kernel already wrote the gradients for unit upstream
     gradients; backward rescales them on the device only if the upstream gradients are not 1."""
@@ -312,11 +380,10 @@ class _MultiboxLossFn(torch.autograd.Function):
         gl, gc = ctx.grads
         ctx.grads = None
         head = ctx.head
-        z = torch.zeros((), dtype=torch.float32, device=head.dev)
-        gout = torch.stack([(g_loc_loss if g_loc_loss is not None else z).to(head.dev, torch.float32).reshape(()),
-                            (g_conf_loss if g_conf_loss is not None else z).to(head.dev, torch.float32).reshape(())])
-        head.scale_grads(gl, gc, gout)
+        head.scale_grads(gl, gc, _upstream(head, g_loc_loss, g_conf_loss))
         ld, cd, lt, ct = ctx.src
+        if ld == gl.device and lt == gl.dtype and cd == gc.device and ct == gc.dtype:
+            return gl, gc, None, None, None, None, None, None
         return gl.to(device=ld, dtype=lt), gc.to(device=cd, dtype=ct), None, None, None, None, None, None
 
 
@@ -390,9 +457,7 @@ class _MultiboxLossLevelsFn(torch.autograd.Function):
         gls, gcs = ctx.grads
         ctx.grads = None
         head = ctx.head
-        z = torch.zeros((), dtype=torch.float32, device=head.dev)
-        gout = torch.stack([(g_loc_loss if g_loc_loss is not None else z).to(head.dev, torch.float32).reshape(()),
-                            (g_conf_loss if g_conf_loss is not None else z).to(head.dev, torch.float32).reshape(())])
+        gout = _upstream(head, g_loc_loss, g_conf_loss)
         for gl, gc in zip(gls, gcs):
             head.scale_grads(gl, gc, gout)
         outs = [g.reshape(shape).to(device=dev, dtype=dt) for g, (shape, dev, dt) in zip(list(gls) + list(gcs), ctx.meta)]
