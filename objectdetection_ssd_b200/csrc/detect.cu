@@ -261,14 +261,15 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     const unsigned base = s_base;
     dir[((size_t)b * gridDim.x + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)h : (unsigned short)0;
     __syncthreads();
-    if (base == 0xffffffffu) return;
-    unsigned long long* seg = cand + (size_t)b * capI + base;
+    if (base != 0xffffffffu) {
+        unsigned long long* seg = cand + (size_t)b * capI + base;
 #pragma unroll 1
-    for (unsigned j = lane; j < wtotal; j += 32) {
-        const unsigned lq = st_q[j];
-        const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
-        const int rb = coarse_rank(__float_as_uint(pj));
-        seg[s_ch[rb] + atomicAdd(&s_fill[rb], 1u)] = make_key(pj, (int)(lq & 31u), r0 + warp * 32 + (int)(lq >> 5));
+        for (unsigned j = lane; j < wtotal; j += 32) {
+            const unsigned lq = st_q[j];
+            const float pj = wrow[(lq >> 5) * C + (lq & 31u)];
+            const int rb = coarse_rank(__float_as_uint(pj));
+            seg[s_ch[rb] + atomicAdd(&s_fill[rb], 1u)] = make_key(pj, (int)(lq & 31u), r0 + warp * 32 + (int)(lq >> 5));
+        }
     }
 }
 
@@ -600,23 +601,37 @@ __device__ __forceinline__ int nms_block(NmsBlock& s, const unsigned long long* 
     return K + __popcll(alive);
 }
 
+__device__ __forceinline__ int compact_kept(const unsigned long long* X, const float4* s_box, const unsigned char* s_keep, int cnt,
+                                            unsigned int* s_wsum, const Kept kp, int K);
+
 // Sweep of one sorted slice held in shared memory (keys X[0,cnt), boxes s_box[0,cnt), cnt <= SL).  Suppression only
-// acts inside a class, so the greedy NMS of a class (Losses.py:44-55) runs inside ONE warp, all classes side by side and
-// without a block-wide barrier: (1) a stable partition of the slice positions by class (match_any inside chunks of 32 +
-// per-class prefix sums over the chunks), (2) per class, 32 candidates at a time in lanes: tested against the boxes of
-// the class kept earlier (previous slices, previous rounds), then resolved in score order - only boxes that are still
-// alive are broadcast with shuffles, (3) the kept flags are compacted in slice (= global score) order onto the kept
-// list.  `scratch` is at least 16 KB of shared memory that is free during the sweep.  Returns the new kept count.
+// acts inside a class (Losses.py:44-55).  (1) A stable partition of the slice positions by class (match_any inside
+// chunks of 32 + per-class prefix sums over the chunks).  (2a) SPARSE sweep, the usual case: thread per candidate - it
+// is tested against the boxes of its class kept by earlier slices (a hit suppresses it for good) and against the
+// higher-scored candidates of its class in this slice; the ones it overlaps are only RECORDED (at most two), because
+// whether they suppress it depends on whether they are kept themselves (a suppressed box suppresses nobody).
+// Candidates without a recorded overlap are decided at once; the few others are resolved in score order by one
+// thread.  (2b) If some candidate overlaps more than two, the general sweep: the greedy NMS of a class inside ONE
+// warp, all classes side by side, 32 candidates at a time in lanes, tested against the boxes of the class kept earlier
+// (previous slices, previous rounds), then resolved in score order - only boxes that are still alive are broadcast
+// with shuffles.  Same decisions either way.  (3) The kept flags are compacted in slice (= global score) order onto
+// the kept list.  `scratch` is at least 16 KB of shared memory that is free during the sweep.  Returns the new kept count.
 __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, const float4* s_box, int cnt, int NF, unsigned char* scratch,
-                                    unsigned int* s_wsum, const Kept kp, int K, const IouThr q)
+                                    unsigned int* s_wsum, const Kept kp, int K, const IouThr q, bool sparse_ok)
 {
     constexpr int NW = NT / 32;
     constexpr int NFP = 32;                                    // row stride of the per-chunk class counts
+    constexpr int OV = 2;                                      // overlaps recorded per candidate by the sparse sweep
     unsigned short* s_order = reinterpret_cast<unsigned short*>(scratch);              // [SL] positions, grouped by class
-    unsigned char* s_keep = scratch + SL * 2;                                          // [SL]
-    unsigned short* s_cc = reinterpret_cast<unsigned short*>(scratch + SL * 3);        // [SL/32][NFP]
-    int* s_cstart = reinterpret_cast<int*>(scratch + SL * 3 + (SL / 32) * NFP * 2);    // [NFP + 1]
-    unsigned int* my_rows = reinterpret_cast<unsigned int*>(s_cstart + NFP + 4) + (threadIdx.x >> 5) * 32;   // [NW][32]
+    unsigned char* s_keep = scratch + SL * 2;                                          // [SL] bit 0 kept; bits 1-2 recorded overlaps
+    int* s_cstart = reinterpret_cast<int*>(scratch + SL * 3);                          // [NFP + 1] (+ padding to 256 bytes)
+    unsigned int* s_dep = reinterpret_cast<unsigned int*>(scratch + SL * 3 + 256);     // [SL/32] positions with recorded overlaps
+    unsigned char* un = scratch + SL * 3 + 256 + (SL / 32) * 4;
+    unsigned short* s_ov = reinterpret_cast<unsigned short*>(un);                      // [SL][OV]   sparse sweep; aliases the two below
+    unsigned short* s_cc = reinterpret_cast<unsigned short*>(un);                      // [SL/32][NFP] partition only
+    unsigned int* my_rows = reinterpret_cast<unsigned int*>(un + (SL / 32) * NFP * 2) + (threadIdx.x >> 5) * 32;   // [NW][32] general sweep
+    static_assert(SL * 3 + 256 + (SL / 32) * 4 + SL * OV * 2 <= SL * 8 && (NFP + 1) * 4 <= 256 &&
+                  (SL / 32) * NFP * 2 + NW * 32 * 4 <= SL * OV * 2, "sweep scratch layout");
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int nchunk = (cnt + 31) >> 5;
@@ -624,6 +639,7 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
 
     for (int i = t; i < nchunk * NFP; i += NT) s_cc[i] = 0;
     for (int i = t; i < cnt; i += NT) s_keep[i] = 0;
+    for (int i = t; i < SL / 32; i += NT) s_dep[i] = 0u;
     __syncthreads();
     for (int ch = warp; ch < nchunk; ch += NW) {
         const int i = ch * 32 + lane;
@@ -654,6 +670,60 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
     }
     __syncthreads();
     PHASE(9);
+
+    if (sparse_ok) {
+        bool dense = false;
+        for (int idx = t; idx < cnt; idx += NT) {              // idx: slot in the class-grouped order
+            const int pos = s_order[idx];
+            const int c = key_cls(X[pos]);
+            const int c0 = s_cstart[c];
+            const float4 bx = s_box[pos];
+            const float ar = box_area(bx);
+            bool sup = false;
+            const int kc0 = kp.cnt[c];
+            const unsigned short* il = kp.idx + (size_t)c * kp.cap;
+            for (int k = 0; k < kc0; ++k) {
+                const int id = il[k];
+                sup = sup || iou_ge_fast(kp.box[id], kp.area[id], bx, ar, q);
+            }
+            int nov = 0;
+            if (!sup) {
+                for (int k = c0; k < idx; ++k) {               // the higher-scored candidates of the class (positions ascending)
+                    const int pj = s_order[k];
+                    const float4 b2 = s_box[pj];
+                    if (iou_ge_fast(b2, box_area(b2), bx, ar, q)) {
+                        if (nov < OV) s_ov[pos * OV + nov] = (unsigned short)pj;
+                        ++nov;
+                    }
+                }
+            }
+            dense = dense || nov > OV;
+            s_keep[pos] = (unsigned char)(((!sup && nov == 0) ? 1 : 0) | (min(nov, OV) << 1));
+            if (!sup && nov > 0) atomicOr(&s_dep[pos >> 5], 1u << (pos & 31));
+        }
+        if (!__syncthreads_or(dense ? 1 : 0)) {
+            if (t == 0) {
+                for (int w = 0; w < nchunk; ++w) {
+                    unsigned m = s_dep[w];
+                    while (m) {                                // ascending position = descending score
+                        const int i = w * 32 + __ffs(m) - 1;
+                        m &= m - 1u;
+                        const int nov = s_keep[i] >> 1;
+                        bool kept = true;
+                        for (int o = 0; o < nov; ++o) kept = kept && !(s_keep[s_ov[i * OV + o]] & 1u);
+                        s_keep[i] = (unsigned char)((kept ? 1 : 0) | (nov << 1));
+                    }
+                }
+            }
+            __syncthreads();
+            PHASE(10);
+            const int Kn = compact_kept(X, s_box, s_keep, cnt, s_wsum, kp, K);
+            PHASE(11);
+            return Kn;
+        }
+        for (int i = t; i < cnt; i += NT) s_keep[i] = 0;       // dense overlaps: the general sweep decides everything
+        __syncthreads();
+    }
 
     for (int c = warp; c < NF; c += NW) {
         const int n_c = s_cstart[c + 1] - s_cstart[c];
@@ -708,15 +778,25 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
     __syncthreads();
     PHASE(10);
 
-    // kept flags -> kept list, in slice order
+    const int Kn = compact_kept(X, s_box, s_keep, cnt, s_wsum, kp, K);
+    PHASE(11);
+    return Kn;
+}
+
+// kept flags of a swept slice -> the kept list (boxes, areas, keys in slice = global score order, per-class index lists).
+// Returns the new kept count (entries past the list's capacity are counted, not stored: the caller stops at top_k + 1).
+__device__ __forceinline__ int compact_kept(const unsigned long long* X, const float4* s_box, const unsigned char* s_keep, int cnt,
+                                            unsigned int* s_wsum, const Kept kp, int K)
+{
+    const int t = threadIdx.x;
     const int per = (cnt + NT - 1) / NT;
     const int lo = min(cnt, t * per), hi = min(cnt, lo + per);
     unsigned local = 0u;
-    for (int i = lo; i < hi; ++i) local += s_keep[i];
+    for (int i = lo; i < hi; ++i) local += s_keep[i] & 1u;
     unsigned total;
     int g = K + (int)block_excl_scan(local, s_wsum, total);
     for (int i = lo; i < hi; ++i) {
-        if (!s_keep[i]) continue;
+        if (!(s_keep[i] & 1u)) continue;
         if (g < kp.cap) {
             const unsigned long long key = X[i];
             const float4 bx = s_box[i];
@@ -727,7 +807,6 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
         ++g;
     }
     __syncthreads();
-    PHASE(11);
     return K + (int)total;
 }
 
@@ -755,7 +834,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                   unsigned int* __restrict__ overflow,
-                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
@@ -788,7 +867,6 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t < CBINS) s_col[t] = 0u;
     if (t < 32) s_kcnt[t] = 0;
-    __syncthreads();
     pdl_wait();                                              // the score kernel's lists and directory are complete
     PHASE(0);
     const unsigned long long* seg = cand + (size_t)b * capI;
@@ -807,12 +885,12 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         unsigned sum = 0u;
 #pragma unroll 4
         for (int c = g; c < T; c += G) {
-            const unsigned short v = gdir[(size_t)c * CBINS + col];
+            const unsigned short v = ld_cg_u16(gdir + (size_t)c * CBINS + col);    // L2 loads: written by CTAs of a grid that may still run
             if (dir_cached) s_dir[c * CBINS + col] = v;
             sum += v;
         }
         if (g < G && sum) atomicAdd(&s_col[col], sum);
-        for (int c = t; c < T; c += NT) s_cbase[c] = dir_base[(size_t)b * T + c];
+        for (int c = t; c < T; c += NT) s_cbase[c] = (unsigned)ld_cg_s32(reinterpret_cast<const int*>(dir_base) + (size_t)b * T + c);
         __syncthreads();
         unsigned total;
         const unsigned c = t < CBINS ? s_col[t] : 0u;
@@ -869,7 +947,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         // where the slice sits in every chunk: chunks are ordered by rank bin, so it is one contiguous piece per chunk
         for (int c = warp; c < T; c += NT / 32) {
             const uint4 v = dir_cached ? *reinterpret_cast<const uint4*>(s_dir + c * CBINS + lane * 8)
-                                       : __ldg(reinterpret_cast<const uint4*>(gdir + (size_t)c * CBINS + lane * 8));
+                                       : ld_cg_v4(reinterpret_cast<const uint4*>(gdir + (size_t)c * CBINS + lane * 8));
             const unsigned w8[4] = {v.x, v.y, v.z, v.w};
             unsigned before = 0u, inside = 0u;
 #pragma unroll
@@ -910,7 +988,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [&](int pos, unsigned long long key) { s_box[pos] = load_box(key); });
             PHASE(3);
             PHASE(4);
-            K = sweep_slice_by_class(X, s_box, cnt, NF, reinterpret_cast<unsigned char*>(Y), ss.wsum, kp, K, make_iou_thr(iou_thr));
+            K = sweep_slice_by_class(X, s_box, cnt, NF, reinterpret_cast<unsigned char*>(Y), ss.wsum, kp, K, make_iou_thr(iou_thr), sparse_ok != 0);
         } else {
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [](int, unsigned long long) {});
             for (int base = 0; base < cnt && K <= top_k; base += 64)
@@ -951,7 +1029,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         }
     }
     if (t == 0) {
-        out_cnt[b] = overflow[b] ? -1 : nout;     // -1: the candidate list exceeded the caller's cap
+        out_cnt[b] = ld_cg_s32(reinterpret_cast<const int*>(overflow) + b) ? -1 : nout;     // -1: the candidate list exceeded the caller's cap
         overflow[b] = 0u;
         cand_cnt[b] = 0u;
     }
@@ -965,12 +1043,12 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                   unsigned int* __restrict__ overflow,
-                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
     detect_nms_body<FROM_SCORES, false>(nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                        img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+                                        img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
 __global__ void __launch_bounds__(NT, 2)
@@ -979,12 +1057,12 @@ detect_nms_levels_kernel(const __grid_constant__ DetLevels dl, const float4* __r
                          unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                          const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                          unsigned int* __restrict__ overflow,
-                         const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                         const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
                          float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                          int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
     detect_nms_body<false, true>(&dl, nullptr, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                 img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+                                 img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
 template <bool FROM_SCORES>
@@ -1009,6 +1087,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     const int capI = detect_cap_image(P, C, n_cap);
 
+    static const int sparse_ok = getenv("SSDHEAD_SWEEP_SPARSE") ? atoi(getenv("SSDHEAD_SWEEP_SPARSE")) : 1;
     dim3 g1(T, B);
     if (dl) {
         SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
@@ -1023,13 +1102,13 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_levels_kernel, dim3(B), dim3(NT), smem_nms, st,
                                   *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     } else {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
                                   (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     }
     count_launch();

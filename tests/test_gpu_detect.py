@@ -235,3 +235,50 @@ def test_detect_randomised_differential():
             _check_exact(out, ref, top_k)
         except AssertionError as e:
             raise AssertionError(f"trial {trial}: P={P} B={B} top_k={top_k} min_score={min_score} iou={iou_thr} ncls={ncls}: {e}")
+
+
+def test_detect_suppression_chains_and_sparse_overlaps():
+    """Hand-made chains inside one class and one slice: A suppresses B, B overlaps C but A does not -> C is KEPT
+    (a suppressed box suppresses nobody, Losses.py:44-55); a candidate overlapping two higher-scored boxes of which
+    only one survives; three mutually overlapping boxes (more recorded overlaps than the sparse sweep stores -> the
+    general sweep); the same geometry in another class must not interact.  Exact against the oracle."""
+    from objectdetection_ssd_b200.head import MultiboxHead, detect_from_scores
+    P = 64
+    g = torch.Generator().manual_seed(7)
+    boxes = torch.zeros(1, P, 4)
+    probs = torch.zeros(1, P, 21)
+    probs[..., 20] = 1.0
+
+    def put(i, cx, cy, w, h, cls, p):
+        boxes[0, i] = torch.tensor([cx, cy, w, h])
+        probs[0, i, cls] = p
+
+    # chain along x: each box overlaps its neighbour (IoU 0.6) but not the one after (IoU 0.33 < 0.45)
+    for k in range(6):
+        put(k, 0.20 + 0.05 * k, 0.2, 0.2, 0.2, 3, 0.9 - 0.05 * k)          # kept: 0, 2, 4  (1 suppressed by 0, 3 by 2, ...)
+    # the same chain in class 7, scores reversed
+    for k in range(6):
+        put(8 + k, 0.20 + 0.05 * k, 0.2, 0.2, 0.2, 7, 0.5 + 0.05 * k)
+    # a box overlapping two higher-scored boxes, one of which is itself suppressed
+    put(20, 0.60, 0.6, 0.2, 0.2, 5, 0.95)
+    put(21, 0.65, 0.6, 0.2, 0.2, 5, 0.90)       # suppressed by 20
+    put(22, 0.70, 0.6, 0.2, 0.2, 5, 0.85)       # overlaps 21 (suppressed) only -> kept
+    put(23, 0.74, 0.6, 0.2, 0.2, 5, 0.80)       # overlaps 21 (0.38: no), 22 (0.67) -> suppressed by 22
+    # four nearly identical boxes: every later one records three overlaps
+    for k in range(4):
+        put(30 + k, 0.3 + 0.002 * k, 0.7, 0.15, 0.15, 11, 0.7 - 0.01 * k)
+    # background clutter in other classes, random small boxes
+    for k in range(40, 64):
+        put(k, float(torch.rand(1, generator=g)), float(torch.rand(1, generator=g)), 0.05, 0.05, int(torch.randint(12, 20, (1,), generator=g)), 0.3)
+    pri = torch.cat([torch.rand(P, 2, generator=g), 0.1 + 0.2 * torch.rand(P, 2, generator=g)], 1)
+    head = MultiboxHead(pri, "cuda")
+    for top_k in (200, 5):
+        out = detect_from_scores(head, boxes, probs, 0.05, 0.45, top_k)
+        torch.cuda.synchronize()
+        ref = _oracle_stage(boxes, probs, 0.05, 0.45, top_k)
+        _check_exact(out, ref, top_k)
+    kept3 = sorted(int(i) for i, c in zip(ref[0][3], ref[0][1]) if int(c) == 3) if top_k == 200 else None
+    out = detect_from_scores(head, boxes, probs, 0.05, 0.45, 200)
+    ids = out["prior"][0, :int(out["cnt"][0])].cpu().tolist()
+    assert {0, 2, 4} <= set(ids) and not ({1, 3, 5} & set(ids)), ids
+    assert {20, 22} <= set(ids) and not ({21, 23} & set(ids)), ids
