@@ -87,3 +87,26 @@ def explain_detect_mismatches(loc_i, conf_i, pri, min_score, iou_thr, top_k, our
         if not (own or c in iou_fragile or at_cut):
             unexplained.append((c, p))
     return len(diff), unexplained
+
+
+def compare_detect_with_oracle(out, loc, conf, pri, min_score, iou_thr, top_k, images):
+    """The device path's detections (own softmax + decode) of ``images`` against the oracle's: common detections agree to
+    1e-5 in score and box, every differing detection needs a boundary proof (explain_detect_mismatches).  Returns the
+    number of (explained) differences."""
+    total = 0
+    for i in images:
+        rb, rc, rp, ri = O.detect_image(loc[i], conf[i], pri, min_score, iou_thr, top_k)
+        k = int(out["cnt"][i])
+        gp, gi = out["prob"][i, :k].cpu(), out["prior"][i, :k].cpu().long()
+        gc, gb = out["cls"][i, :k].cpu().long(), out["boxes"][i, :k].cpu()
+        ref = {(int(b), int(a)): j for j, (a, b) in enumerate(zip(ri, rc))}
+        ours = {(int(b), int(a)): j for j, (a, b) in enumerate(zip(gi, gc))}
+        common = sorted(set(ref) & set(ours))
+        j = torch.tensor([ours[c] for c in common], dtype=torch.long)
+        h = torch.tensor([ref[c] for c in common], dtype=torch.long)
+        assert torch.allclose(gp[j], rp[h], rtol=1e-5, atol=1e-8), f"image {i}: scores"
+        assert torch.allclose(gb[j], rb[h], rtol=1e-5, atol=1e-6), f"image {i}: boxes"
+        n, unexplained = explain_detect_mismatches(loc[i], conf[i], pri, min_score, iou_thr, top_k, set(ours), set(ref))
+        assert not unexplained, f"image {i}: {len(unexplained)} of {n} differing detections have no boundary proof: {unexplained[:5]}"
+        total += n
+    return total

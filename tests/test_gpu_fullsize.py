@@ -3,9 +3,10 @@
   configs[3]  SSD300 head, batch 256            match + loss fwd/bwd
   configs[2]  SSD300 detect, batch 64, bias +6  decode + NMS + top-200
   configs[4]  24 564 priors, 100 gt/image, batch 128   match + loss, decode + NMS (the configuration's stated size)
-Every image of every batch is covered by the properties; in addition a slice of each batch is compared with the oracle
-directly (the Python oracle needs seconds per image at these sizes): 3 of the 256 images of configs[3], 2 of 300, 2 of
-the 128 stress images, 2 of 64 / 2 of 256 / 1 of 128 images for detect.
+Every image of every batch is covered by the properties, AND every image is compared with the oracle: the whole
+256-image (300-image, 128-image stress) batch of the training head - class map, CE, mined sets with a rank-boundary
+proof, losses, every gradient row - and all 64 / 256 images of the detect batches (32 of the 128 stress images: the
+oracle's per-class NMS loop needs ~0.5 s per 24 564-prior image), differing detections only with a boundary proof.
 """
 import pytest
 import torch
@@ -83,10 +84,19 @@ def _loss_properties(pri, loc, conf, tb, tc, check_images):
     assert abs(out2["losses"][1].item() - out["losses"][1].item()) <= 1e-6 * out["losses"][1].item()
 
 
+def _whole_batch_vs_oracle(pri, loc, conf, tb, tc):
+    """every image of the batch against the oracle (the same checks the small-batch loss tests make)"""
+    from tests.test_gpu_loss import _check_loss
+    out, ref = _check_loss(pri, loc, conf, tb, tc)
+    assert torch.equal(out["cls_u8"].long().cpu(), ref["cls"]), "class map of every image"
+    assert torch.equal(out["npos"][:loc.shape[0]].long().cpu(), ref["npos"])
+
+
 def test_train_head_batch256_properties():
     pri = H.priors()
     loc, conf, tb, tc = H.train_inputs(71, 256, pri.shape[0])
     _loss_properties(pri, loc, conf, tb, tc, check_images=[0, 100, 255])
+    _whole_batch_vs_oracle(pri, loc, conf, tb, tc)
 
 
 def test_train_head_batch300_exceeds_coresident_grid():
@@ -95,20 +105,24 @@ def test_train_head_batch300_exceeds_coresident_grid():
     pri = H.priors()
     loc, conf, tb, tc = H.train_inputs(75, 300, pri.shape[0])
     _loss_properties(pri, loc, conf, tb, tc, check_images=[0, 299])
+    _whole_batch_vs_oracle(pri, loc, conf, tb, tc)
 
 
 def test_train_head_stress_24564_priors_100_gt():
     pri = H.priors("ssd512")
     loc, conf, tb, tc = H.train_inputs(72, 128, pri.shape[0], min_gt=100, max_gt=100)
     _loss_properties(pri, loc, conf, tb, tc, check_images=[0, 127])
+    _whole_batch_vs_oracle(pri, loc, conf, tb, tc)
 
 
-def _detect_properties(pri, loc, conf, min_score, top_k, check_images):
+def _detect_properties(pri, loc, conf, min_score, top_k, check_images, oracle_images=None):
     from objectdetection_ssd_b200.head import detect, detect_from_scores
     head = _head(pri)
     B, P = loc.shape[0], pri.shape[0]
     out = detect(head, loc, conf, min_score, 0.45, top_k)
     torch.cuda.synchronize()
+    n = H.compare_detect_with_oracle(out, loc, conf, pri, min_score, 0.45, top_k, range(B) if oracle_images is None else oracle_images)
+    print(f"detect B={B}: {n} detections differ from the oracle's, all with a boundary proof")
     cnt = out["cnt"].cpu()
     assert (cnt >= 0).all() and (cnt <= top_k).all()
     pxy = None
@@ -161,4 +175,4 @@ def test_detect_batch256_bias6_properties():
 def test_detect_stress_24564_priors():
     pri = H.priors("ssd512")
     loc, conf = H.detect_inputs(74, 128, pri.shape[0], bg_bias=6.0)
-    _detect_properties(pri, loc, conf, 0.01, 200, check_images=[0])
+    _detect_properties(pri, loc, conf, 0.01, 200, check_images=[0], oracle_images=range(0, 128, 4))
