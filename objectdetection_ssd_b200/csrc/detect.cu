@@ -57,8 +57,8 @@ struct DetectWs {
                                    //           by coarse rank bin (highest probabilities first)
     unsigned long long* scr_a;     // [B][capI] slice buffers for slices that do not fit shared memory
     unsigned long long* scr_b;     // [B][capI]
-    unsigned short* dir;           // [B][T][CBINS] keys per coarse rank bin of every chunk (rewritten by every call)
-    unsigned int* dir_base;        // [B][T]    start of the chunk in the image's list
+    unsigned short* dir;           // [B][T][CBINS] per chunk: keys in the coarse rank bins BEFORE each bin (exclusive prefix sums; rewritten by every call)
+    unsigned int* dir_base;        // [B][T][2] start of the chunk in the image's list, keys in the chunk
     unsigned int* cand_cnt;        // [B]       zero on entry, zero on exit
     unsigned int* overflow;        // [B]       zero on entry, zero on exit
 };
@@ -77,7 +77,7 @@ static size_t detect_ws_layout(int B, int P, int C, int n, DetectWs* w, void* ba
     void* p1 = take((size_t)B * capI * 8);
     void* p2 = take((size_t)B * capI * 8);
     void* p3 = take((size_t)B * T * CBINS * 2);
-    void* p4 = take((size_t)B * T * 4);
+    void* p4 = take((size_t)B * T * 8);
     void* p5 = take((size_t)B * 4);
     void* p6 = take((size_t)B * 4);
     if (w) { w->cand = (unsigned long long*)p0; w->scr_a = (unsigned long long*)p1; w->scr_b = (unsigned long long*)p2;
@@ -250,7 +250,8 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     if (t == 0) {
         const bool fits = chunk + total <= (unsigned)capI;
         s_base = fits ? chunk : 0xffffffffu;
-        dir_base[(size_t)b * gridDim.x + tile] = fits ? chunk : 0u;
+        dir_base[((size_t)b * gridDim.x + tile) * 2] = fits ? chunk : 0u;
+        dir_base[((size_t)b * gridDim.x + tile) * 2 + 1] = fits ? total : 0u;
         if (!fits) atomicOr(&overflow[b], 1u);                   // the whole chunk is dropped; out_cnt[b] becomes -1
     }
     __syncthreads();
@@ -259,7 +260,10 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     for (int w = 0; w < NW; ++w) if (w < warp) wb += s_wsum[w];
     s_ch[t] = wb + hin - h;
     const unsigned base = s_base;
-    dir[((size_t)b * gridDim.x + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)h : (unsigned short)0;
+    // the directory row of this chunk: keys before each rank bin (a chunk holds at most 20 x 256 keys: 16 bits).  Prefix sums
+    // instead of counts: the sweep kernel gets a slice's position in the chunk with two loads, and the image's coarse
+    // prefix sums are the column sums of the rows - no scan on its side
+    dir[((size_t)b * gridDim.x + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)(wb + hin - h) : (unsigned short)0;
     __syncthreads();
     if (base != 0xffffffffu) {
         unsigned long long* seg = cand + (size_t)b * capI + base;
@@ -822,7 +826,7 @@ static size_t nms_smem_bytes(int NF, int top_k, int T)
     off += (size_t)FBINS * 4;          // counters
     off += kcap * 4;                   // kept areas
     off += 32 * 4;                     // per-class kept counts
-    off += (size_t)T * 4 * 4;          // per-chunk base, start, length, offset of the current slice
+    off += (size_t)T * 5 * 4;          // per-chunk base, key count; start, length, offset of the current slice
     off += (size_t)NF * kcap * 2;      // per-class index lists
     return (off + 15) & ~(size_t)15;
 }
@@ -854,6 +858,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     unsigned int* s_cstart = reinterpret_cast<unsigned int*>(sp);            sp += (size_t)T * 4;
     unsigned int* s_clen = reinterpret_cast<unsigned int*>(sp);              sp += (size_t)T * 4;
     unsigned int* s_coff = reinterpret_cast<unsigned int*>(sp);              sp += (size_t)T * 4;
+    unsigned int* s_ctot = reinterpret_cast<unsigned int*>(sp);              sp += (size_t)T * 4;
     unsigned short* s_kidx = reinterpret_cast<unsigned short*>(sp);
     // the image's directory (T x 256 counts) is kept in the box buffer, which is idle while a slice is gathered
     bool dir_cached = (size_t)T * CBINS * 2 <= (size_t)SL * 16;       // until the first slice's boxes overwrite it
@@ -867,6 +872,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t < CBINS) s_col[t] = 0u;
     if (t < 32) s_kcnt[t] = 0;
+    if (t == 0) s_CS[CBINS] = 0u;
     pdl_wait();                                              // the score kernel's lists and directory are complete
     PHASE(0);
     const unsigned long long* seg = cand + (size_t)b * capI;
@@ -877,26 +883,28 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     int* oc = out_cls + (size_t)b * top_k;
     int* oi = out_prior ? out_prior + (size_t)b * top_k : nullptr;
 
-    // column sums of the directory = the image's coarse histogram -> prefix sums CS[r] = number of keys in rank bins
-    // < r (bin 0 = highest probabilities)
+    // column sums of the directory rows (per-chunk prefix sums) = the image's coarse prefix sums: CS[r] = number of keys in
+    // rank bins < r (bin 0 = highest probabilities); CS[CBINS] = all keys of the image
     {
         constexpr int G = NT / CBINS;                        // thread groups sharing the chunks of a column
         const int col = t % CBINS, g = t / CBINS;
         unsigned sum = 0u;
 #pragma unroll 4
         for (int c = g; c < T; c += G) {
-            const unsigned short v = ld_cg_u16(gdir + (size_t)c * CBINS + col);    // L2 loads: written by CTAs of a grid that may still run
+            const unsigned short v = ld_cg_u16(gdir + (size_t)c * CBINS + col);
             if (dir_cached) s_dir[c * CBINS + col] = v;
             sum += v;
         }
         if (g < G && sum) atomicAdd(&s_col[col], sum);
-        for (int c = t; c < T; c += NT) s_cbase[c] = (unsigned)ld_cg_s32(reinterpret_cast<const int*>(dir_base) + (size_t)b * T + c);
+        for (int c = t; c < T; c += NT) {
+            const unsigned long long w2 = ld_cg_u64(reinterpret_cast<const unsigned long long*>(dir_base) + (size_t)b * T + c);
+            const unsigned tot_c = (unsigned)(w2 >> 32);
+            s_cbase[c] = (unsigned)w2;
+            s_ctot[c] = tot_c;
+            if (tot_c) atomicAdd(&s_CS[CBINS], tot_c);
+        }
         __syncthreads();
-        unsigned total;
-        const unsigned c = t < CBINS ? s_col[t] : 0u;
-        const unsigned ex = block_excl_scan(c, ss.wsum, total);
-        if (t < CBINS) s_CS[t] = ex;
-        if (t == 0) s_CS[CBINS] = total;
+        if (t < CBINS) s_CS[t] = s_col[t];
         __syncthreads();
     }
 
@@ -944,25 +952,14 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         const unsigned long long kmin0 = pre ? (unsigned long long)((top18 - (rc1 - 1)) << 18) << 32 : 0ull;
         const BinMap bin0(kmin0, kmax0);
         if (pre) for (int i = t; i < FBINS; i += NT) s_cnt[i] = 0u;
-        // where the slice sits in every chunk: chunks are ordered by rank bin, so it is one contiguous piece per chunk
-        for (int c = warp; c < T; c += NT / 32) {
-            const uint4 v = dir_cached ? *reinterpret_cast<const uint4*>(s_dir + c * CBINS + lane * 8)
-                                       : ld_cg_v4(reinterpret_cast<const uint4*>(gdir + (size_t)c * CBINS + lane * 8));
-            const unsigned w8[4] = {v.x, v.y, v.z, v.w};
-            unsigned before = 0u, inside = 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int r = lane * 8 + k;
-                const unsigned cntk = (w8[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                before += r < rc0 ? cntk : 0u;
-                inside += (r >= rc0 && r < rc1) ? cntk : 0u;
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                before += __shfl_xor_sync(FULL, before, d);
-                inside += __shfl_xor_sync(FULL, inside, d);
-            }
-            if (lane == 0) { s_cstart[c] = before; s_clen[c] = inside; }
+        // where the slice sits in every chunk: chunks are ordered by rank bin, so it is one contiguous piece per chunk -
+        // from the chunk's prefix sums, two loads
+        for (int c = t; c < T; c += NT) {
+            const unsigned p0 = dir_cached ? s_dir[c * CBINS + rc0] : ld_cg_u16(gdir + (size_t)c * CBINS + rc0);
+            const unsigned p1 = rc1 >= CBINS ? s_ctot[c]
+                                             : (dir_cached ? (unsigned)s_dir[c * CBINS + rc1] : (unsigned)ld_cg_u16(gdir + (size_t)c * CBINS + rc1));
+            s_cstart[c] = p0;
+            s_clen[c] = p1 - p0;
         }
         __syncthreads();
         for (int c0 = 0; c0 < T; c0 += NT) {                    // T <= NT: one round
