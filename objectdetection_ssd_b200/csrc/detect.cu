@@ -609,33 +609,24 @@ __device__ __forceinline__ int compact_kept(const unsigned long long* X, const f
                                             unsigned int* s_wsum, const Kept kp, int K);
 
 // Sweep of one sorted slice held in shared memory (keys X[0,cnt), boxes s_box[0,cnt), cnt <= SL).  Suppression only
-// acts inside a class (Losses.py:44-55).  (1) A stable partition of the slice positions by class (match_any inside
-// chunks of 32 + per-class prefix sums over the chunks).  (2a) SPARSE sweep, the usual case: thread per candidate - it
-// is tested against the boxes of its class kept by earlier slices (a hit suppresses it for good) and against the
-// higher-scored candidates of its class in this slice; the ones it overlaps are only RECORDED (at most two), because
-// whether they suppress it depends on whether they are kept themselves (a suppressed box suppresses nobody).
-// Candidates without a recorded overlap are decided at once; the few others are resolved in score order by one
-// thread.  (2b) If some candidate overlaps more than two, the general sweep: the greedy NMS of a class inside ONE
-// warp, all classes side by side, 32 candidates at a time in lanes, tested against the boxes of the class kept earlier
-// (previous slices, previous rounds), then resolved in score order - only boxes that are still alive are broadcast
-// with shuffles.  Same decisions either way.  (3) The kept flags are compacted in slice (= global score) order onto
-// the kept list.  `scratch` is at least 16 KB of shared memory that is free during the sweep.  Returns the new kept count.
+// acts inside a class, so the greedy NMS of a class (Losses.py:44-55) runs inside ONE warp, all classes side by side and
+// without a block-wide barrier: (1) a stable partition of the slice positions by class (match_any inside chunks of 32 +
+// per-class prefix sums over the chunks), (2) per class, 32 candidates at a time in lanes: tested against the boxes of
+// the class kept earlier (previous slices, previous rounds), then all pairs of the round through register shuffles
+// (lane i's box is broadcast, one ballot = row i of the overlap matrix), resolved in score order - only boxes that
+// are still alive and overlap somebody are walked, (3) the kept flags are compacted in slice (= global score) order
+// onto the kept list.  `scratch` is at least 16 KB of shared memory that is free during the sweep.  Returns the new
+// kept count.
 __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, const float4* s_box, int cnt, int NF, unsigned char* scratch,
-                                    unsigned int* s_wsum, const Kept kp, int K, const IouThr q, bool sparse_ok)
+                                    unsigned int* s_wsum, const Kept kp, int K, const IouThr q)
 {
     constexpr int NW = NT / 32;
     constexpr int NFP = 32;                                    // row stride of the per-chunk class counts
-    constexpr int OV = 2;                                      // overlaps recorded per candidate by the sparse sweep
     unsigned short* s_order = reinterpret_cast<unsigned short*>(scratch);              // [SL] positions, grouped by class
-    unsigned char* s_keep = scratch + SL * 2;                                          // [SL] bit 0 kept; bits 1-2 recorded overlaps
-    int* s_cstart = reinterpret_cast<int*>(scratch + SL * 3);                          // [NFP + 1] (+ padding to 256 bytes)
-    unsigned int* s_dep = reinterpret_cast<unsigned int*>(scratch + SL * 3 + 256);     // [SL/32] positions with recorded overlaps
-    unsigned char* un = scratch + SL * 3 + 256 + (SL / 32) * 4;
-    unsigned short* s_ov = reinterpret_cast<unsigned short*>(un);                      // [SL][OV]   sparse sweep; aliases the two below
-    unsigned short* s_cc = reinterpret_cast<unsigned short*>(un);                      // [SL/32][NFP] partition only
-    unsigned int* my_rows = reinterpret_cast<unsigned int*>(un + (SL / 32) * NFP * 2) + (threadIdx.x >> 5) * 32;   // [NW][32] general sweep
-    static_assert(SL * 3 + 256 + (SL / 32) * 4 + SL * OV * 2 <= SL * 8 && (NFP + 1) * 4 <= 256 &&
-                  (SL / 32) * NFP * 2 + NW * 32 * 4 <= SL * OV * 2, "sweep scratch layout");
+    unsigned char* s_keep = scratch + SL * 2;                                          // [SL]
+    unsigned short* s_cc = reinterpret_cast<unsigned short*>(scratch + SL * 3);        // [SL/32][NFP]
+    int* s_cstart = reinterpret_cast<int*>(scratch + SL * 3 + (SL / 32) * NFP * 2);    // [NFP + 1]
+    static_assert(SL * 3 + (SL / 32) * NFP * 2 + (NFP + 1) * 4 <= SL * 8, "sweep scratch layout");
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int nchunk = (cnt + 31) >> 5;
@@ -643,7 +634,6 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
 
     for (int i = t; i < nchunk * NFP; i += NT) s_cc[i] = 0;
     for (int i = t; i < cnt; i += NT) s_keep[i] = 0;
-    for (int i = t; i < SL / 32; i += NT) s_dep[i] = 0u;
     __syncthreads();
     for (int ch = warp; ch < nchunk; ch += NW) {
         const int i = ch * 32 + lane;
@@ -675,60 +665,6 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
     __syncthreads();
     PHASE(9);
 
-    if (sparse_ok) {
-        bool dense = false;
-        for (int idx = t; idx < cnt; idx += NT) {              // idx: slot in the class-grouped order
-            const int pos = s_order[idx];
-            const int c = key_cls(X[pos]);
-            const int c0 = s_cstart[c];
-            const float4 bx = s_box[pos];
-            const float ar = box_area(bx);
-            bool sup = false;
-            const int kc0 = kp.cnt[c];
-            const unsigned short* il = kp.idx + (size_t)c * kp.cap;
-            for (int k = 0; k < kc0; ++k) {
-                const int id = il[k];
-                sup = sup || iou_ge_fast(kp.box[id], kp.area[id], bx, ar, q);
-            }
-            int nov = 0;
-            if (!sup) {
-                for (int k = c0; k < idx; ++k) {               // the higher-scored candidates of the class (positions ascending)
-                    const int pj = s_order[k];
-                    const float4 b2 = s_box[pj];
-                    if (iou_ge_fast(b2, box_area(b2), bx, ar, q)) {
-                        if (nov < OV) s_ov[pos * OV + nov] = (unsigned short)pj;
-                        ++nov;
-                    }
-                }
-            }
-            dense = dense || nov > OV;
-            s_keep[pos] = (unsigned char)(((!sup && nov == 0) ? 1 : 0) | (min(nov, OV) << 1));
-            if (!sup && nov > 0) atomicOr(&s_dep[pos >> 5], 1u << (pos & 31));
-        }
-        if (!__syncthreads_or(dense ? 1 : 0)) {
-            if (t == 0) {
-                for (int w = 0; w < nchunk; ++w) {
-                    unsigned m = s_dep[w];
-                    while (m) {                                // ascending position = descending score
-                        const int i = w * 32 + __ffs(m) - 1;
-                        m &= m - 1u;
-                        const int nov = s_keep[i] >> 1;
-                        bool kept = true;
-                        for (int o = 0; o < nov; ++o) kept = kept && !(s_keep[s_ov[i * OV + o]] & 1u);
-                        s_keep[i] = (unsigned char)((kept ? 1 : 0) | (nov << 1));
-                    }
-                }
-            }
-            __syncthreads();
-            PHASE(10);
-            const int Kn = compact_kept(X, s_box, s_keep, cnt, s_wsum, kp, K);
-            PHASE(11);
-            return Kn;
-        }
-        for (int i = t; i < cnt; i += NT) s_keep[i] = 0;       // dense overlaps: the general sweep decides everything
-        __syncthreads();
-    }
-
     for (int c = warp; c < NF; c += NW) {
         const int n_c = s_cstart[c + 1] - s_cstart[c];
         unsigned short* L = s_order + s_cstart[c];
@@ -750,21 +686,21 @@ __device__ __noinline__ int sweep_slice_by_class(const unsigned long long* X, co
                 const float4 b2 = s_box[L[k]];
                 sup = sup || iou_ge_fast(b2, box_area(b2), bx, ar, q);
             }
-            // all pairs of the round along the diagonals (independent iterations, they pipeline): lane i ends up with
-            // the later lanes its box overlaps; then only rows that overlap somebody are walked in score order
+            // all pairs of the round: the box of lane i is broadcast with shuffles, every later lane tests itself against
+            // it, and one ballot is the row of the 32 x 32 overlap matrix that lane i keeps (the later lanes its box
+            // overlaps) - no shared-memory traffic and no dependent loads inside the loop; then only rows that overlap
+            // somebody are walked in score order
             const int nr = min(32, n_c - r0);
-            my_rows[lane] = 0u;
-            __syncwarp();
+            unsigned row = 0u;
 #pragma unroll 4
-            for (int d = 1; d < nr; ++d) {                    // lane j against lane j - d
-                const int pi = __shfl_up_sync(FULL, pos, d);
-                if (lane >= d && v) {
-                    const float4 bi = s_box[pi];
-                    if (iou_ge_fast(bi, box_area(bi), bx, ar, q)) atomicOr(&my_rows[lane - d], 1u << lane);
-                }
+            for (int i = 0; i < nr - 1; ++i) {
+                const float4 bi = make_float4(__shfl_sync(FULL, bx.x, i), __shfl_sync(FULL, bx.y, i),
+                                              __shfl_sync(FULL, bx.z, i), __shfl_sync(FULL, bx.w, i));
+                const float ai = __shfl_sync(FULL, ar, i);
+                const bool ov = lane > i && v && iou_ge_fast(bi, ai, bx, ar, q);
+                const unsigned m = __ballot_sync(FULL, ov);
+                if (lane == i) row = m;
             }
-            __syncwarp();
-            const unsigned row = my_rows[lane];
             unsigned alive = __ballot_sync(FULL, v && !sup);
             unsigned todo = __ballot_sync(FULL, row != 0u);
             while (todo) {
@@ -796,11 +732,11 @@ __device__ __forceinline__ int compact_kept(const unsigned long long* X, const f
     const int per = (cnt + NT - 1) / NT;
     const int lo = min(cnt, t * per), hi = min(cnt, lo + per);
     unsigned local = 0u;
-    for (int i = lo; i < hi; ++i) local += s_keep[i] & 1u;
+    for (int i = lo; i < hi; ++i) local += s_keep[i];
     unsigned total;
     int g = K + (int)block_excl_scan(local, s_wsum, total);
     for (int i = lo; i < hi; ++i) {
-        if (!(s_keep[i] & 1u)) continue;
+        if (!s_keep[i]) continue;
         if (g < kp.cap) {
             const unsigned long long key = X[i];
             const float4 bx = s_box[i];
@@ -838,7 +774,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                   unsigned int* __restrict__ overflow,
-                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
@@ -985,7 +921,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [&](int pos, unsigned long long key) { s_box[pos] = load_box(key); });
             PHASE(3);
             PHASE(4);
-            K = sweep_slice_by_class(X, s_box, cnt, NF, reinterpret_cast<unsigned char*>(Y), ss.wsum, kp, K, make_iou_thr(iou_thr), sparse_ok != 0);
+            K = sweep_slice_by_class(X, s_box, cnt, NF, reinterpret_cast<unsigned char*>(Y), ss.wsum, kp, K, make_iou_thr(iou_thr));
         } else {
             sort_desc(X, Y, cnt, s_S, s_cnt, ss, pre, kmin0, kmax0, [](int, unsigned long long) {});
             for (int base = 0; base < cnt && K <= top_k; base += 64)
@@ -1040,12 +976,12 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                   unsigned int* __restrict__ overflow,
-                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
     detect_nms_body<FROM_SCORES, false>(nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                        img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+                                        img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
 __global__ void __launch_bounds__(NT, 2)
@@ -1054,12 +990,12 @@ detect_nms_levels_kernel(const __grid_constant__ DetLevels dl, const float4* __r
                          unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                          const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
                          unsigned int* __restrict__ overflow,
-                         const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr, int sparse_ok,
+                         const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
                          float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                          int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
     detect_nms_body<false, true>(&dl, nullptr, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                 img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+                                 img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
 template <bool FROM_SCORES>
@@ -1084,7 +1020,6 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     const int capI = detect_cap_image(P, C, n_cap);
 
-    static const int sparse_ok = getenv("SSDHEAD_SWEEP_SPARSE") ? atoi(getenv("SSDHEAD_SWEEP_SPARSE")) : 1;
     dim3 g1(T, B);
     if (dl) {
         SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
@@ -1099,13 +1034,13 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_levels_kernel, dim3(B), dim3(NT), smem_nms, st,
                                   *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     } else {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
                                   (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr, sparse_ok,
+                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     }
     count_launch();
