@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define SSDHEAD_ABI_VERSION 2   /* 2: sparse gradient return (ssdhead_mine_sparse, ssdhead_ctx_multibox_loss_host_sparse) */
+#define SSDHEAD_ABI_VERSION 3   /* 2: sparse gradient return (ssdhead_mine_sparse, ssdhead_ctx_multibox_loss_host_sparse);
+                                   3: resident gradient tensors (ssdhead_multibox_step_resident, ssdhead_ctx_multibox_loss_dev_resident) */
 
 #define SSDHEAD_E_BADARG      (-1)  /* null pointer / negative size */
 #define SSDHEAD_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for */
@@ -46,6 +47,7 @@ extern "C" {
 #define SSDHEAD_WS_LOSS   1
 #define SSDHEAD_WS_DETECT 2
 #define SSDHEAD_WS_NMS    3
+#define SSDHEAD_WS_ROWS   4   /* rows workspace of ssdhead_multibox_step_resident */
 
 int         ssdhead_abi_version(void);
 const char* ssdhead_error_string(int code);
@@ -172,6 +174,27 @@ int ssdhead_multibox_step_sharded(const float* loc_dev, const float* conf_dev,
                           int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev,
                           int32_t* err_flag_dev, void* stream);
 size_t ssdhead_xchg_bytes(void);
+/* ssdhead_multibox_step with RESIDENT gradient tensors.  The gradient of this loss is sparse: only positives and mined
+ * negatives (about 4 * Npos of the P rows of an image, Losses.py:177-197) carry one.  A caller that keeps the SAME
+ * grad_loc / grad_conf tensors from step to step (a training loop does: they only feed the head's conv backward, which
+ * reads them) hands them over once, zero-filled, together with a zero-filled SSDHEAD_WS_ROWS workspace; from then on
+ * every call retracts the rows the previous call wrote and writes its own, so the tensors hold exactly this step's
+ * dense gradient - bit-identical to ssdhead_multibox_step's - without 873 KB of zero background per image per step
+ * ever being written (the streaming kernel runs forward-only: conf is read, nothing dense is stored).
+ * Contract: between calls nobody else writes the two tensors or the rows workspace; after anything else touched them
+ * (or the tensors were reallocated) zero-fill all three again.  A smaller batch may follow a larger one (the rows of
+ * the images beyond B stay listed and are retracted when those images return).  R = 1: one GPU; R > 1: the batch is
+ * sharded by image and the remaining arguments are those of ssdhead_multibox_step_sharded.  P < 65536. */
+int ssdhead_multibox_step_resident(const float* loc_dev, const float* conf_dev,
+                          const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                          const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                          uint8_t* cls_u8_dev, int32_t* best_prior_dev, int32_t* npos_dev,
+                          void* ws_loss_dev, size_t ws_loss_bytes, void* ws_match_dev, size_t ws_match_bytes,
+                          void* ws_rows_dev, size_t ws_rows_bytes,
+                          int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev,
+                          int32_t* err_flag_dev, void* stream);
 int ssdhead_mine(const float* loc_dev, const float* conf_dev,
                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                  const float* pri_xyxy_dev, const float* pri_cxcywh_dev,
@@ -342,6 +365,16 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* ctx, const float* loc_dev, const 
                                   int B, int sumG, int neg_ratio, float pos_iou,
                                   double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
                                   void* stream);
+/* ssdhead_ctx_multibox_loss_dev with RESIDENT gradient tensors (ssdhead_multibox_step_resident; after ssdhead_ctx_xchg_import
+ * the sharded step).  The context owns the rows workspace and remembers the two tensors.  fresh != 0: the context
+ * zero-fills grad_loc [B,P,4] / grad_conf [B,P,C] and forgets the previous rows first (first call, new tensors, or
+ * after anybody else wrote them); fresh == 0: the tensors must be the ones of the previous call (else SSDHEAD_E_STATE)
+ * and hold what that call left in them. */
+int ssdhead_ctx_multibox_loss_dev_resident(ssdhead_ctx* ctx, const float* loc_dev, const float* conf_dev,
+                                  const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
+                                  int B, int sumG, int neg_ratio, float pos_iou,
+                                  double* sums_dev, float* losses_dev, float* grad_loc_dev, float* grad_conf_dev,
+                                  int fresh, void* stream);
 /* ssdhead_ctx_multibox_loss_dev on per-level head tensors (ssdhead_levels, gradients inside the struct): one GPU, or
  * - after ssdhead_ctx_xchg_import - the sharded two-kernel step with global normalisation. */
 int ssdhead_ctx_multibox_loss_levels_dev(ssdhead_ctx* ctx, const ssdhead_levels* levels,

@@ -13,8 +13,8 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libssdhead.so")
 
-ABI_VERSION = 2
-WS_MATCH, WS_LOSS, WS_DETECT, WS_NMS = 0, 1, 2, 3
+ABI_VERSION = 3
+WS_MATCH, WS_LOSS, WS_DETECT, WS_NMS, WS_ROWS = 0, 1, 2, 3, 4
 E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN, E_STATE = -1, -2, -3, -4, -5
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -42,6 +42,8 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "ssdhead_multibox_step_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
+    "ssdhead_multibox_step_resident": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
     "ssdhead_xchg_bytes": (_sz, []),
     "ssdhead_ctx_xchg_export": (_i, [_vp, _vp]),
     "ssdhead_ctx_xchg_import": (_i, [_vp, _vp, _i, _i]),
@@ -61,6 +63,7 @@ SIGNATURES = {
     "ssdhead_host_alloc": (_vp, [_sz]),
     "ssdhead_host_free": (None, [_vp]),
     "ssdhead_ctx_multibox_loss_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ssdhead_ctx_multibox_loss_dev_resident": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "ssdhead_ctx_multibox_loss_begin": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, C.POINTER(_vp), _vp]),
     "ssdhead_ctx_multibox_loss_end": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ssdhead_ctx_multibox_loss_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),

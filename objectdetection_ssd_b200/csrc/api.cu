@@ -5,6 +5,7 @@ namespace ssdhead {
 unsigned long long g_launch_count = 0;
 size_t loss_workspace_bytes(int B, int P, int C);          // loss.cu
 size_t detect_workspace_bytes(int B, int P, int C, int n); // detect.cu
+size_t resident_rows_bytes(int B, int P);                   // loss.cu
 }  // namespace ssdhead
 
 using namespace ssdhead;
@@ -41,6 +42,8 @@ size_t ssdhead_workspace_bytes(int which, int B, int P, int C, int n)
         case SSDHEAD_WS_DETECT:
         case SSDHEAD_WS_NMS:
             return detect_workspace_bytes(B, P, C, n);
+        case SSDHEAD_WS_ROWS:
+            return resident_rows_bytes(B, P);
         default:
             return 0;
     }

@@ -194,6 +194,10 @@ struct ssdhead_ctx {
     float *losses;
     // workspaces
     void *ws_match, *ws_loss, *ws_detect;
+    // resident gradient tensors (ssdhead_ctx_multibox_loss_dev_resident): rows workspace + the tensors it describes
+    void* ws_rows;
+    size_t ws_rows_bytes;
+    float *res_grad_loc, *res_grad_conf;
     size_t ws_match_bytes, ws_loss_bytes, ws_loss_total, ws_detect_bytes;
     // detect outputs (host-buffer path)
     float *det_boxes, *det_prob;
@@ -294,6 +298,7 @@ void ssdhead_ctx_destroy(ssdhead_ctx* c)
     if (c->xchg_local) cudaFree(c->xchg_local);
     if (c->xchg_peers_dev) cudaFree(c->xchg_peers_dev);
     if (c->err_flag) cudaFree(c->err_flag);
+    if (c->ws_rows) cudaFree(c->ws_rows);
     void* more[] = {c->npos_global, c->sp_cnt, c->sp_idx, c->sp_conf, c->sp_loc};
     for (void* b : more) if (b) cudaFree(b);
     cudaStream_t st[] = {c->s_main, c->s_aux, c->s_h2d, c->s_d2h};
@@ -436,6 +441,39 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* c, const float* loc, const float*
     return ssdhead_multibox_step(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
                                  neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
                                  nullptr, nullptr, c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, stream);
+}
+
+int ssdhead_ctx_multibox_loss_dev_resident(ssdhead_ctx* c, const float* loc, const float* conf,
+                                  const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off, int B, int sumG,
+                                  int neg_ratio, float pos_iou,
+                                  double* sums, float* losses, float* grad_loc, float* grad_conf, int fresh, void* stream)
+{
+    if (!c || !grad_loc || !grad_conf) return SSDHEAD_E_BADARG;
+    if (B <= 0 || B > c->maxB || sumG < 0 || sumG > c->max_sumG) return SSDHEAD_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c->ws_rows) {
+        SSD_CHECK_CUDA(cudaSetDevice(c->device));
+        c->ws_rows_bytes = ssdhead_workspace_bytes(SSDHEAD_WS_ROWS, c->maxB, c->P, c->C, 0);
+        if (c->ws_rows_bytes == 0) return SSDHEAD_E_UNSUPPORTED;
+        SSD_CHECK_CUDA(cudaMalloc(&c->ws_rows, c->ws_rows_bytes));
+        fresh = 1;
+    }
+    if (fresh) {
+        SSD_CHECK_CUDA(cudaMemsetAsync(c->ws_rows, 0, c->ws_rows_bytes, st));
+        SSD_CHECK_CUDA(cudaMemsetAsync(grad_loc, 0, (size_t)B * c->P * 4 * sizeof(float), st));
+        SSD_CHECK_CUDA(cudaMemsetAsync(grad_conf, 0, (size_t)B * c->P * c->C * sizeof(float), st));
+        c->res_grad_loc = grad_loc; c->res_grad_conf = grad_conf;
+    } else if (grad_loc != c->res_grad_loc || grad_conf != c->res_grad_conf) {
+        return SSDHEAD_E_STATE;                          // not the tensors the rows workspace describes
+    }
+    { const int zr = ctx_loss_ws_for(c, B, st); if (zr) return zr; }
+    const bool sharded = c->xchg_R > 1;
+    return ssdhead_multibox_step_resident(loc, conf, gt_xyxy, gt_cls, gt_off, c->pri_xyxy, c->pri_cxcywh, B, c->P, c->C, sumG,
+                                          neg_ratio, pos_iou, sums, losses, grad_loc, grad_conf, c->cls_u8, c->best_prior, c->npos,
+                                          c->ws_loss, c->ws_loss_bytes, c->ws_match, c->ws_match_bytes, c->ws_rows, c->ws_rows_bytes,
+                                          sharded ? c->xchg_R : 1, sharded ? c->xchg_rank : 0, sharded ? ++c->xchg_seq : 0u,
+                                          sharded ? c->xchg_peers_dev : nullptr, sharded ? c->xchg_local : nullptr,
+                                          sharded ? c->err_flag : nullptr, stream);
 }
 
 int ssdhead_ctx_multibox_loss_levels_dev(ssdhead_ctx* c, const ssdhead_levels* levels,

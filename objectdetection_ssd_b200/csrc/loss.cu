@@ -601,6 +601,10 @@ struct MineParams {
     int* sp_idx;
     int* sp_cnt;                    // [B][2]: rows of the image (may exceed cap: then only cap were stored), positives
     int sp_cap;
+    // resident gradient tensors (ssdhead_multibox_step_resident): grad_conf / grad_loc are all-zero except for the rows
+    // the PREVIOUS step wrote, which are listed here; this step retracts them, writes its own rows and lists those
+    unsigned char* res_base;        // per image one record of res_stride bytes (independent of B): int32 rows, int32 positives,
+    size_t res_stride;              // then uint16 [P] the rows of the image that carry a gradient, positives first (nullable)
 };
 
 
@@ -685,6 +689,22 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     pdl_trigger();
     pdl_wait();                                              // CE, class bytes, best priors, positive counts are ready
     __syncthreads();                                         // s_max / s_nsel / gt staging above are visible
+    int* res_cnt = nullptr;
+    unsigned short* res_rows = nullptr;
+    if (GRADS && !SPARSE && p.res_base) {
+        // resident gradient tensors: zero the rows the previous step left in this image (everything else is zero
+        // already), so no dense zero background is written at all.  The new rows are written after several barriers.
+        res_cnt = reinterpret_cast<int*>(p.res_base + (size_t)b * p.res_stride);
+        res_rows = reinterpret_cast<unsigned short*>(p.res_base + (size_t)b * p.res_stride + 8);
+        const int n_prev = res_cnt[0], npl_prev = res_cnt[1];
+        for (int i = t; i < n_prev; i += MN_T) {
+            const int j = (int)res_rows[i];
+            float* g = gconf_row(j);
+#pragma unroll
+            for (int q = 0; q < C; ++q) g[q] = 0.0f;
+            if (i < npl_prev) *gloc_row(j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     LPHASE(0);
     GMARK_MIN(1); GMARK_MAX(2);
 #ifdef SSDHEAD_PHASE_TIMES
@@ -957,6 +977,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
     const uint32_t npl = s_npl;                  // positives, listed from the end
     const uint32_t nsel = s_nsel + npl;
     if (SPARSE && t == 0) { p.sp_cnt[2 * b] = (int)nsel; p.sp_cnt[2 * b + 1] = (int)npl; }
+    if (GRADS && !SPARSE && res_rows && t == 0) { res_cnt[0] = (int)nsel; res_cnt[1] = (int)npl; }
 #ifdef SSDHEAD_PHASE_TIMES
     if (t == 0 && b < 1024) { g_cta[b][0] = clock64() - cta_t0; g_cta[b][3] = nsel; }
 #endif
@@ -1057,6 +1078,7 @@ __device__ __forceinline__ void mine_body(const MineParams& p, const LevelTab* _
         const float* my_crow = LEVELS ? conf_row(j) : nullptr;      // per-level tensors: locate the row once, pass pointers
         float* my_grow = (LEVELS && GRADS) ? gconf_row(j) : nullptr;
         if (SPARSE && valid && idx < (uint32_t)p.sp_cap) p.sp_idx[(size_t)b * p.sp_cap + idx] = j;
+        if (GRADS && !SPARSE && res_rows && valid) res_rows[idx] = (unsigned short)j;
         if (staged) {
             // element e = lane + 32 i of the warp's 32 x C block belongs to row e / C, whose index lane e / C holds;
             // all loads are issued before the first shared-memory store (which the compiler must assume may alias)
@@ -1297,6 +1319,15 @@ size_t loss_workspace_bytes(int B, int P, int C)
            round_up((size_t)B * P * sizeof(unsigned short), 16);      // CE, then the best-gt map of large-G batches
 }
 
+// rows workspace of the resident-gradient step: one record per image, the same for every batch size - int32 rows,
+// int32 positives, uint16 [P] row indices (P < 65536)
+static size_t resident_row_stride(int P) { return round_up(8 + (size_t)P * sizeof(unsigned short), 16); }
+size_t resident_rows_bytes(int B, int P)
+{
+    if (B <= 0 || P <= 0 || P >= 65536) return 0;
+    return (size_t)B * resident_row_stride(P);
+}
+
 static int g_num_sms = 0;
 static int num_sms()
 {
@@ -1487,7 +1518,8 @@ static int multibox_step_impl(const float* loc, const float* conf,
                           uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
                           uint32_t* mined_mask, float* ce,
                           void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
-                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag);
+                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag,
+                          void* ws_rows = nullptr, size_t ws_rows_bytes = 0);
 
 int ssdhead_multibox_step(const float* loc, const float* conf,
                           const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
@@ -1523,6 +1555,32 @@ int ssdhead_multibox_step_sharded(const float* loc, const float* conf,
                               sums, losses, grad_loc, grad_conf, cls_u8, best_prior, npos, nullptr, nullptr,
                               ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, R, rank, seq, peers_dev, xchg_local_dev,
                               err_flag_dev);
+}
+
+// ssdhead_multibox_step with RESIDENT gradient tensors: grad_loc / grad_conf are all-zero when first handed over (together
+// with a zero-filled rows workspace) and are then only ever written by this call.  The gradient of this loss is
+// sparse (about 4 * Npos of the P rows of an image), so instead of writing 873 KB of zero background per image per step
+// the step retracts the ~200 rows the previous step wrote and writes its own - the tensors hold exactly the dense
+// gradient of this step afterwards (Losses.py:177-197 + autograd), bit-identical to ssdhead_multibox_step's.
+// With R > 1 the batch is sharded as in ssdhead_multibox_step_sharded.
+int ssdhead_multibox_step_resident(const float* loc, const float* conf,
+                          const float* gt_xyxy, const float* gt_cls, const int32_t* gt_off,
+                          const float* pri_xyxy, const float* pri_cxcywh,
+                          int B, int P, int C, int sumG, int neg_ratio, float pos_iou,
+                          double* sums, float* losses, float* grad_loc, float* grad_conf,
+                          uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
+                          void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes,
+                          void* ws_rows, size_t ws_rows_bytes,
+                          int R, int rank, unsigned int seq, void* const* peers_dev, void* xchg_local_dev, int32_t* err_flag_dev,
+                          void* stream)
+{
+    if (!ws_rows || !grad_loc || !grad_conf) return SSDHEAD_E_BADARG;
+    if (R < 1 || R > XCHG_MAX_R || rank < 0 || rank >= R || (R > 1 && seq == 0u)) return SSDHEAD_E_BADARG;
+    if (R > 1 && (!peers_dev || !xchg_local_dev || !err_flag_dev)) return SSDHEAD_E_BADARG;
+    return multibox_step_impl(loc, conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, pri_cxcywh, B, P, C, sumG, neg_ratio, pos_iou,
+                              sums, losses, grad_loc, grad_conf, cls_u8, best_prior, npos, nullptr, nullptr,
+                              ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream,
+                              R > 1 ? R : 0, rank, seq, peers_dev, xchg_local_dev, err_flag_dev, ws_rows, ws_rows_bytes);
 }
 
 // ssdhead_multibox_step on per-level head tensors (Model.py:212-235 without the permute/cat copies)
@@ -1776,14 +1834,24 @@ static int multibox_step_impl(const float* loc, const float* conf,
                           uint8_t* cls_u8, int32_t* best_prior, int32_t* npos,
                           uint32_t* mined_mask, float* ce,
                           void* ws_loss, size_t ws_loss_bytes, void* ws_match, size_t ws_match_bytes, void* stream,
-                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag)
+                          int R, int rank, unsigned seq, void* const* peers_dev, void* xchg_local, int* err_flag,
+                          void* ws_rows, size_t ws_rows_bytes)
 {
     if (!loc || !pri_cxcywh || !sums || !losses || neg_ratio < 0) return SSDHEAD_E_BADARG;
     if (!aligned16(loc) || !aligned16(pri_cxcywh)) return SSDHEAD_E_ALIGN;
+    // resident gradient tensors: the streaming kernel writes no zero background (it runs forward-only), the mining
+    // kernel retracts the previous step's rows and writes this step's
+    const bool resident = ws_rows != nullptr;
+    if (resident) {
+        if (!grad_loc || !grad_conf || B < 0 || P <= 0 || P >= 65536) return SSDHEAD_E_BADARG;
+        if (!aligned16(ws_rows) || !aligned16(grad_loc)) return SSDHEAD_E_ALIGN;
+        if (ws_rows_bytes < resident_rows_bytes(B, P)) return SSDHEAD_E_WORKSPACE;
+    }
     // (ws_loss is validated by the call below before anything is written through this pointer)
     unsigned short* obj_map = (ws_loss && B > 0 && use_obj_map(B, sumG) && loss_workspace_bytes(B, P, C) && ws_loss_bytes >= loss_workspace_bytes(B, P, C))
                                   ? ws_obj(ws_loss, B, P) : nullptr;
-    int rc = ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce, grad_loc, grad_conf,
+    int rc = ce_match_stream_impl(conf, gt_xyxy, gt_cls, gt_off, pri_xyxy, B, P, C, sumG, pos_iou, ce,
+                                  resident ? nullptr : grad_loc, resident ? nullptr : grad_conf,
                                   cls_u8, best_prior, npos, ws_loss, ws_loss_bytes, ws_match, ws_match_bytes, stream, false, obj_map);
     if (rc || B == 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1811,6 +1879,10 @@ static int multibox_step_impl(const float* loc, const float* conf,
     prm.arrive_total = (unsigned long long*)(image_counter + 2);   // 8-byte aligned word of the 16-byte tail
     prm.xchg_R = R; prm.xchg_rank = rank; prm.xchg_seq = seq;
     prm.xchg_peers = (unsigned long long* const*)peers_dev; prm.xchg_local = (unsigned long long*)xchg_local; prm.err_flag = err_flag;
+    if (resident) {
+        prm.res_base = (unsigned char*)ws_rows;
+        prm.res_stride = resident_row_stride(P);
+    }
     if (mined_mask) SSD_CHECK_CUDA(cudaMemsetAsync(mined_mask, 0, (size_t)B * ((P + 31) / 32) * sizeof(uint32_t), st));
     rc = grad_loc ? launch_mine_fin<21, true>(prm, st) : launch_mine_fin<21, false>(prm, st);
     if (rc != 1) return rc;

@@ -127,6 +127,17 @@ class SSDHeadContext:
             self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
             float(pos_iou), sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, stream), "ssdhead_ctx_multibox_loss_dev")
 
+    def loss_dev_resident(self, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, sums_ptr, losses_ptr,
+                          grad_loc_ptr, grad_conf_ptr, stream, fresh: bool = False, neg_ratio: int = 3, pos_iou: float = 0.5):
+        """``loss_dev`` with RESIDENT gradient tensors: the same ``grad_loc`` / ``grad_conf`` from step to step; every
+        call retracts the rows the previous call wrote and writes its own (the gradient is sparse: ~4 Npos of 8732 rows
+        per image), so no dense zero background is written.  ``fresh=True`` on the first call, with new tensors, or after
+        anybody else wrote them (the context zero-fills them).  Same bits as ``loss_dev``."""
+        _lib.check(self.lib.ssdhead_ctx_multibox_loss_dev_resident(
+            self._h, loc_ptr, conf_ptr, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, int(B), int(sumG), int(neg_ratio),
+            float(pos_iou), sums_ptr, losses_ptr, grad_loc_ptr, grad_conf_ptr, 1 if fresh else 0, stream),
+            "ssdhead_ctx_multibox_loss_dev_resident")
+
     def loss_levels_dev(self, levels, gt_xyxy_ptr, gt_cls_ptr, gt_off_ptr, B, sumG, sums_ptr, losses_ptr, stream,
                         neg_ratio: int = 3, pos_iou: float = 0.5):
         """``loss_dev`` on per-level head tensors: ``levels`` is a filled ``_lib.Levels`` (conf / loc / grad pointers per

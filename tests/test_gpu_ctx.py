@@ -184,3 +184,49 @@ def test_loss_host_sparse_rows_equal_the_dense_gradients(B, pinned_rows):
     with pytest.raises(RuntimeError):
         r2.scatter(P)
     ctx.close()
+
+
+def test_resident_gradient_tensors_equal_the_dense_step():
+    """ssdhead_ctx_multibox_loss_dev_resident: the same gradient tensors from step to step, every step retracts the
+    previous step's rows and writes its own - after every step the tensors must hold exactly what the dense step
+    (zero background + rows, ssdhead_ctx_multibox_loss_dev) writes: same bits, same losses.  Covers changing batches,
+    a smaller batch between larger ones, repeated inputs (the same rows written again), and the `fresh` hand-over
+    after somebody else scribbled over the tensors."""
+    from objectdetection_ssd_b200.ctx import SSDHeadContext
+    from objectdetection_ssd_b200 import _lib
+    maxB = 12
+    pri = H.priors()
+    P = pri.shape[0]
+    ctx = SSDHeadContext(pri.numpy(), max_batch=maxB)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    gl_res = torch.full((maxB, P, 4), 7.0, device="cuda")            # garbage: `fresh` must clean it
+    gc_res = torch.full((maxB, P, 21), -3.0, device="cuda")
+    sums_r = torch.empty(2, dtype=torch.float64, device="cuda")
+    loss_r = torch.empty(2, device="cuda")
+    sums_d = torch.empty(2, dtype=torch.float64, device="cuda")
+    loss_d = torch.empty(2, device="cuda")
+    plan = [(31, 12, True), (32, 12, False), (32, 12, False), (33, 5, False), (34, 12, False), (35, 12, True), (36, 1, False), (31, 12, False)]
+    for step, (seed, B, fresh) in enumerate(plan):
+        _, loc, conf, gb, gc, gx, gcl, off = _inputs(seed, B)
+        tl, tcf, tgx, tgc, toff = d(loc), d(conf), d(gx), d(gcl), d(off)
+        if fresh and step > 0:
+            gc_res.fill_(1.0)                                        # somebody else wrote the tensors
+            gl_res.fill_(2.0)
+        ctx.loss_dev_resident(tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
+                              sums_r.data_ptr(), loss_r.data_ptr(), gl_res.data_ptr(), gc_res.data_ptr(), st, fresh=fresh)
+        gl_d, gc_d = torch.empty_like(tl), torch.empty_like(tcf)
+        ctx.loss_dev(tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), B, int(off[-1]),
+                     sums_d.data_ptr(), loss_d.data_ptr(), gl_d.data_ptr(), gc_d.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.equal(loss_r, loss_d) and torch.equal(sums_r, sums_d), f"step {step}: losses"
+        assert torch.equal(gc_res[:B], gc_d), f"step {step}: grad_conf"
+        assert torch.equal(gl_res[:B], gl_d), f"step {step}: grad_loc"
+        assert int((gc_d.abs().sum(-1) != 0).sum()) > 0
+    # other tensors without `fresh`: refused, nothing launched
+    other = torch.zeros_like(gc_res)
+    rc = ctx.lib.ssdhead_ctx_multibox_loss_dev_resident(ctx._h, tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(),
+                                                        toff.data_ptr(), B, int(off[-1]), 3, 0.5, sums_r.data_ptr(), loss_r.data_ptr(),
+                                                        gl_res.data_ptr(), other.data_ptr(), 0, st)
+    assert rc == -5
+    ctx.close()

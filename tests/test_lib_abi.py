@@ -35,13 +35,15 @@ def test_ctypes_table_covers_the_header(lib):
 
 def test_metadata_entry_points(lib):
     from objectdetection_ssd_b200 import _lib
-    assert lib.ssdhead_abi_version() == 2
+    assert lib.ssdhead_abi_version() == 3
     assert lib.ssdhead_error_string(0) == b"ok"
     assert b"workspace" in lib.ssdhead_error_string(-3)
     assert lib.ssdhead_workspace_bytes(_lib.WS_MATCH, 32, 8732, 21, 200) > 0
     assert lib.ssdhead_workspace_bytes(_lib.WS_LOSS, 32, 8732, 21, 0) >= 32 * 8732 * 4
     assert lib.ssdhead_workspace_bytes(_lib.WS_LOSS, 1, 100000, 21, 0) == 0          # beyond the shared-memory bound
     assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 0) > 64 * 8732 * 16
+    assert lib.ssdhead_workspace_bytes(_lib.WS_ROWS, 256, 8732, 21, 0) >= 256 * (8732 * 2 + 8)
+    assert lib.ssdhead_workspace_bytes(_lib.WS_ROWS, 1, 70000, 21, 0) == 0           # row indices are 16 bits
     assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 1024) < lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 0)
 
 
