@@ -848,6 +848,56 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
+def time_resident(dev, B=256, steps=200, warmup=10):
+    """The training-head step with RESIDENT gradient tensors (ssdhead_ctx_multibox_loss_dev_resident): the same
+    grad_loc / grad_conf from step to step, every step retracts the previous step's rows and writes its own, no dense
+    zero background is written.  Inputs rotate through >= 2 x 126 MB of distinct device buffers."""
+    from objectdetection_ssd_b200 import synth
+    from objectdetection_ssd_b200.ctx import SSDHeadContext
+    from objectdetection_ssd_b200.priors import make_priors
+    pri = make_priors()
+    P = int(pri.shape[0])
+    ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)
+    nset = max(2, int(2 * 126e6 // (B * P * 25 * 4)) + 1)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sets = []
+    for i in range(nset):
+        gb, gc = synth.make_gt(500 + i, B)
+        loc, conf = synth.make_head(500 + i, B, P)
+        gx, gcl, off = synth.pack_gt(gb, gc)
+        sets.append((d(loc), d(conf), d(gx), d(gcl), d(off), int(off[-1])))
+    gl = torch.empty(B, P, 4, device=dev)
+    gcf = torch.empty(B, P, 21, device=dev)
+    sums = torch.empty(2, dtype=torch.float64, device=dev)
+    losses = torch.empty(2, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def step(i, fresh=False):
+        l, c, gx, gcl, off, sg = sets[i % nset]
+        ctx.loss_dev_resident(l.data_ptr(), c.data_ptr(), gx.data_ptr(), gcl.data_ptr(), off.data_ptr(), B, sg,
+                              sums.data_ptr(), losses.data_ptr(), gl.data_ptr(), gcf.data_ptr(), st, fresh=fresh)
+    step(0, fresh=True)
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # the tensors must hold exactly the dense step's gradient of the LAST batch
+    l, c, gx, gcl, off, sg = sets[(steps - 1) % nset]
+    gl2, gc2 = torch.empty_like(gl), torch.empty_like(gcf)
+    ctx.loss_dev(l.data_ptr(), c.data_ptr(), gx.data_ptr(), gcl.data_ptr(), off.data_ptr(), B, sg,
+                 sums.data_ptr(), losses.data_ptr(), gl2.data_ptr(), gc2.data_ptr(), st)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(gl, gl2) and torch.equal(gcf, gc2))
+    ctx.close()
+    return {"ms_step": ms, "equals_dense_step": same}
+
+
 def others(args, rank, dev, local, peak):
     """The other single-GPU configurations of BASELINE.json and the reference-facing Python surface, short runs."""
     out = []
@@ -872,6 +922,17 @@ def others(args, rank, dev, local, peak):
                 "torch_cat_of_the_levels_ms": r4["ms_cat"],
                 "note": "the concatenated layout pays value's step PLUS torch_cat_of_the_levels_ms (Model.py:234-235) "
                         "and the same again in backward"})
+    r8 = time_resident(dev)
+    out.append({"workload": "train head, batch 256, RESIDENT gradient tensors (ssdhead_ctx_multibox_loss_dev_resident: the "
+                            "caller keeps grad_loc / grad_conf from step to step; every step retracts the previous step's "
+                            "~4 Npos rows per image and writes its own - no dense zero background)",
+                "images_per_s": 256 / (r8["ms_step"] * 1e-3), "ms_per_step": r8["ms_step"],
+                "tensors_equal_the_dense_step_bit_for_bit": r8["equals_dense_step"],
+                "note": "234 MB fewer HBM writes per step, yet only a few us faster: without the zero-fill the streaming kernel "
+                        "is bound by its fused match + softmax instruction stream (~72 us, IPC 2.3 at 18 warps per SM), "
+                        "just under the 78 us the dense step needs for its HBM traffic"})
+    if not r8["equals_dense_step"]:
+        raise SystemExit("bench.py: the resident gradient tensors differ from the dense step's")
     for b5, host in ((256, False), (256, True), (32, False)):
         r5 = time_dropin(dev, b5, steps=100, host_lists=host)
         out.append({"workload": f"drop-in surface: Losses.ssd((loc, conf), classes, bboxes) + (l1 + l2).backward(), batch {b5}, "

@@ -1,13 +1,17 @@
 """Join an ncu source-page CSV (SASS view) with nvdisasm line info: warp-stall samples per CUDA source line.
 
-usage: ncu_lines.py <report.ncu-rep> <cubin> <kernel name substring> [min_samples]
+usage: ncu_lines.py <report.ncu-rep> <cubin> <kernel name substring> [min_samples] [kernel regex]
+(NCU_LAUNCH_SKIP=<n> selects the n-th launch of the report instead of a kernel-name regex: template instantiations
+share their base name)
 """
 import csv, re, subprocess, sys, collections
 
 rep, cubin, kname = sys.argv[1:4]
 kregex = sys.argv[5] if len(sys.argv) > 5 else kname
 min_s = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kregex], capture_output=True, text=True).stdout
+import os
+sel = ["--launch-skip", os.environ["NCU_LAUNCH_SKIP"], "--launch-count", "1"] if os.environ.get("NCU_LAUNCH_SKIP") else ["-k", "regex:" + kregex]
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
 hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
