@@ -368,8 +368,9 @@ int ssdhead_ctx_multibox_loss_dev(ssdhead_ctx* ctx, const float* loc_dev, const 
 /* ssdhead_ctx_multibox_loss_dev with RESIDENT gradient tensors (ssdhead_multibox_step_resident; after ssdhead_ctx_xchg_import
  * the sharded step).  The context owns the rows workspace and remembers the two tensors.  fresh != 0: the context
  * zero-fills grad_loc [B,P,4] / grad_conf [B,P,C] and forgets the previous rows first (first call, new tensors, or
- * after anybody else wrote them); fresh == 0: the tensors must be the ones of the previous call (else SSDHEAD_E_STATE)
- * and hold what that call left in them. */
+ * after anybody else wrote them); fresh == 0: the tensors must be the ones of the previous call and B at most the B
+ * of the last fresh call - only that many images were zero-filled - (else SSDHEAD_E_STATE), and they must hold what
+ * the previous call left in them. */
 int ssdhead_ctx_multibox_loss_dev_resident(ssdhead_ctx* ctx, const float* loc_dev, const float* conf_dev,
                                   const float* gt_xyxy_dev, const float* gt_cls_dev, const int32_t* gt_off_dev,
                                   int B, int sumG, int neg_ratio, float pos_iou,

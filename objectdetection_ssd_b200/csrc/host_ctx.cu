@@ -198,6 +198,7 @@ struct ssdhead_ctx {
     void* ws_rows;
     size_t ws_rows_bytes;
     float *res_grad_loc, *res_grad_conf;
+    int res_B;                              // images of the two tensors that were zero-filled at the hand-over
     size_t ws_match_bytes, ws_loss_bytes, ws_loss_total, ws_detect_bytes;
     // detect outputs (host-buffer path)
     float *det_boxes, *det_prob;
@@ -462,9 +463,9 @@ int ssdhead_ctx_multibox_loss_dev_resident(ssdhead_ctx* c, const float* loc, con
         SSD_CHECK_CUDA(cudaMemsetAsync(c->ws_rows, 0, c->ws_rows_bytes, st));
         SSD_CHECK_CUDA(cudaMemsetAsync(grad_loc, 0, (size_t)B * c->P * 4 * sizeof(float), st));
         SSD_CHECK_CUDA(cudaMemsetAsync(grad_conf, 0, (size_t)B * c->P * c->C * sizeof(float), st));
-        c->res_grad_loc = grad_loc; c->res_grad_conf = grad_conf;
-    } else if (grad_loc != c->res_grad_loc || grad_conf != c->res_grad_conf) {
-        return SSDHEAD_E_STATE;                          // not the tensors the rows workspace describes
+        c->res_grad_loc = grad_loc; c->res_grad_conf = grad_conf; c->res_B = B;
+    } else if (grad_loc != c->res_grad_loc || grad_conf != c->res_grad_conf || B > c->res_B) {
+        return SSDHEAD_E_STATE;                          // not the tensors the rows workspace describes, or images beyond the clean part
     }
     { const int zr = ctx_loss_ws_for(c, B, st); if (zr) return zr; }
     const bool sharded = c->xchg_R > 1;

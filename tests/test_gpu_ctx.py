@@ -230,3 +230,17 @@ def test_resident_gradient_tensors_equal_the_dense_step():
                                                         gl_res.data_ptr(), other.data_ptr(), 0, st)
     assert rc == -5
     ctx.close()
+    # a batch larger than the one the tensors were handed over with: refused as well (only that many images are clean)
+    ctx = SSDHeadContext(pri.numpy(), max_batch=maxB)
+    _, loc, conf, gb, gc, gx, gcl, off = _inputs(40, 4)
+    tl, tcf, tgx, tgc, toff = d(loc), d(conf), d(gx), d(gcl), d(off)
+    ctx.loss_dev_resident(tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(), toff.data_ptr(), 4, int(off[-1]),
+                          sums_r.data_ptr(), loss_r.data_ptr(), gl_res.data_ptr(), gc_res.data_ptr(), st, fresh=True)
+    _, loc, conf, gb, gc, gx, gcl, off = _inputs(41, 8)
+    tl, tcf, tgx, tgc, toff = d(loc), d(conf), d(gx), d(gcl), d(off)
+    rc = ctx.lib.ssdhead_ctx_multibox_loss_dev_resident(ctx._h, tl.data_ptr(), tcf.data_ptr(), tgx.data_ptr(), tgc.data_ptr(),
+                                                        toff.data_ptr(), 8, int(off[-1]), 3, 0.5, sums_r.data_ptr(), loss_r.data_ptr(),
+                                                        gl_res.data_ptr(), gc_res.data_ptr(), 0, st)
+    assert rc == -5
+    torch.cuda.synchronize()
+    ctx.close()
