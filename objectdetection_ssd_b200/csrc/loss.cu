@@ -6,7 +6,7 @@
 // The path is therefore split into one streaming kernel and one small per-image kernel:
 //
 //   ce_stream_kernel   persistent CTAs, one producer warp + 8 consumer warps.  The producer moves
-//                      256-row tiles of conf (21 504 B) into a 4-stage shared-memory ring with 1-D
+//                      256-row tiles of conf (21 504 B) into a 2-stage shared-memory ring with 1-D
 //                      TMA bulk copies (mbarrier full/empty pipeline) and, from a zeroed tile in
 //                      shared memory, bulk-stores the zero background of grad_conf / grad_loc.
 //                      Consumers do thread-per-row log-softmax out of shared memory (row stride 21
@@ -329,7 +329,25 @@ match_finalize_kernel(const float* __restrict__ gt_cls, const int* __restrict__ 
 }
 
 constexpr int CE_ROWS = 256;                      // rows per tile = consumer threads
-constexpr int CE_STAGES = 4;
+// Ring depth, resident CTAs per SM and zero-tile size of the streaming kernel (compile-time: tools/variants.py builds and
+// times alternatives).  Measured on B200 at B=256 / 128 (step, us): 4 stages + a whole zeroed tile (round 1) 106.6 / 66.4;
+// 3 stages 104.4 / 64.4; 2 stages + a 64-row zero tile 103.6 / 62.8 (two CTAs x two 21.5 KB tiles in flight per SM
+// still cover HBM's latency-bandwidth product, and the smaller shared-memory footprint - 97 KB instead of 215 KB per SM -
+// leaves the L1 to the match's loads); three CTAs per SM (72-register cap) 111.1.  Staging the tile's prior boxes through
+// the ring as well changed nothing at any depth.
+#ifndef SSDHEAD_CE_STAGES
+#define SSDHEAD_CE_STAGES 2
+#endif
+#ifndef SSDHEAD_CE_CTAS
+#define SSDHEAD_CE_CTAS 2
+#endif
+#ifndef SSDHEAD_CE_ZERO_ROWS
+#define SSDHEAD_CE_ZERO_ROWS 64
+#endif
+constexpr int CE_STAGES = SSDHEAD_CE_STAGES;      // stages of the conf ring
+constexpr int CE_CTAS = SSDHEAD_CE_CTAS;          // resident CTAs per SM the kernel is built for
+constexpr int CE_ZERO_ROWS = SSDHEAD_CE_ZERO_ROWS;// rows of the zeroed tile the gradient background is bulk-stored from
+static_assert(CE_ZERO_ROWS * 21 * 4 >= 256 * 16 && (CE_ZERO_ROWS * 21 * 4) % 16 == 0, "the zero tile must cover one tile of loc rows");
 constexpr int CE_THREADS = CE_ROWS + 32;          // + one producer warp
 
 // Head outputs given PER PYRAMID LEVEL: the reference permutes every conv output to NHWC and
@@ -372,6 +390,7 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
                const FusedMatch& fm, const LevelTab* __restrict__ lvp)
 {
     constexpr uint32_t TILE_BYTES = CE_ROWS * C * 4;
+    constexpr uint32_t ZERO_BYTES = CE_ZERO_ROWS * C * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[CE_STAGES];
     __shared__ __align__(8) uint64_t s_empty[CE_STAGES];
@@ -387,7 +406,7 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
         mbar_fence_init();
     }
     if (ZERO_FILL) {
-        for (int i = t; i < (int)(TILE_BYTES / 16); i += CE_THREADS)
+        for (int i = t; i < (int)(ZERO_BYTES / 16); i += CE_THREADS)
             reinterpret_cast<float4*>(zero_tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async_smem();
     }
@@ -419,7 +438,8 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
                 mbar_expect_tx(&s_full[s], nr * C * 4);
                 bulk_g2s(smem_raw + (size_t)s * TILE_BYTES, src, nr * C * 4, &s_full[s]);
                 if (ZERO_FILL) {
-                    bulk_s2g(gc, zero_tile, nr * C * 4);
+                    for (uint32_t o = 0; o < nr * C * 4; o += ZERO_BYTES)       // the conf rows' background in zero-tile sized pieces
+                        bulk_s2g(reinterpret_cast<unsigned char*>(gc) + o, zero_tile, min(ZERO_BYTES, nr * C * 4 - o));
                     bulk_s2g(gl, zero_tile, nr * 16);
                     bulk_commit();
                 }
@@ -531,7 +551,7 @@ ce_stream_body(const float* __restrict__ conf, float* __restrict__ ce_out,
 }
 
 template <int C, bool ZERO_FILL, bool MATCH>
-__global__ void __launch_bounds__(CE_THREADS, 2)
+__global__ void __launch_bounds__(CE_THREADS, CE_CTAS)
 ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
                  float* __restrict__ grad_conf, float* __restrict__ grad_loc, long long total_rows, int use_tma,
                  const FusedMatch fm)
@@ -541,7 +561,7 @@ ce_stream_kernel(const float* __restrict__ conf, float* __restrict__ ce_out,
 
 // the same kernel reading / zero-filling per-level tensors in place (no concatenated [B,P,*] tensors exist)
 template <int C, bool ZERO_FILL>
-__global__ void __launch_bounds__(CE_THREADS, 2)
+__global__ void __launch_bounds__(CE_THREADS, CE_CTAS)
 ce_stream_levels_kernel(float* __restrict__ ce_out, long long total_rows, const FusedMatch fm, const __grid_constant__ LevelTab lv)
 {
     ce_stream_body<C, ZERO_FILL, true, true>(nullptr, ce_out, nullptr, nullptr, total_rows, 1, fm, &lv);
@@ -1344,12 +1364,12 @@ static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, floa
                             const FusedMatch& fm, cudaStream_t st)
 {
     constexpr size_t tile = (size_t)CE_ROWS * C * 4;
-    const size_t smem_ce = tile * CE_STAGES + (GRADS ? tile : 0);
+    const size_t smem_ce = tile * CE_STAGES + (GRADS ? (size_t)CE_ZERO_ROWS * C * 4 : 0);
     auto kce = ce_stream_kernel<C, GRADS, MATCH>;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ce));
     const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(grad_conf) && aligned16(grad_loc)))) ? 1 : 0;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS;
-    const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
+    const int grid_ce = (int)std::min<long long>(tiles, (long long)CE_CTAS * num_sms());
     SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, conf, ce, grad_conf, grad_loc, rows, use_tma, fm));
     count_launch();
     return 0;
@@ -1591,12 +1611,12 @@ static int multibox_step_levels_impl(const LevelTab& lv, const FusedMatch& fm, M
 {
     constexpr int C = 21;
     constexpr size_t tile = (size_t)CE_ROWS * C * 4;
-    const size_t smem_ce = tile * CE_STAGES + (GRADS ? tile : 0);
+    const size_t smem_ce = tile * CE_STAGES + (GRADS ? (size_t)CE_ZERO_ROWS * C * 4 : 0);
     auto kce = ce_stream_levels_kernel<C, GRADS>;
     SSD_CHECK_CUDA(cudaFuncSetAttribute(kce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ce));
     const long long rows = (long long)B * P;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS + lv.n;
-    const int grid_ce = (int)std::min<long long>(tiles, 2LL * num_sms());
+    const int grid_ce = (int)std::min<long long>(tiles, (long long)CE_CTAS * num_sms());
     LevelTab lt = lv;
     {
         // stride ~ 0.618 T, coprime with T: consecutive visits land in different levels in proportion to their sizes
