@@ -33,8 +33,9 @@
 extern "C" {
 #endif
 
-#define SSDHEAD_ABI_VERSION 3   /* 2: sparse gradient return (ssdhead_mine_sparse, ssdhead_ctx_multibox_loss_host_sparse);
-                                   3: resident gradient tensors (ssdhead_multibox_step_resident, ssdhead_ctx_multibox_loss_dev_resident) */
+#define SSDHEAD_ABI_VERSION 4   /* 2: sparse gradient return (ssdhead_mine_sparse, ssdhead_ctx_multibox_loss_host_sparse);
+                                   3: resident gradient tensors (ssdhead_multibox_step_resident, ssdhead_ctx_multibox_loss_dev_resident);
+                                   4: ssdhead_detect_fallbacks (short-list route of the detect kernels; larger detect workspace) */
 
 #define SSDHEAD_E_BADARG      (-1)  /* null pointer / negative size */
 #define SSDHEAD_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for */
@@ -257,7 +258,16 @@ int ssdhead_scale_grads(float* grad_loc_dev, size_t n_loc, float* grad_conf_dev,
  * output is identical to the reference's full per-class sweeps.
  * Outputs: out_boxes [B,top_k,4], out_prob [B,top_k], out_cls int32 [B,top_k],
  *          out_prior int32 [B,top_k] (prior id of each detection; nullable), out_cnt int32 [B].
- * Two kernels (softmax/threshold/candidate keys; per-image slice sort + class-parallel NMS + output).
+ * Kernels (short-list route, the default): a sampling kernel picks a score floor per image (>= min_score)
+ * above which ~1600 candidates are expected; a persistent streaming kernel lists only the candidates above
+ * it; the sweep kernel (per-image slice sort + class-parallel NMS + output) runs on that short list.  The
+ * short list decides the output exactly when the sweep keeps top_k + 1 boxes inside it or the floor never
+ * rose above min_score (a candidate's fate depends only on higher-scored candidates); for any other image
+ * the sweep CTA lists the image again with the floor at min_score and sweeps the full list, so the output
+ * never depends on the floor.  ssdhead_detect_fallbacks reports how many images of the last call needed
+ * that.  The exhaustive route (two kernels: every candidate >= min_score listed, then the sweep) serves
+ * calls with 0 < max_candidates < P, and every call when SSDHEAD_DETECT_SHORTLIST=0 is set in the
+ * environment; only this route can report an overflowed cap (out_cnt[b] = -1).
  * P <= 131072, top_k <= ~1400.  Probabilities given to the _from_scores twin must be >= 0.
  * The workspace must be zero-filled before its FIRST use; every call leaves its counters zeroed. */
 int ssdhead_detect(const float* loc_dev, const float* conf_dev, const float* pri_cxcywh_dev,
@@ -273,6 +283,13 @@ int ssdhead_detect_from_scores(const float* boxes_cxcywh_dev, const float* probs
                                const float* img_wh_dev, int max_candidates,
                                float* out_boxes_dev, float* out_prob_dev, int32_t* out_cls_dev, int32_t* out_prior_dev,
                                int32_t* out_cnt_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Number of images of the LAST ssdhead_detect* call on this workspace (same B, P, C, max_candidates) that the
+ * short list did not decide and that were listed in full by their sweep CTA (0 .. B); blocks on `stream`.  A
+ * caller that sees most images counted (heavy suppression: fewer than top_k survivors among the ~1600 best
+ * candidates) may prefer SSDHEAD_DETECT_SHORTLIST=0.  No reference counterpart (a property of this implementation). */
+int ssdhead_detect_fallbacks(const void* ws_dev, size_t ws_bytes, int B, int P, int C, int max_candidates,
+                             int32_t* host_count, void* stream);
 
 /* ---- evaluation: get_map(), Util.py:783-885 (VOC 11-point interpolated AP; consumer of the detect output) -------
  * Detections and ground truth are packed image-major with int32 offsets [num_images+1] (det_off, gt_off).  Per class:

@@ -13,7 +13,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libssdhead.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 WS_MATCH, WS_LOSS, WS_DETECT, WS_NMS, WS_ROWS = 0, 1, 2, 3, 4
 E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN, E_STATE = -1, -2, -3, -4, -5
 
@@ -55,6 +55,7 @@ SIGNATURES = {
     "ssdhead_finish_loss": (_i, [_vp, _vp, _vp, _vp]),
     "ssdhead_scale_grads": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "ssdhead_detect": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdhead_detect_fallbacks": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp]),
     "ssdhead_detect_from_scores": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdhead_voc_ap_workspace_bytes": (_sz, [_i, _i, _i]),
     "ssdhead_voc_ap": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),

@@ -107,6 +107,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -185,7 +188,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
 {
-    static const int mask = getenv("SSDHEAD_PDL") ? atoi(getenv("SSDHEAD_PDL")) : 13;   // 1 CE stream, 2 finaliser, 4 mine, 8 detect; measured: CE + mine best, chaining the finaliser (2) is slower
+    static const int mask = getenv("SSDHEAD_PDL") ? atoi(getenv("SSDHEAD_PDL")) : 253;  // 1 CE stream, 2 finaliser, 4 mine; detect: 8 / 32 exhaustive score / sweep, 16 fused short-list kernel, 64 / 128 fallback score / sweep, 256 sampling kernel (off: 40 us slower at batch 256); measured: CE + mine best, chaining the finaliser (2) is slower
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

@@ -12,6 +12,10 @@
 // formulation produces can never reach the output.  If the list runs out with <= top_k boxes kept the output is
 // the class-major concatenation (Losses.py:71-73), produced by a stable partition of the kept list by class.
 //
+// Two routes with identical outputs.  The SHORT-LIST route (default; detect_floor_kernel + detect_stream_kernel +
+// detect_sweep_kernel, described at SAMPLE_STRIDE below) lists only the candidates above a sampled score floor and falls
+// back, per image and inside the sweep kernel, to the full list when that was not enough.  The EXHAUSTIVE route
+// (SSDHEAD_DETECT_SHORTLIST=0, or a max_candidates cap below P) lists every candidate:
 //   detect_score_kernel  grid (row tiles, B), 256 rows per CTA: the tile's conf rows arrive in shared memory with one
 //                        1-D TMA bulk copy (plain loads when unaligned), one thread per prior does the softmax and
 //                        appends a 64-bit key (prob bits << 32 | ~(class << 24 | prior)) to the image's candidate list
@@ -61,6 +65,11 @@ struct DetectWs {
     unsigned int* dir_base;        // [B][T][2] start of the chunk in the image's list, keys in the chunk
     unsigned int* cand_cnt;        // [B]       zero on entry, zero on exit
     unsigned int* overflow;        // [B]       zero on entry, zero on exit
+    // short-list route (score floor from a sample of the rows)
+    float* floor;                  // [B]       score floor of the image (>= min_score), rewritten by every call
+    unsigned int* hist;            // [B][CBINS] keys of the short list per coarse rank bin; zero on entry, zero on exit
+    unsigned int* flag_cnt;        // [1]       images whose short list did not decide the output (reset by the next call's sampling kernel)
+    unsigned int* work;            // [2]       next score item, CTAs that left the stream kernel; zero on entry, zero on exit
 };
 
 static inline int detect_cap_image(int P, int C, int n) { return (C - 1) * (n > 0 ? std::min(n, P) : P); }
@@ -80,6 +89,11 @@ static size_t detect_ws_layout(int B, int P, int C, int n, DetectWs* w, void* ba
     void* p4 = take((size_t)B * T * 8);
     void* p5 = take((size_t)B * 4);
     void* p6 = take((size_t)B * 4);
+    void* p7 = take((size_t)B * 4);
+    void* p8 = take((size_t)B * CBINS * 4);
+    void* p9 = take(16);
+    void* p10 = take(16);
+    if (w) { w->floor = (float*)p7; w->hist = (unsigned int*)p8; w->flag_cnt = (unsigned int*)p9; w->work = (unsigned int*)p10; }
     if (w) { w->cand = (unsigned long long*)p0; w->scr_a = (unsigned long long*)p1; w->scr_b = (unsigned long long*)p2;
              w->dir = (unsigned short*)p3; w->dir_base = (unsigned int*)p4;
              w->cand_cnt = (unsigned int*)p5; w->overflow = (unsigned int*)p6; }
@@ -114,14 +128,69 @@ struct DetLevels {
     int cnt[MAX_LEVELS];
     int start[MAX_LEVELS + 1];
     int tile0[MAX_LEVELS + 1];
+    int item0[MAX_LEVELS + 1];     // the same for the 480-row items of a sweep CTA that lists its image again
     const float* conf[MAX_LEVELS];
     const float* loc[MAX_LEVELS];
 };
 
 // ------------------------------------------------------------------------------------------------
+// Where the conf rows of score tile `tile` of image b sit: first prior of the tile (global order), rows, source pointer.
+template <int C, bool LEVELS>
+__device__ __forceinline__ void
+score_tile_rows(const float* __restrict__ conf, int P, int b, int tile, const DetLevels* __restrict__ dl,
+                int& r0, int& nrows, const float*& src)
+{
+    r0 = tile * SC_T;
+    nrows = min(SC_T, P - r0);
+    src = conf + ((size_t)b * P + r0) * C;
+    if (LEVELS) {
+        int l = 0;
+#pragma unroll
+        for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && tile >= dl->tile0[q]) l = q;
+        const int off = (tile - dl->tile0[l]) * SC_T;
+        nrows = min(SC_T, dl->cnt[l] - off);
+        r0 = dl->start[l] + off;
+        src = dl->conf[l] + ((size_t)b * dl->cnt[l] + off) * C;
+    }
+}
+
+// The same for the short-list route's items of ROWS rows (256: the score tiles; 480: a sweep CTA listing its image again).
+template <int C, bool LEVELS, int ROWS>
+__device__ __forceinline__ void
+item_rows(const float* __restrict__ conf, int P, int b, int j, const DetLevels* __restrict__ dl, int& r0, int& nrows, const float*& src)
+{
+    r0 = j * ROWS;
+    nrows = min(ROWS, P - r0);
+    src = conf + ((size_t)b * P + r0) * C;
+    if (LEVELS) {
+        const int* first = ROWS == SC_T ? dl->tile0 : dl->item0;
+        int l = 0;
+#pragma unroll
+        for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && j >= first[q]) l = q;
+        const int off = (j - first[l]) * ROWS;
+        nrows = min(ROWS, dl->cnt[l] - off);
+        r0 = dl->start[l] + off;
+        src = dl->conf[l] + ((size_t)b * dl->cnt[l] + off) * C;
+    }
+}
+// first prior (global order) of item j, rows given at run time
+template <bool LEVELS>
+__device__ __forceinline__ int item_first_row(const DetLevels* __restrict__ dl, int rows, int j)
+{
+    if (!LEVELS) return j * rows;
+    const int* first = rows == SC_T ? dl->tile0 : dl->item0;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && j >= first[q]) l = q;
+    return dl->start[l] + (j - first[l]) * rows;
+}
+
+// One score tile of image b in the EXHAUSTIVE route (every candidate >= min_score is listed).  s_bar is initialised by
+// the caller (count 1); `parity` is the phase this call waits for; T = score tiles per image.
 template <int C, bool FROM_SCORES, bool LEVELS>
 __device__ __forceinline__ void
-detect_score_body(const float* __restrict__ conf, int P, float min_score, int capI,
+detect_score_body(const int b, const int tile, const int T, uint64_t* s_bar_p, const uint32_t parity,
+                  const float* __restrict__ conf, int P, float min_score, int capI,
                   unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
                   unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
                   unsigned int* __restrict__ overflow, const DetLevels* __restrict__ dl)
@@ -136,32 +205,20 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     __shared__ unsigned int s_wtot[NW];
     __shared__ unsigned int s_wsum[NW];
     __shared__ unsigned int s_base;
-    __shared__ __align__(8) uint64_t s_bar;
-    const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    int r0 = tile * SC_T;                                   // first prior of the tile (global order)
-    int nrows = min(SC_T, P - r0);
-    const float* src = conf + ((size_t)b * P + r0) * C;
-    if (LEVELS) {
-        int l = 0;
-#pragma unroll
-        for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && tile >= dl->tile0[q]) l = q;
-        const int off = (tile - dl->tile0[l]) * SC_T;
-        nrows = min(SC_T, dl->cnt[l] - off);
-        r0 = dl->start[l] + off;
-        src = dl->conf[l] + ((size_t)b * dl->cnt[l] + off) * C;
-    }
+    uint64_t& s_bar = *s_bar_p;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int r0, nrows;
+    const float* src;
+    score_tile_rows<C, LEVELS>(conf, P, b, tile, dl, r0, nrows, src);
     const uint32_t bytes = (uint32_t)nrows * C * 4u;
     const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0;
 
-    if (bulk && t == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
     s_ch[t] = 0u;
     s_fill[t] = 0u;
-    pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
-    pdl_wait();                          // the previous call's sweep may still be reading the lists we overwrite
     __syncthreads();
     if (bulk) {
         if (t == 0) { mbar_expect_tx(&s_bar, bytes); bulk_g2s(s_conf, src, bytes, &s_bar); }
-        mbar_wait(&s_bar, 0u);
+        mbar_wait(&s_bar, parity);
     } else if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 7u) == 0) {
         // 8-byte aligned rows (e.g. an odd image of a level with an odd half-count of priors): float2 loads
         const float2* src2 = reinterpret_cast<const float2*>(src);
@@ -250,8 +307,8 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     if (t == 0) {
         const bool fits = chunk + total <= (unsigned)capI;
         s_base = fits ? chunk : 0xffffffffu;
-        dir_base[((size_t)b * gridDim.x + tile) * 2] = fits ? chunk : 0u;
-        dir_base[((size_t)b * gridDim.x + tile) * 2 + 1] = fits ? total : 0u;
+        dir_base[((size_t)b * T + tile) * 2] = fits ? chunk : 0u;
+        dir_base[((size_t)b * T + tile) * 2 + 1] = fits ? total : 0u;
         if (!fits) atomicOr(&overflow[b], 1u);                   // the whole chunk is dropped; out_cnt[b] becomes -1
     }
     __syncthreads();
@@ -263,7 +320,7 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     // the directory row of this chunk: keys before each rank bin (a chunk holds at most 20 x 256 keys: 16 bits).  Prefix sums
     // instead of counts: the sweep kernel gets a slice's position in the chunk with two loads, and the image's coarse
     // prefix sums are the column sums of the rows - no scan on its side
-    dir[((size_t)b * gridDim.x + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)(wb + hin - h) : (unsigned short)0;
+    dir[((size_t)b * T + tile) * CBINS + t] = base != 0xffffffffu ? (unsigned short)(wb + hin - h) : (unsigned short)0;
     __syncthreads();
     if (base != 0xffffffffu) {
         unsigned long long* seg = cand + (size_t)b * capI + base;
@@ -277,6 +334,21 @@ detect_score_body(const float* __restrict__ conf, int P, float min_score, int ca
     }
 }
 
+template <int C, bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_score_grid(const float* __restrict__ conf, int P, float min_score, int capI,
+                  unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
+                  unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
+                  unsigned int* __restrict__ overflow, const DetLevels* __restrict__ dl)
+{
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
+    pdl_wait();                          // the previous call's sweep may still be reading the lists we overwrite
+    detect_score_body<C, FROM_SCORES, LEVELS>(blockIdx.y, blockIdx.x, gridDim.x, &s_bar, 0u, conf, P, min_score, capI,
+                                              cand, cand_cnt, dir, dir_base, overflow, dl);
+}
+
 template <int C, bool FROM_SCORES>
 __global__ void __launch_bounds__(SC_T)
 detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int capI,
@@ -284,7 +356,7 @@ detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int 
                     unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
                     unsigned int* __restrict__ overflow)
 {
-    detect_score_body<C, FROM_SCORES, false>(conf, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, nullptr);
+    detect_score_grid<C, FROM_SCORES, false>(conf, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, nullptr);
 }
 
 template <int C>
@@ -294,7 +366,133 @@ detect_score_levels_kernel(int P, float min_score, int capI,
                            unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
                            unsigned int* __restrict__ overflow, const __grid_constant__ DetLevels dl)
 {
-    detect_score_body<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl);
+    detect_score_grid<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Short-list route.  At min_score = 0.01 an image has tens of thousands of candidates, and the sweep stops after a few
+// hundred of them: listing all of them is what made the score kernel issue-bound.
+//   detect_floor_kernel   looks at every SAMPLE_STRIDE-th row of an image and picks a score FLOOR (an edge of the coarse
+//                         rank bins, >= min_score) above which about SAMPLE_STRIDE x SAMPLE_TARGET candidates are expected.
+//   detect_stream_kernel  persistent, warp-specialised: a producer lane draws 256-row ITEMS from a global counter and moves
+//                         them into a two-stage ring with bulk copies (full/empty mbarriers); 8 consumer warps work on their
+//                         own 32 rows without any CTA-wide barrier - thread-per-row softmax (the exhaustive route's
+//                         arithmetic), class mask against the image's floor, one shared-memory atomic per warp for its
+//                         place in the item's key segment, keys straight to global memory.  No dense passes, no directory.
+//   detect_sweep_kernel   one CTA per image: the sweep of the exhaustive route on the short list.  A candidate's fate
+//                         depends only on higher-scored candidates, so if the sweep keeps top_k + 1 boxes inside the short
+//                         list - or the floor never rose above min_score - the output is the exhaustive route's, bit for
+//                         bit.  Otherwise the CTA lists the image AGAIN itself with the floor at min_score (the same
+//                         producer/consumer loop over its own items, 15 consumer warps) and sweeps the full list: the
+//                         output never depends on the floor, and nothing runs behind the kernel.
+// An item's keys go to a fixed segment of the image's list - 20 keys per row, at 20 x (first row) - so nothing can overflow.
+constexpr int SAMPLE_STRIDE = 35;     // coprime with the 4 / 6 priors per cell: every aspect ratio is sampled; SSD300: one row per thread
+constexpr int SAMPLE_TARGET = 46;     // sampled candidates above the floor: ~1600 listed keys per image
+constexpr int SCW = 8;                // consumer warps of the stream kernel: items of 256 rows (the score tiles of the exhaustive route)
+constexpr int RCW = NT / 32 - 1;      // consumer warps when a sweep CTA lists its image again: items of 480 rows
+static_assert(SCW * 32 == SC_T, "the stream kernel's items are the exhaustive route's score tiles");
+
+// row -> foreground probabilities p[0..NF), exactly the exhaustive route's arithmetic; returns the row's best one
+template <int C, bool FROM_SCORES>
+__device__ __forceinline__ float row_probs(const float* __restrict__ x, float (&e)[C], float& m, float& inv)
+{
+    constexpr int NF = C - 1;
+#pragma unroll
+    for (int q = 0; q < C; ++q) e[q] = x[q];
+    inv = 1.0f;
+    m = 0.0f;
+    if (!FROM_SCORES) {
+        m = e[0];
+#pragma unroll
+        for (int q = 1; q < C; ++q) m = fmaxf(m, e[q]);
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < C; ++q) { e[q] = fast_exp_ftz(__fsub_rn(e[q], m)); s = __fadd_rn(s, e[q]); }
+        inv = __fdiv_rn(1.0f, s);
+    }
+    float best = e[0];
+#pragma unroll
+    for (int q = 1; q < NF; ++q) best = fmaxf(best, e[q]);
+    return FROM_SCORES ? best : __fmul_rn(best, inv);          // rounding is monotone: max(e) * inv == max(e * inv)
+}
+// probability of class q of a row recomputed from the row (same operations => same bits as row_probs)
+template <bool FROM_SCORES>
+__device__ __forceinline__ float prob_again(const float* __restrict__ x, int q, float m, float inv)
+{
+    return FROM_SCORES ? x[q] : __fmul_rn(fast_exp_ftz(__fsub_rn(x[q], m)), inv);
+}
+
+template <int C, bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_floor_body(const float* __restrict__ conf, int P, float min_score, float* __restrict__ floor_out,
+                  unsigned int* __restrict__ flag_cnt, const DetLevels* __restrict__ dl)
+{
+    constexpr int NF = C - 1;
+    __shared__ unsigned int s_h[CBINS];
+    __shared__ unsigned int s_ws[SC_T / 32];
+    __shared__ int s_r;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    s_h[t] = 0u;
+    if (t == 0) s_r = CBINS;
+    pdl_wait();                          // FIRST: whoever starts behind this grid may rely on everything before it being complete
+    pdl_trigger();
+    if (b == 0 && t == 0) flag_cnt[0] = 0u;
+    __syncthreads();
+    for (int r = t * SAMPLE_STRIDE; r < P; r += SC_T * SAMPLE_STRIDE) {
+        const float* x = conf + ((size_t)b * P + r) * C;
+        if (LEVELS) {
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < MAX_LEVELS; ++q) if (q < dl->n && r >= dl->start[q]) l = q;
+            x = dl->conf[l] + ((size_t)b * dl->cnt[l] + (r - dl->start[l])) * C;
+        }
+        float e[C], m, inv;
+        const float best = row_probs<C, FROM_SCORES>(x, e, m, inv);
+        if (best >= min_score) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+                const float p = FROM_SCORES ? e[q] : __fmul_rn(e[q], inv);
+                if (p >= min_score) atomicAdd(&s_h[coarse_rank(__float_as_uint(p))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    // the first rank bin (from the top) at which the sampled candidates reach the target: its lower edge is the floor
+    const unsigned h = s_h[t];
+    unsigned incl = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_ws[warp] = incl;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SC_T / 32; ++w) if (w < warp) incl += s_ws[w];
+    if (incl >= (unsigned)SAMPLE_TARGET && incl - h < (unsigned)SAMPLE_TARGET) s_r = t;
+    __syncthreads();
+    if (t == 0) {
+        float F = min_score;             // too few candidates in the sample: list everything (the exhaustive semantics)
+        const int r = s_r;
+        if (r < CBINS - 1) {
+            const float edge = __uint_as_float(((0x3f800000u >> 18) - (unsigned)r) << 18);
+            if (edge > min_score) F = edge;
+        }
+        floor_out[b] = F;
+    }
+}
+
+template <int C, bool FROM_SCORES>
+__global__ void __launch_bounds__(SC_T)
+detect_floor_kernel(const float* __restrict__ conf, int P, float min_score, float* __restrict__ floor_out, unsigned int* __restrict__ flag_cnt)
+{
+    detect_floor_body<C, FROM_SCORES, false>(conf, P, min_score, floor_out, flag_cnt, nullptr);
+}
+template <int C>
+__global__ void __launch_bounds__(SC_T)
+detect_floor_levels_kernel(int P, float min_score, float* __restrict__ floor_out, unsigned int* __restrict__ flag_cnt, const __grid_constant__ DetLevels dl)
+{
+    detect_floor_body<C, false, true>(nullptr, P, min_score, floor_out, flag_cnt, &dl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -767,9 +965,28 @@ static size_t nms_smem_bytes(int NF, int top_k, int T)
     return (off + 15) & ~(size_t)15;
 }
 
-template <bool FROM_SCORES, bool LEVELS>
-__device__ __forceinline__ void
-detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
+// FLOOR: the short-list route (the image's keys sit in one fixed segment per score item + a coarse histogram) instead
+// of the exhaustive route's chunks and directory; fl.* are used by it alone.
+struct FloorArgs {
+    float* floor;                  // [B]
+    unsigned int* hist;            // [B][CBINS]
+    unsigned int* icnt;            // [B][items per image] keys listed by each item
+    unsigned int* work;            // [2]
+    unsigned int* flag_cnt;        // [1] images listed twice (statistic)
+    float min_score;
+};
+// how an image's rows were cut into items when its short list was written
+struct ItemLayout {
+    int rows;                      // rows per item
+    int n;                         // items per image
+    bool raised;                   // the list holds only candidates above a floor > min_score
+};
+
+// Returns false when the image was not decided (FLOOR only; nothing has been written then).
+template <bool FROM_SCORES, bool LEVELS, bool FLOOR>
+__device__ __forceinline__ bool
+detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
+                  const DetLevels* __restrict__ dl, const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
                   unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a,
                   unsigned long long* __restrict__ scr_b, const unsigned short* __restrict__ dir,
                   const unsigned int* __restrict__ dir_base, unsigned int* __restrict__ cand_cnt,
@@ -804,12 +1021,13 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     __shared__ unsigned int s_CS[CBINS + 1];
     __shared__ unsigned int s_col[CBINS];
     __shared__ int s_rc1;
+    __shared__ unsigned int s_gcnt;
 
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t < CBINS) s_col[t] = 0u;
     if (t < 32) s_kcnt[t] = 0;
     if (t == 0) s_CS[CBINS] = 0u;
-    pdl_wait();                                              // the score kernel's lists and directory are complete
+    __syncthreads();
     PHASE(0);
     const unsigned long long* seg = cand + (size_t)b * capI;
     const unsigned short* gdir = dir + (size_t)b * T * CBINS;
@@ -819,6 +1037,19 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
     int* oc = out_cls + (size_t)b * top_k;
     int* oi = out_prior ? out_prior + (size_t)b * top_k : nullptr;
 
+    if (FLOOR) {
+        // the image's coarse prefix sums from the histogram the listing counted its keys into (left zeroed)
+        unsigned h = 0u;
+        if (t < CBINS) {
+            h = (unsigned)ld_cg_s32(reinterpret_cast<const int*>(fl.hist) + (size_t)b * CBINS + t);
+            if (h) fl.hist[(size_t)b * CBINS + t] = 0u;
+        }
+        unsigned total;
+        const unsigned ex = block_excl_scan(h, ss.wsum, total);
+        if (t < CBINS) s_CS[t] = ex;
+        if (t == 0) s_CS[CBINS] = total;
+        __syncthreads();
+    } else
     // column sums of the directory rows (per-chunk prefix sums) = the image's coarse prefix sums: CS[r] = number of keys in
     // rank bins < r (bin 0 = highest probabilities); CS[CBINS] = all keys of the image
     {
@@ -888,6 +1119,24 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         const unsigned long long kmin0 = pre ? (unsigned long long)((top18 - (rc1 - 1)) << 18) << 32 : 0ull;
         const BinMap bin0(kmin0, kmax0);
         if (pre) for (int i = t; i < FBINS; i += NT) s_cnt[i] = 0u;
+        if (FLOOR) {
+            // the short list is unordered: one pass over its keys picks the slice's (the sort below orders them)
+            if (t == 0) s_gcnt = 0u;
+            __syncthreads();
+            for (int j = warp; j < il.n; j += NT / 32) {
+                const int n_j = ld_cg_s32(reinterpret_cast<const int*>(fl.icnt) + (size_t)b * T + j);
+                const unsigned long long* sj = seg + (size_t)item_first_row<LEVELS>(dl, il.rows, j) * NF;
+                for (int i = lane; i < n_j; i += 32) {
+                    const unsigned long long k = ld_cg_u64(sj + i);
+                    const int r = coarse_rank((unsigned)(k >> 32));
+                    if (r >= rc0 && r < rc1) {
+                        X[atomicAdd(&s_gcnt, 1u)] = k;
+                        if (pre) atomicAdd(&s_cnt[bin0(k)], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
         // where the slice sits in every chunk: chunks are ordered by rank bin, so it is one contiguous piece per chunk -
         // from the chunk's prefix sums, two loads
         for (int c = t; c < T; c += NT) {
@@ -915,6 +1164,7 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
             }
         }
         __syncthreads();
+        }
         PHASE(2);
         if (in_smem) {
             // boxes are decoded as soon as a key's final position is known
@@ -934,6 +1184,8 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         PHASE(5);
     }
 
+    if (FLOOR && K <= top_k && il.raised) return false;     // the short list ran out before top_k + 1 boxes were kept and
+                                                             // candidates below the floor exist: not decided here
     float sx = 1.0f, sy = 1.0f;
     if (img_wh) { sx = img_wh[2 * b]; sy = img_wh[2 * b + 1]; }
     auto emit = [&](int slot, int i) {
@@ -962,13 +1214,19 @@ detect_nms_body(const DetLevels* __restrict__ dl, const float4* __restrict__ loc
         }
     }
     if (t == 0) {
-        out_cnt[b] = ld_cg_s32(reinterpret_cast<const int*>(overflow) + b) ? -1 : nout;     // -1: the candidate list exceeded the caller's cap
-        overflow[b] = 0u;
-        cand_cnt[b] = 0u;
+        if (FLOOR) {
+            out_cnt[b] = nout;
+        } else {
+            out_cnt[b] = ld_cg_s32(reinterpret_cast<const int*>(overflow) + b) ? -1 : nout;     // -1: the candidate list exceeded the caller's cap
+            overflow[b] = 0u;
+            cand_cnt[b] = 0u;
+        }
     }
     PHASE(6);
+    return true;
 }
 
+// The same sweep, as two kernels' entry: the exhaustive route's (lists and directory from detect_score_kernel) ...
 template <bool FROM_SCORES>
 __global__ void __launch_bounds__(NT, 2)
 detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
@@ -980,8 +1238,9 @@ detect_nms_kernel(const float4* __restrict__ loc_or_boxes, const float4* __restr
                   float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                   int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
-    detect_nms_body<FROM_SCORES, false>(nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                        img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+    pdl_wait();                                              // the score kernel's lists and directory are complete
+    detect_nms_body<FROM_SCORES, false, false>(blockIdx.x, FloorArgs{}, ItemLayout{}, nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base,
+                                               cand_cnt, overflow, img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
 __global__ void __launch_bounds__(NT, 2)
@@ -994,8 +1253,225 @@ detect_nms_levels_kernel(const __grid_constant__ DetLevels dl, const float4* __r
                          float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
                          int* __restrict__ out_prior, int* __restrict__ out_cnt)
 {
-    detect_nms_body<false, true>(&dl, nullptr, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base, cand_cnt, overflow,
-                                 img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+    pdl_wait();
+    detect_nms_body<false, true, false>(blockIdx.x, FloorArgs{}, ItemLayout{}, &dl, nullptr, pri_cxcywh, cand, scr_a, scr_b, dir, dir_base,
+                                        cand_cnt, overflow, img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+
+// ... and the short-list route's.  Scoring loop shared by detect_stream_kernel (items of all images from a global counter,
+// NCW = 8 consumer warps) and by a sweep CTA that lists its image again (its own items, NCW = 15): warp NCW's lane 0 is
+// the producer, warps 0 .. NCW-1 consume.  `ring`: 2 x NCW x 32 rows of shared memory.  Items w in [w_begin, w_end) drawn
+// from *counter (global) or counted privately (counter == nullptr); item w = image w / ipi, item w % ipi of that image.
+template <int C, bool FROM_SCORES, bool LEVELS, int NCW>
+__device__ __forceinline__ void
+score_items(unsigned char* ring, unsigned int* counter, const int w_begin, const int w_end, const int ipi, const bool wait_pdl,
+            const float* __restrict__ floor, const float f_const,
+            const float* __restrict__ conf, const int P, const DetLevels* __restrict__ dl,
+            unsigned long long* __restrict__ cand, const int capI, unsigned int* __restrict__ icnt, const int icnt_stride,
+            unsigned int* __restrict__ hist)
+{
+    constexpr int NF = C - 1;
+    constexpr int ROWS = NCW * 32;
+    constexpr uint32_t STAGE_BYTES = ROWS * C * 4;
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ __align__(8) uint64_t s_empty[2];
+    __shared__ int s_desc[2];                                // item in the stage, or -1: no more items
+    __shared__ unsigned int s_icnt[2];                       // keys the stage's item has listed so far
+    __shared__ int s_it[2];                                  // item whose key count is still to be published, per stage
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], NCW); mbar_init(&s_empty[1], NCW);
+        mbar_fence_init();
+        s_icnt[0] = 0u; s_icnt[1] = 0u; s_it[0] = -1; s_it[1] = -1;
+    }
+    __syncthreads();
+    int st = 0;
+    uint32_t ph = 0u;
+    if (warp == NCW) {
+        if (lane == 0) {
+            unsigned wnext = counter ? atomicAdd(counter, 1u) : (unsigned)w_begin;
+            for (;;) {
+                mbar_wait(&s_empty[st], ph ^ 1u);            // the stage is free: the item that was in it is complete
+                const int fin = s_it[st];
+                if (fin >= 0) icnt[(size_t)(fin / ipi) * icnt_stride + fin % ipi] = s_icnt[st];
+                s_it[st] = -1;
+                s_icnt[st] = 0u;
+                const int d = (int)wnext < w_end ? (int)wnext : -1;
+                s_desc[st] = d;
+                if (d < 0) { mbar_arrive(&s_full[st]); break; }
+                int r0, nrows; const float* src;
+                item_rows<C, LEVELS, ROWS>(conf, P, d / ipi, d % ipi, dl, r0, nrows, src);
+                const uint32_t bytes = (uint32_t)nrows * C * 4u;
+                if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0) {
+                    mbar_expect_tx(&s_full[st], bytes);
+                    bulk_g2s(ring + (size_t)st * STAGE_BYTES, src, bytes, &s_full[st]);
+                } else {
+                    mbar_arrive(&s_full[st]);                // rows not 16-byte aligned: the consumers read them from global memory
+                }
+                s_it[st] = d;
+                wnext = counter ? atomicAdd(counter, 1u) : wnext + 1u;     // the next index travels while this item is processed
+                st ^= 1; if (st == 0) ph ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else if (warp < NCW) {
+        if (wait_pdl) pdl_wait();                            // the floors are final
+        for (;;) {
+            mbar_wait(&s_full[st], ph);
+            const int d = s_desc[st];
+            if (d < 0) break;
+            const int b = d / ipi, j = d % ipi;
+            const float F = floor ? __ldcg(floor + b) : f_const;
+            int r0, nrows; const float* src;
+            item_rows<C, LEVELS, ROWS>(conf, P, b, j, dl, r0, nrows, src);
+            const uint32_t bytes = (uint32_t)nrows * C * 4u;
+            const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0;
+            const int row = warp * 32 + lane;
+            const float* x = bulk ? reinterpret_cast<const float*>(ring + (size_t)st * STAGE_BYTES) + row * C : src + (size_t)row * C;
+            unsigned cmask = 0u;
+            float m = 0.0f, inv = 1.0f;
+            if (row < nrows) {
+                float e[C];
+                row_probs<C, FROM_SCORES>(x, e, m, inv);
+#pragma unroll
+                for (int q = 0; q < NF; ++q) cmask |= ((FROM_SCORES ? e[q] : __fmul_rn(e[q], inv)) >= F ? 1u : 0u) << q;
+            }
+            // the warp's place in the item's segment: one shared-memory atomic
+            const unsigned mine = (unsigned)__popc(cmask);
+            unsigned incl = mine;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned o = __shfl_up_sync(FULL, incl, dd);
+                if (lane >= dd) incl += o;
+            }
+            const unsigned wtotal = __shfl_sync(FULL, incl, 31);
+            if (wtotal) {
+                unsigned base = 0u;
+                if (lane == 31) base = atomicAdd(&s_icnt[st], wtotal);
+                base = __shfl_sync(FULL, base, 31);
+                unsigned long long* seg = cand + (size_t)b * capI + (size_t)r0 * NF + (base + incl - mine);
+                unsigned int* hb = hist + (size_t)b * CBINS;
+                while (cmask) {
+                    const int q = __ffs(cmask) - 1;
+                    cmask &= cmask - 1u;
+                    const float p = prob_again<FROM_SCORES>(x, q, m, inv);
+                    *seg++ = make_key(p, q, r0 + row);
+                    atomicAdd(&hb[coarse_rank(__float_as_uint(p))], 1u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);        // release: the warp's keys and its count are ordered before the producer's read
+            st ^= 1; if (st == 0) ph ^= 1u;
+        }
+    }
+    __syncthreads();                                         // every consumer warp has left: all items are complete
+    if (t == NCW * 32) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (s_it[q] >= 0) icnt[(size_t)(s_it[q] / ipi) * icnt_stride + s_it[q] % ipi] = s_icnt[q];
+    }
+    __syncthreads();
+}
+
+template <int C, bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_stream_body(const FloorArgs fl, const float* __restrict__ conf, const int B, const int P, const int ipi,
+                   const DetLevels* __restrict__ dl, unsigned long long* __restrict__ cand, const int capI, const int icnt_stride)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
+    // conf is final before this grid starts (the sampling kernel in front of it is an ordinary launch) and the previous call
+    // is complete: the producer starts at once, only the consumers wait for the floors
+    score_items<C, FROM_SCORES, LEVELS, SCW>(smem_raw, fl.work, 0, B * ipi, ipi, true, fl.floor, 0.0f, conf, P, dl, cand, capI, fl.icnt, icnt_stride, fl.hist);
+    // the last CTA to leave resets the work counters (every other CTA has drawn its last index by then)
+    if (threadIdx.x == 0) {
+        const unsigned e = atomicAdd(&fl.work[1], 1u);
+        if (e == gridDim.x - 1) { fl.work[0] = 0u; fl.work[1] = 0u; }
+    }
+}
+
+template <int C, bool FROM_SCORES>
+__global__ void __launch_bounds__((SCW + 1) * 32, 4)
+detect_stream_kernel(const FloorArgs fl, const float* __restrict__ conf, const int B, const int P, const int ipi,
+                     unsigned long long* __restrict__ cand, const int capI, const int icnt_stride)
+{
+    detect_stream_body<C, FROM_SCORES, false>(fl, conf, B, P, ipi, nullptr, cand, capI, icnt_stride);
+}
+template <int C>
+__global__ void __launch_bounds__((SCW + 1) * 32, 4)
+detect_stream_levels_kernel(const FloorArgs fl, const int B, const int P, const int ipi, const __grid_constant__ DetLevels dl,
+                            unsigned long long* __restrict__ cand, const int capI, const int icnt_stride)
+{
+    detect_stream_body<C, false, true>(fl, nullptr, B, P, ipi, &dl, cand, capI, icnt_stride);
+}
+
+template <int C, bool FROM_SCORES, bool LEVELS>
+__device__ __forceinline__ void
+detect_sweep_body(const FloorArgs fl, const float* __restrict__ conf, const int ipi_a, const int ipi_b,
+                  const DetLevels* __restrict__ dl, const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
+                  unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a, unsigned long long* __restrict__ scr_b,
+                  const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                  float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
+                  int* __restrict__ out_prior, int* __restrict__ out_cnt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();                                              // the stream kernel's short lists are complete
+    const ItemLayout la = {SC_T, ipi_a, __ldcg(fl.floor + b) > fl.min_score};
+    if (detect_nms_body<FROM_SCORES, LEVELS, true>(b, fl, la, dl, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, nullptr, nullptr, nullptr, nullptr,
+                                                   img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt))
+        return;
+    // Not decided: the short list ran out with at most top_k boxes kept and candidates below the floor exist.  List the
+    // image again with the floor at min_score - every candidate, as the exhaustive route does - and sweep that list.
+    if (threadIdx.x == 0) atomicAdd(fl.flag_cnt, 1u);
+    fence_proxy_async_smem();                                // the sweep wrote the ring's bytes with ordinary stores
+    __syncthreads();
+    score_items<C, FROM_SCORES, LEVELS, RCW>(smem_raw, nullptr, b * ipi_b, (b + 1) * ipi_b, ipi_b, false, nullptr, fl.min_score,
+                                             conf, P, dl, cand, capI, fl.icnt, T, fl.hist);
+    const ItemLayout lb = {RCW * 32, ipi_b, false};
+    detect_nms_body<FROM_SCORES, LEVELS, true>(b, fl, lb, dl, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, nullptr, nullptr, nullptr, nullptr,
+                                               img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+
+template <int C, bool FROM_SCORES>
+__global__ void __launch_bounds__(NT, 2)
+detect_sweep_kernel(const FloorArgs fl, const float* __restrict__ conf, const int ipi_a, const int ipi_b,
+                    const float4* __restrict__ loc_or_boxes, const float4* __restrict__ pri_cxcywh,
+                    unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a, unsigned long long* __restrict__ scr_b,
+                    const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                    float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
+                    int* __restrict__ out_prior, int* __restrict__ out_cnt)
+{
+    detect_sweep_body<C, FROM_SCORES, false>(fl, conf, ipi_a, ipi_b, nullptr, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b,
+                                             img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+template <int C>
+__global__ void __launch_bounds__(NT, 2)
+detect_sweep_levels_kernel(const FloorArgs fl, const int ipi_a, const int ipi_b, const __grid_constant__ DetLevels dl,
+                           const float4* __restrict__ pri_cxcywh,
+                           unsigned long long* __restrict__ cand, unsigned long long* __restrict__ scr_a, unsigned long long* __restrict__ scr_b,
+                           const float* __restrict__ img_wh, int P, int NF, int T, int capI, int top_k, float iou_thr,
+                           float4* __restrict__ out_boxes, float* __restrict__ out_prob, int* __restrict__ out_cls,
+                           int* __restrict__ out_prior, int* __restrict__ out_cnt)
+{
+    detect_sweep_body<C, false, true>(fl, nullptr, ipi_a, ipi_b, &dl, nullptr, pri_cxcywh, cand, scr_a, scr_b,
+                                      img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
+}
+
+// SSDHEAD_DETECT_SHORTLIST=0 forces the exhaustive route (developer switch: the two routes give identical outputs)
+static bool shortlist_enabled()
+{
+    const char* e = getenv("SSDHEAD_DETECT_SHORTLIST");          // read per call: tests compare the two routes in one process
+    return !e || atoi(e) != 0;
+}
+
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
 }
 
 template <bool FROM_SCORES>
@@ -1019,31 +1495,69 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     const size_t need = detect_ws_layout(B, P, C, n_cap, &w, ws);
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     const int capI = detect_cap_image(P, C, n_cap);
+    // the short-list route gives every row its 20 key slots in the image's list (a max_candidates below P rules it out)
+    const bool fast = shortlist_enabled() && capI == NF * P && (long long)B * T < (1ll << 30);
 
-    dim3 g1(T, B);
-    if (dl) {
-        SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
-                                  P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, *dl));
-    } else {
-        SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
-                                  conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
+    if (fast) {
+        const int ipi_a = T;                                                  // 256-row items = the score tiles
+        const int ipi_b = dl ? dl->item0[dl->n] : (P + RCW * 32 - 1) / (RCW * 32);
+        const FloorArgs fl = {w.floor, w.hist, w.dir_base, w.work, w.flag_cnt, min_score};
+        const size_t smem_stream = (size_t)2 * SCW * 32 * C * 4;
+        const size_t smem_sweep = std::max(smem_nms, (size_t)2 * RCW * 32 * C * 4);
+        int per_sm = 0;
+        // sample -> floor (an ordinary launch: everything in front of this call is complete when it starts, which is what
+        // lets the stream kernel's producers request conf at once); stream kernel: short lists; sweep kernel
+        if (dl) {
+            auto ks = detect_stream_levels_kernel<21>;
+            auto kw = detect_sweep_levels_kernel<21>;
+            SSD_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+            SSD_CHECK_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sweep));
+            SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, (SCW + 1) * 32, smem_stream));
+            if (per_sm < 1) return SSDHEAD_E_UNSUPPORTED;
+            const int grid = (int)std::min<long long>((long long)B * ipi_a, (long long)per_sm * sm_count());
+            SSD_CHECK_CUDA(launch_pdl(256, detect_floor_levels_kernel<21>, dim3(B), dim3(SC_T), 0, st, P, min_score, w.floor, w.flag_cnt, *dl));
+            SSD_CHECK_CUDA(launch_pdl(16, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, B, P, ipi_a, *dl, w.cand, capI, T));
+            SSD_CHECK_CUDA(launch_pdl(32, kw, dim3(B), dim3(NT), smem_sweep, st, fl, ipi_a, ipi_b, *dl, (const float4*)pri_cxcywh,
+                                      w.cand, w.scr_a, w.scr_b, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                      (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
+        } else {
+            auto ks = detect_stream_kernel<21, FROM_SCORES>;
+            auto kw = detect_sweep_kernel<21, FROM_SCORES>;
+            SSD_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+            SSD_CHECK_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sweep));
+            SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, (SCW + 1) * 32, smem_stream));
+            if (per_sm < 1) return SSDHEAD_E_UNSUPPORTED;
+            const int grid = (int)std::min<long long>((long long)B * ipi_a, (long long)per_sm * sm_count());
+            SSD_CHECK_CUDA(launch_pdl(256, detect_floor_kernel<21, FROM_SCORES>, dim3(B), dim3(SC_T), 0, st, conf, P, min_score, w.floor, w.flag_cnt));
+            SSD_CHECK_CUDA(launch_pdl(16, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, conf, B, P, ipi_a, w.cand, capI, T));
+            SSD_CHECK_CUDA(launch_pdl(32, kw, dim3(B), dim3(NT), smem_sweep, st, fl, conf, ipi_a, ipi_b, (const float4*)loc, (const float4*)pri_cxcywh,
+                                      w.cand, w.scr_a, w.scr_b, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                      (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
+        }
+        count_launch(3);
+        return 0;
     }
-    count_launch();
 
+    // the exhaustive route
+    const dim3 g1(T, B);
     if (dl) {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
+        SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
+                                  P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, *dl));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_levels_kernel, dim3(B), dim3(NT), smem_nms, st,
-                                  *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, (const unsigned short*)w.dir,
+                                  (const unsigned int*)w.dir_base, w.cand_cnt, w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     } else {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
+        SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
+                                  conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
-                                  (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, w.dir, w.dir_base, w.cand_cnt,
-                                  w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
+                                  (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, (const unsigned short*)w.dir,
+                                  (const unsigned int*)w.dir_base, w.cand_cnt, w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
                                   (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
     }
-    count_launch();
+    count_launch(2);
     return 0;
 }
 
@@ -1080,21 +1594,32 @@ int ssdhead_detect_levels(const ssdhead_levels* levels, const float* pri_cxcywh,
     if (!levels || levels->num_levels < 1 || levels->num_levels > MAX_LEVELS) return SSDHEAD_E_BADARG;
     DetLevels dl = {};
     dl.n = levels->num_levels;
-    int sum = 0, t0 = 0;
+    int sum = 0, t0 = 0, i0 = 0;
     for (int l = 0; l < dl.n; ++l) {
         const int n = levels->count[l];
         if (n <= 0 || !levels->conf[l] || !levels->loc[l]) return SSDHEAD_E_BADARG;
         if (!aligned16(levels->loc[l])) return SSDHEAD_E_ALIGN;             // float4 rows; conf rows may sit anywhere
-        dl.cnt[l] = n; dl.start[l] = sum; dl.tile0[l] = t0;
+        dl.cnt[l] = n; dl.start[l] = sum; dl.tile0[l] = t0; dl.item0[l] = i0;
         dl.conf[l] = levels->conf[l]; dl.loc[l] = levels->loc[l];
         sum += n;
         t0 += (n + SC_T - 1) / SC_T;
+        i0 += (n + RCW * 32 - 1) / (RCW * 32);
     }
-    for (int l = dl.n; l <= MAX_LEVELS; ++l) { dl.start[l] = sum; dl.tile0[l] = t0; }
+    for (int l = dl.n; l <= MAX_LEVELS; ++l) { dl.start[l] = sum; dl.tile0[l] = t0; dl.item0[l] = i0; }
     if (sum != P) return SSDHEAD_E_BADARG;
     return run_detect<false>(nullptr, nullptr, pri_cxcywh, B, P, C, min_score, iou_thr, top_k, img_wh,
                              out_boxes, out_prob, out_cls, out_prior, out_cnt, ws, ws_bytes, max_candidates,
                              (cudaStream_t)stream, &dl);
+}
+
+int ssdhead_detect_fallbacks(const void* ws, size_t ws_bytes, int B, int P, int C, int max_candidates, int32_t* host_count, void* stream)
+{
+    if (!ws || !host_count || B <= 0 || P <= 0 || C < 2 || max_candidates < 0) return SSDHEAD_E_BADARG;
+    DetectWs w;
+    if (ws_bytes < detect_ws_layout(B, P, C, max_candidates, &w, const_cast<void*>(ws))) return SSDHEAD_E_WORKSPACE;
+    SSD_CHECK_CUDA(cudaMemcpyAsync(host_count, w.flag_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SSD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
 }
 
 #ifdef SSDHEAD_PHASE_TIMES

@@ -83,10 +83,6 @@ __device__ __forceinline__ float row_cross_entropy(const float* __restrict__ row
     return __fadd_rn(ce, 0.0f);                  // -0.0 -> +0.0 so the bit pattern orders like the value
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------
 // Natural match fused into the streaming kernel (Losses.py:150-157): the consumer thread that scores prior p of
 // image b also finds the best gt of that prior (T1) and takes part in the per-gt arg-max over priors (T2, merged with

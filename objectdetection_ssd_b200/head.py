@@ -427,6 +427,17 @@ def _detect(head: MultiboxHead, a: torch.Tensor, b: torch.Tensor, min_score: flo
     return out
 
 
+def detect_fallbacks(head: MultiboxHead, B: int, max_candidates: int = 0) -> int:
+    """Images of the LAST detect call with this batch size that the short-list route could not decide (they were served
+    by the exhaustive kernels; the output is the same either way).  Synchronises the stream."""
+    import ctypes
+    ws = head._workspace(_lib.WS_DETECT, B, int(max_candidates))
+    n = ctypes.c_int32(-1)
+    _lib.check(head.lib.ssdhead_detect_fallbacks(_ptr(ws), ws.numel(), B, head.P, head.C, int(max_candidates),
+                                                 ctypes.addressof(n), _stream(head.dev)), "ssdhead_detect_fallbacks")
+    return int(n.value)
+
+
 def detect(head: MultiboxHead, loc, conf, min_score=0.2, iou_thr=0.45, top_k=200, img_wh=None, max_candidates=0):
     return _detect(head, loc, conf, min_score, iou_thr, top_k, img_wh, max_candidates, False)
 

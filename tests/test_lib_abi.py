@@ -35,7 +35,7 @@ def test_ctypes_table_covers_the_header(lib):
 
 def test_metadata_entry_points(lib):
     from objectdetection_ssd_b200 import _lib
-    assert lib.ssdhead_abi_version() == 3
+    assert lib.ssdhead_abi_version() == 4
     assert lib.ssdhead_error_string(0) == b"ok"
     assert b"workspace" in lib.ssdhead_error_string(-3)
     assert lib.ssdhead_workspace_bytes(_lib.WS_MATCH, 32, 8732, 21, 200) > 0

@@ -29,7 +29,10 @@ def run(B, bias, steps=50, warm=5, top_k=200):
     for i in range(steps): step(i)
     e1.record(); torch.cuda.synchronize()
     tt = e0.elapsed_time(e1) / steps
-    print(json.dumps(dict(B=B, bias=bias, step_us=round(tt * 1e3, 1), img_per_s=round(B / (tt * 1e-3)),
+    import ctypes
+    nfb = ctypes.c_int32(-1)
+    lib.ssdhead_detect_fallbacks(ws.data_ptr(), ws.numel(), B, P, 21, 0, ctypes.addressof(nfb), st)
+    print(json.dumps(dict(B=B, bias=bias, fallbacks=nfb.value, step_us=round(tt * 1e3, 1), img_per_s=round(B / (tt * 1e-3)),
                           frac_of_6538=round(B * 878800 / (tt * 1e-3) / 1e9 / 6538.6, 4), cnt=on[:4].tolist())))
 
 if __name__ == "__main__":
