@@ -38,7 +38,14 @@ namespace ssdhead {
 #ifdef SSDHEAD_PHASE_TIMES      // developer build: SM clock at the phase boundaries of the first image's sweep CTA
 __device__ long long g_phase[16];
 #define PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase[i] = clock64(); } while (0)
+// stream kernel, per CTA: [0] items, [1] consumer warp 0: clocks waiting for item data, [2] clocks working on rows,
+// [3] producer: clocks waiting for a free stage, [4] clocks of its bookkeeping, [5] [6] global timer at start / end,
+// [7] clocks of the sampling prologue
+__device__ long long g_stream[2048][8];
+__device__ __forceinline__ long long gtimer() { long long v; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v)); return v; }
+#define STREAM_STAT(stmt) do { stmt; } while (0)
 #else
+#define STREAM_STAT(stmt) do { } while (0)
 #define PHASE(i) do { } while (0)
 #endif
 
@@ -66,8 +73,7 @@ struct DetectWs {
     unsigned int* cand_cnt;        // [B]       zero on entry, zero on exit
     unsigned int* overflow;        // [B]       zero on entry, zero on exit
     // short-list route (score floor from a sample of the rows)
-    float* floor;                  // [B]       score floor of the image (>= min_score), rewritten by every call
-    unsigned int* hist;            // [B][CBINS] keys of the short list per coarse rank bin; zero on entry, zero on exit
+    unsigned long long* floor;     // [B]       1 << 32 | bits of the image's score floor (>= min_score) once it is known; zero on entry, zero on exit
     unsigned int* flag_cnt;        // [1]       images whose short list did not decide the output (reset by the next call's sampling kernel)
     unsigned int* work;            // [2]       next score item, CTAs that left the stream kernel; zero on entry, zero on exit
 };
@@ -89,11 +95,10 @@ static size_t detect_ws_layout(int B, int P, int C, int n, DetectWs* w, void* ba
     void* p4 = take((size_t)B * T * 8);
     void* p5 = take((size_t)B * 4);
     void* p6 = take((size_t)B * 4);
-    void* p7 = take((size_t)B * 4);
-    void* p8 = take((size_t)B * CBINS * 4);
+    void* p7 = take((size_t)B * 8);
     void* p9 = take(16);
     void* p10 = take(16);
-    if (w) { w->floor = (float*)p7; w->hist = (unsigned int*)p8; w->flag_cnt = (unsigned int*)p9; w->work = (unsigned int*)p10; }
+    if (w) { w->floor = (unsigned long long*)p7; w->flag_cnt = (unsigned int*)p9; w->work = (unsigned int*)p10; }
     if (w) { w->cand = (unsigned long long*)p0; w->scr_a = (unsigned long long*)p1; w->scr_b = (unsigned long long*)p2;
              w->dir = (unsigned short*)p3; w->dir_base = (unsigned int*)p4;
              w->cand_cnt = (unsigned int*)p5; w->overflow = (unsigned int*)p6; }
@@ -388,6 +393,13 @@ detect_score_levels_kernel(int P, float min_score, int capI,
 // An item's keys go to a fixed segment of the image's list - 20 keys per row, at 20 x (first row) - so nothing can overflow.
 constexpr int SAMPLE_STRIDE = 35;     // coprime with the 4 / 6 priors per cell: every aspect ratio is sampled; SSD300: one row per thread
 constexpr int SAMPLE_TARGET = 46;     // sampled candidates above the floor: ~1600 listed keys per image
+#ifndef SSDHEAD_STREAM_CTAS
+#define SSDHEAD_STREAM_CTAS 4         // resident CTAs per SM the stream kernel is built for
+#endif
+#ifndef SSDHEAD_STREAM_STAGES
+#define SSDHEAD_STREAM_STAGES 2       // stages of its item ring (measured at batch 256: 2 x 4 CTAs 66.8 us, 3 x 3 67.9, 4 x 2 76.7, 2 x 5 82.2)
+#endif
+constexpr int SST = SSDHEAD_STREAM_STAGES;
 constexpr int SCW = 8;                // consumer warps of the stream kernel: items of 256 rows (the score tiles of the exhaustive route)
 constexpr int RCW = NT / 32 - 1;      // consumer warps when a sweep CTA lists its image again: items of 480 rows
 static_assert(SCW * 32 == SC_T, "the stream kernel's items are the exhaustive route's score tiles");
@@ -422,22 +434,24 @@ __device__ __forceinline__ float prob_again(const float* __restrict__ x, int q, 
     return FROM_SCORES ? x[q] : __fmul_rn(fast_exp_ftz(__fsub_rn(x[q], m)), inv);
 }
 
-template <int C, bool FROM_SCORES, bool LEVELS>
-__device__ __forceinline__ void
-detect_floor_body(const float* __restrict__ conf, int P, float min_score, float* __restrict__ floor_out,
-                  unsigned int* __restrict__ flag_cnt, const DetLevels* __restrict__ dl)
+// barrier of the first 256 threads of a CTA (the stream kernel's consumer warps), or of a whole 256-thread CTA
+template <bool NAMED> __device__ __forceinline__ void sync256() {
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+}
+
+// Score floor of image b from every SAMPLE_STRIDE-th row, by 256 threads (t = 0 .. 255); valid in thread 0.
+template <int C, bool FROM_SCORES, bool LEVELS, bool NAMED>
+__device__ __forceinline__ float
+sample_floor(const int b, const float* __restrict__ conf, int P, float min_score, const DetLevels* __restrict__ dl)
 {
     constexpr int NF = C - 1;
     __shared__ unsigned int s_h[CBINS];
     __shared__ unsigned int s_ws[SC_T / 32];
     __shared__ int s_r;
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     s_h[t] = 0u;
     if (t == 0) s_r = CBINS;
-    pdl_wait();                          // FIRST: whoever starts behind this grid may rely on everything before it being complete
-    pdl_trigger();
-    if (b == 0 && t == 0) flag_cnt[0] = 0u;
-    __syncthreads();
+    sync256<NAMED>();
     for (int r = t * SAMPLE_STRIDE; r < P; r += SC_T * SAMPLE_STRIDE) {
         const float* x = conf + ((size_t)b * P + r) * C;
         if (LEVELS) {
@@ -456,7 +470,7 @@ detect_floor_body(const float* __restrict__ conf, int P, float min_score, float*
             }
         }
     }
-    __syncthreads();
+    sync256<NAMED>();
     // the first rank bin (from the top) at which the sampled candidates reach the target: its lower edge is the floor
     const unsigned h = s_h[t];
     unsigned incl = h;
@@ -466,33 +480,19 @@ detect_floor_body(const float* __restrict__ conf, int P, float min_score, float*
         if (lane >= d) incl += o;
     }
     if (lane == 31) s_ws[warp] = incl;
-    __syncthreads();
+    sync256<NAMED>();
 #pragma unroll
     for (int w = 0; w < SC_T / 32; ++w) if (w < warp) incl += s_ws[w];
     if (incl >= (unsigned)SAMPLE_TARGET && incl - h < (unsigned)SAMPLE_TARGET) s_r = t;
-    __syncthreads();
-    if (t == 0) {
-        float F = min_score;             // too few candidates in the sample: list everything (the exhaustive semantics)
-        const int r = s_r;
-        if (r < CBINS - 1) {
-            const float edge = __uint_as_float(((0x3f800000u >> 18) - (unsigned)r) << 18);
-            if (edge > min_score) F = edge;
-        }
-        floor_out[b] = F;
+    sync256<NAMED>();
+    float F = min_score;                 // too few candidates in the sample: list everything (the exhaustive semantics)
+    const int r = s_r;
+    if (r < CBINS - 1) {
+        const float edge = __uint_as_float(((0x3f800000u >> 18) - (unsigned)r) << 18);
+        if (edge > min_score) F = edge;
     }
-}
-
-template <int C, bool FROM_SCORES>
-__global__ void __launch_bounds__(SC_T)
-detect_floor_kernel(const float* __restrict__ conf, int P, float min_score, float* __restrict__ floor_out, unsigned int* __restrict__ flag_cnt)
-{
-    detect_floor_body<C, FROM_SCORES, false>(conf, P, min_score, floor_out, flag_cnt, nullptr);
-}
-template <int C>
-__global__ void __launch_bounds__(SC_T)
-detect_floor_levels_kernel(int P, float min_score, float* __restrict__ floor_out, unsigned int* __restrict__ flag_cnt, const __grid_constant__ DetLevels dl)
-{
-    detect_floor_body<C, false, true>(nullptr, P, min_score, floor_out, flag_cnt, &dl);
+    sync256<NAMED>();                    // s_r / s_h are reused by the next image
+    return F;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -968,8 +968,7 @@ static size_t nms_smem_bytes(int NF, int top_k, int T)
 // FLOOR: the short-list route (the image's keys sit in one fixed segment per score item + a coarse histogram) instead
 // of the exhaustive route's chunks and directory; fl.* are used by it alone.
 struct FloorArgs {
-    float* floor;                  // [B]
-    unsigned int* hist;            // [B][CBINS]
+    unsigned long long* floor;     // [B] valid flag << 32 | floor bits: one word, so a reader needs no second load and no fence
     unsigned int* icnt;            // [B][items per image] keys listed by each item
     unsigned int* work;            // [2]
     unsigned int* flag_cnt;        // [1] images listed twice (statistic)
@@ -1037,15 +1036,35 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
     int* oc = out_cls + (size_t)b * top_k;
     int* oi = out_prior ? out_prior + (size_t)b * top_k : nullptr;
 
+    int fl_n = 0;                                            // keys in the image's short list
     if (FLOOR) {
-        // the image's coarse prefix sums from the histogram the listing counted its keys into (left zeroed)
-        unsigned h = 0u;
-        if (t < CBINS) {
-            h = (unsigned)ld_cg_s32(reinterpret_cast<const int*>(fl.hist) + (size_t)b * CBINS + t);
-            if (h) fl.hist[(size_t)b * CBINS + t] = 0u;
+        // the items' key counts: where every item's segment starts in the list and in the flat numbering of the image's keys
+        const unsigned n_j = t < il.n ? (unsigned)ld_cg_s32(reinterpret_cast<const int*>(fl.icnt) + (size_t)b * T + t) : 0u;
+        unsigned ntot;
+        const unsigned off_j = block_excl_scan(n_j, ss.wsum, ntot);
+        if (t < il.n) { s_coff[t] = off_j; s_cbase[t] = (unsigned)item_first_row<LEVELS>(dl, il.rows, t) * (unsigned)NF; }
+        fl_n = (int)ntot;
+        __syncthreads();
+        // one pass over the keys: the image's coarse histogram (s_col was zeroed above) -> prefix sums
+        for (int f0 = 0; f0 < fl_n; f0 += 4 * NT) {
+            unsigned long long kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + u * NT + t;
+                kk[u] = 0ull;
+                if (f < fl_n) {
+                    int lo = 0, hi = il.n - 1;
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_coff[mid] <= (unsigned)f) lo = mid; else hi = mid - 1; }
+                    kk[u] = ld_cg_u64(seg + s_cbase[lo] + ((unsigned)f - s_coff[lo]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f0 + u * NT + t < fl_n) atomicAdd(&s_col[coarse_rank((unsigned)(kk[u] >> 32))], 1u);
         }
+        __syncthreads();
         unsigned total;
-        const unsigned ex = block_excl_scan(h, ss.wsum, total);
+        const unsigned ex = block_excl_scan(t < CBINS ? s_col[t] : 0u, ss.wsum, total);
         if (t < CBINS) s_CS[t] = ex;
         if (t == 0) s_CS[CBINS] = total;
         __syncthreads();
@@ -1123,15 +1142,27 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
             // the short list is unordered: one pass over its keys picks the slice's (the sort below orders them)
             if (t == 0) s_gcnt = 0u;
             __syncthreads();
-            for (int j = warp; j < il.n; j += NT / 32) {
-                const int n_j = ld_cg_s32(reinterpret_cast<const int*>(fl.icnt) + (size_t)b * T + j);
-                const unsigned long long* sj = seg + (size_t)item_first_row<LEVELS>(dl, il.rows, j) * NF;
-                for (int i = lane; i < n_j; i += 32) {
-                    const unsigned long long k = ld_cg_u64(sj + i);
-                    const int r = coarse_rank((unsigned)(k >> 32));
+            // flat key f sits in the item whose range of the flat numbering holds f (binary search over the items' offsets);
+            // four keys per thread are requested before any is looked at
+            for (int f0 = 0; f0 < fl_n; f0 += 4 * NT) {
+                unsigned long long kk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = f0 + u * NT + t;
+                    kk[u] = 0ull;
+                    if (f < fl_n) {
+                        int lo = 0, hi = il.n - 1;
+                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_coff[mid] <= (unsigned)f) lo = mid; else hi = mid - 1; }
+                        kk[u] = ld_cg_u64(seg + s_cbase[lo] + ((unsigned)f - s_coff[lo]));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (f0 + u * NT + t >= fl_n) continue;
+                    const int r = coarse_rank((unsigned)(kk[u] >> 32));
                     if (r >= rc0 && r < rc1) {
-                        X[atomicAdd(&s_gcnt, 1u)] = k;
-                        if (pre) atomicAdd(&s_cnt[bin0(k)], 1u);
+                        X[atomicAdd(&s_gcnt, 1u)] = kk[u];
+                        if (pre) atomicAdd(&s_cnt[bin0(kk[u])], 1u);
                     }
                 }
             }
@@ -1262,113 +1293,170 @@ detect_nms_levels_kernel(const __grid_constant__ DetLevels dl, const float4* __r
 // NCW = 8 consumer warps) and by a sweep CTA that lists its image again (its own items, NCW = 15): warp NCW's lane 0 is
 // the producer, warps 0 .. NCW-1 consume.  `ring`: 2 x NCW x 32 rows of shared memory.  Items w in [w_begin, w_end) drawn
 // from *counter (global) or counted privately (counter == nullptr); item w = image w / ipi, item w % ipi of that image.
-template <int C, bool FROM_SCORES, bool LEVELS, int NCW>
+// SAMPLE (stream kernel only): before their first item the consumer warps compute the floors of the images
+// blockIdx.x, blockIdx.x + gridDim.x, ... and publish them (floor[b], then ready[b] with release) - while the producer's
+// first copies are already in flight; a producer that needs the floor of an image waits for its flag.  Every CTA of the
+// grid is resident (the grid is sized with the occupancy query) and no CTA waits before its own images are published, so
+// the flags always arrive.
+struct ItemDesc {                  // what the producer tells the consumers about the item in a stage
+    int item;                      // -1: no more items
+    int b, r0, nrows, bulk;
+    float F;
+    const float* src;
+};
+
+// one consumer warp's 32 rows of an item: class mask against the floor, the warp's place in the item's segment (one
+// shared-memory atomic), keys to global memory.  `x`: the lane's row (shared or global memory - two instantiations, so
+// the compiler knows the address space)
+template <int C, bool FROM_SCORES, typename Ptr>
 __device__ __forceinline__ void
-score_items(unsigned char* ring, unsigned int* counter, const int w_begin, const int w_end, const int ipi, const bool wait_pdl,
-            const float* __restrict__ floor, const float f_const,
+score_rows(Ptr x, const bool valid, const float F, const int prior, unsigned int* s_icnt_st, unsigned long long* __restrict__ seg0)
+{
+    constexpr int NF = C - 1;
+    unsigned cmask = 0u;
+    float m = 0.0f, inv = 1.0f;
+    if (valid) {
+        float e[C];
+        row_probs<C, FROM_SCORES>(x, e, m, inv);
+#pragma unroll
+        for (int q = 0; q < NF; ++q) cmask |= ((FROM_SCORES ? e[q] : __fmul_rn(e[q], inv)) >= F ? 1u : 0u) << q;
+    }
+    if (cmask) {                                             // about one lane in five: its keys' place in the item's segment
+        unsigned long long* seg = seg0 + atomicAdd(s_icnt_st, (unsigned)__popc(cmask));
+        do {
+            const int q = __ffs(cmask) - 1;
+            cmask &= cmask - 1u;
+            *seg++ = make_key(prob_again<FROM_SCORES>(x, q, m, inv), q, prior);
+        } while (cmask);
+    }
+}
+
+template <int C, bool FROM_SCORES, bool LEVELS, int NCW, int NST, bool SAMPLE>
+__device__ __forceinline__ void
+score_items(unsigned char* ring, unsigned int* counter, const int w_begin, const int w_end, const int ipi, const int B,
+            unsigned long long* __restrict__ floor, const float f_const,
             const float* __restrict__ conf, const int P, const DetLevels* __restrict__ dl,
-            unsigned long long* __restrict__ cand, const int capI, unsigned int* __restrict__ icnt, const int icnt_stride,
-            unsigned int* __restrict__ hist)
+            unsigned long long* __restrict__ cand, const int capI, unsigned int* __restrict__ icnt, const int icnt_stride)
 {
     constexpr int NF = C - 1;
     constexpr int ROWS = NCW * 32;
     constexpr uint32_t STAGE_BYTES = ROWS * C * 4;
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ __align__(8) uint64_t s_empty[2];
-    __shared__ int s_desc[2];                                // item in the stage, or -1: no more items
-    __shared__ unsigned int s_icnt[2];                       // keys the stage's item has listed so far
-    __shared__ int s_it[2];                                  // item whose key count is still to be published, per stage
+    __shared__ __align__(8) uint64_t s_full[NST];
+    __shared__ __align__(8) uint64_t s_empty[NST];
+    __shared__ ItemDesc s_desc[NST];
+    __shared__ unsigned int s_icnt[NST];                     // keys the stage's item has listed so far
+    __shared__ int s_it[NST];                                // item whose key count is still to be published, per stage
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) {
-        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], NCW); mbar_init(&s_empty[1], NCW);
+#pragma unroll
+        for (int q = 0; q < NST; ++q) { mbar_init(&s_full[q], 1); mbar_init(&s_empty[q], NCW); s_icnt[q] = 0u; s_it[q] = -1; }
         mbar_fence_init();
-        s_icnt[0] = 0u; s_icnt[1] = 0u; s_it[0] = -1; s_it[1] = -1;
     }
     __syncthreads();
     int st = 0;
     uint32_t ph = 0u;
     if (warp == NCW) {
         if (lane == 0) {
-            unsigned wnext = counter ? atomicAdd(counter, 1u) : (unsigned)w_begin;
+            // Nothing the producer needs per item may cost it a round trip to L2 - it serves the whole CTA: the index of
+            // the item after the next (w2) and the floor word of the next item (fw1) are requested one item ahead.
+            unsigned w1 = counter ? atomicAdd(counter, 1u) : (unsigned)w_begin;
+            unsigned w2 = counter ? atomicAdd(counter, 1u) : w1 + 1u;
+            unsigned long long fw1 = 0ull;
+            if (SAMPLE && (int)w1 < w_end) fw1 = ld_relaxed_gpu_u64(floor + (int)w1 / ipi);
+#ifdef SSDHEAD_PHASE_TIMES
+            long long pw = 0, pb = 0, pc0, pc1;
+            if (SAMPLE && blockIdx.x < 2048) g_stream[blockIdx.x][5] = gtimer();
+#endif
             for (;;) {
+                STREAM_STAT(pc0 = clock64());
                 mbar_wait(&s_empty[st], ph ^ 1u);            // the stage is free: the item that was in it is complete
+                STREAM_STAT(pc1 = clock64(); pw += pc1 - pc0);
                 const int fin = s_it[st];
                 if (fin >= 0) icnt[(size_t)(fin / ipi) * icnt_stride + fin % ipi] = s_icnt[st];
                 s_it[st] = -1;
                 s_icnt[st] = 0u;
-                const int d = (int)wnext < w_end ? (int)wnext : -1;
-                s_desc[st] = d;
+                const int d = (int)w1 < w_end ? (int)w1 : -1;
+                s_desc[st].item = d;
                 if (d < 0) { mbar_arrive(&s_full[st]); break; }
+                const int b = d / ipi;
                 int r0, nrows; const float* src;
-                item_rows<C, LEVELS, ROWS>(conf, P, d / ipi, d % ipi, dl, r0, nrows, src);
+                item_rows<C, LEVELS, ROWS>(conf, P, b, d - b * ipi, dl, r0, nrows, src);
                 const uint32_t bytes = (uint32_t)nrows * C * 4u;
-                if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0) {
-                    mbar_expect_tx(&s_full[st], bytes);
-                    bulk_g2s(ring + (size_t)st * STAGE_BYTES, src, bytes, &s_full[st]);
-                } else {
-                    mbar_arrive(&s_full[st]);                // rows not 16-byte aligned: the consumers read them from global memory
-                }
+                const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0;
+                // the copy first (its bytes are counted on the barrier whenever they land; the phase cannot complete before
+                // this thread's own arrival below), then everything else the consumers need to know
+                if (bulk) bulk_g2s(ring + (size_t)st * STAGE_BYTES, src, bytes, &s_full[st]);
                 s_it[st] = d;
-                wnext = counter ? atomicAdd(counter, 1u) : wnext + 1u;     // the next index travels while this item is processed
-                st ^= 1; if (st == 0) ph ^= 1u;
+                float F = f_const;
+                if (SAMPLE) {
+                    int spins = 0;
+                    while ((fw1 >> 32) == 0ull) {            // the image's floor is still being sampled (first items of a call only)
+                        if (++spins > (1 << 22)) __trap();   // seconds: fail loudly, do not hang
+                        fw1 = ld_relaxed_gpu_u64(floor + b);
+                    }
+                    F = __uint_as_float((unsigned)fw1);
+                }
+                s_desc[st].b = b; s_desc[st].r0 = r0; s_desc[st].nrows = nrows; s_desc[st].bulk = bulk ? 1 : 0;
+                s_desc[st].F = F; s_desc[st].src = src;
+                if (bulk) mbar_expect_tx(&s_full[st], bytes); else mbar_arrive(&s_full[st]);   // not 16-byte aligned: the consumers read global memory
+                w1 = w2;
+                if (SAMPLE && (int)w1 < w_end) fw1 = ld_relaxed_gpu_u64(floor + (int)w1 / ipi);
+                w2 = counter ? atomicAdd(counter, 1u) : w2 + 1u;
+                if (++st == NST) { st = 0; ph ^= 1u; }
+                STREAM_STAT(pb += clock64() - pc1);
             }
+#ifdef SSDHEAD_PHASE_TIMES
+            if (SAMPLE && blockIdx.x < 2048) { g_stream[blockIdx.x][3] = pw; g_stream[blockIdx.x][4] = pb; }
+#endif
         }
         __syncwarp();
     } else if (warp < NCW) {
-        if (wait_pdl) pdl_wait();                            // the floors are final
+        if (SAMPLE) {
+            pdl_wait();                                      // (the stream kernel is the first kernel of a call)
+#ifdef SSDHEAD_PHASE_TIMES
+            const long long sc0 = clock64();
+#endif
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                const float F = sample_floor<C, FROM_SCORES, LEVELS, true>(b, conf, P, f_const, dl);
+                if (t == 0) st_relaxed_gpu_u64(floor + b, (1ull << 32) | (unsigned long long)__float_as_uint(F));   // one word: flag and value
+            }
+#ifdef SSDHEAD_PHASE_TIMES
+            if (t == 0 && blockIdx.x < 2048) g_stream[blockIdx.x][7] = clock64() - sc0;
+#endif
+        }
+#ifdef SSDHEAD_PHASE_TIMES
+        long long cw = 0, cr = 0, cn = 0, cc0, cc1;
+#endif
         for (;;) {
+            STREAM_STAT(cc0 = clock64());
             mbar_wait(&s_full[st], ph);
-            const int d = s_desc[st];
+            STREAM_STAT(cc1 = clock64(); cw += cc1 - cc0);
+            const int d = s_desc[st].item;
             if (d < 0) break;
-            const int b = d / ipi, j = d % ipi;
-            const float F = floor ? __ldcg(floor + b) : f_const;
-            int r0, nrows; const float* src;
-            item_rows<C, LEVELS, ROWS>(conf, P, b, j, dl, r0, nrows, src);
-            const uint32_t bytes = (uint32_t)nrows * C * 4u;
-            const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15u) == 0;
+            const int b = s_desc[st].b, r0 = s_desc[st].r0;
             const int row = warp * 32 + lane;
-            const float* x = bulk ? reinterpret_cast<const float*>(ring + (size_t)st * STAGE_BYTES) + row * C : src + (size_t)row * C;
-            unsigned cmask = 0u;
-            float m = 0.0f, inv = 1.0f;
-            if (row < nrows) {
-                float e[C];
-                row_probs<C, FROM_SCORES>(x, e, m, inv);
-#pragma unroll
-                for (int q = 0; q < NF; ++q) cmask |= ((FROM_SCORES ? e[q] : __fmul_rn(e[q], inv)) >= F ? 1u : 0u) << q;
-            }
-            // the warp's place in the item's segment: one shared-memory atomic
-            const unsigned mine = (unsigned)__popc(cmask);
-            unsigned incl = mine;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const unsigned o = __shfl_up_sync(FULL, incl, dd);
-                if (lane >= dd) incl += o;
-            }
-            const unsigned wtotal = __shfl_sync(FULL, incl, 31);
-            if (wtotal) {
-                unsigned base = 0u;
-                if (lane == 31) base = atomicAdd(&s_icnt[st], wtotal);
-                base = __shfl_sync(FULL, base, 31);
-                unsigned long long* seg = cand + (size_t)b * capI + (size_t)r0 * NF + (base + incl - mine);
-                unsigned int* hb = hist + (size_t)b * CBINS;
-                while (cmask) {
-                    const int q = __ffs(cmask) - 1;
-                    cmask &= cmask - 1u;
-                    const float p = prob_again<FROM_SCORES>(x, q, m, inv);
-                    *seg++ = make_key(p, q, r0 + row);
-                    atomicAdd(&hb[coarse_rank(__float_as_uint(p))], 1u);
-                }
+            const bool valid = row < s_desc[st].nrows;
+            unsigned long long* seg0 = cand + (size_t)b * capI + (size_t)r0 * NF;
+            if (s_desc[st].bulk) {
+                extern __shared__ __align__(16) unsigned char smem_ring[];      // == ring: the address space is known here
+                score_rows<C, FROM_SCORES>(reinterpret_cast<const float*>(smem_ring + (size_t)st * STAGE_BYTES) + row * C, valid,
+                                           s_desc[st].F, r0 + row, &s_icnt[st], seg0);
+            } else {
+                score_rows<C, FROM_SCORES>(s_desc[st].src + (size_t)row * C, valid, s_desc[st].F, r0 + row, &s_icnt[st], seg0);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[st]);        // release: the warp's keys and its count are ordered before the producer's read
-            st ^= 1; if (st == 0) ph ^= 1u;
+            if (++st == NST) { st = 0; ph ^= 1u; }
+            STREAM_STAT(cr += clock64() - cc1; ++cn);
         }
+#ifdef SSDHEAD_PHASE_TIMES
+        if (SAMPLE && t == 0 && blockIdx.x < 2048) { long long* g = g_stream[blockIdx.x]; g[0] = cn; g[1] = cw; g[2] = cr; g[6] = gtimer(); }
+#endif
     }
     __syncthreads();                                         // every consumer warp has left: all items are complete
     if (t == NCW * 32) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < NST; ++q)
             if (s_it[q] >= 0) icnt[(size_t)(s_it[q] / ipi) * icnt_stride + s_it[q] % ipi] = s_icnt[q];
     }
     __syncthreads();
@@ -1381,9 +1469,11 @@ detect_stream_body(const FloorArgs fl, const float* __restrict__ conf, const int
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
-    // conf is final before this grid starts (the sampling kernel in front of it is an ordinary launch) and the previous call
-    // is complete: the producer starts at once, only the consumers wait for the floors
-    score_items<C, FROM_SCORES, LEVELS, SCW>(smem_raw, fl.work, 0, B * ipi, ipi, true, fl.floor, 0.0f, conf, P, dl, cand, capI, fl.icnt, icnt_stride, fl.hist);
+    // An ordinary launch: everything in front of this call is complete, so the producer requests conf at once while the
+    // consumer warps sample the floors.
+    if (blockIdx.x == 0 && threadIdx.x == 0) fl.flag_cnt[0] = 0u;
+    score_items<C, FROM_SCORES, LEVELS, SCW, SST, true>(smem_raw, fl.work, 0, B * ipi, ipi, B, fl.floor, fl.min_score,
+                                                   conf, P, dl, cand, capI, fl.icnt, icnt_stride);
     // the last CTA to leave resets the work counters (every other CTA has drawn its last index by then)
     if (threadIdx.x == 0) {
         const unsigned e = atomicAdd(&fl.work[1], 1u);
@@ -1392,14 +1482,14 @@ detect_stream_body(const FloorArgs fl, const float* __restrict__ conf, const int
 }
 
 template <int C, bool FROM_SCORES>
-__global__ void __launch_bounds__((SCW + 1) * 32, 4)
+__global__ void __launch_bounds__((SCW + 1) * 32, SSDHEAD_STREAM_CTAS)
 detect_stream_kernel(const FloorArgs fl, const float* __restrict__ conf, const int B, const int P, const int ipi,
                      unsigned long long* __restrict__ cand, const int capI, const int icnt_stride)
 {
     detect_stream_body<C, FROM_SCORES, false>(fl, conf, B, P, ipi, nullptr, cand, capI, icnt_stride);
 }
 template <int C>
-__global__ void __launch_bounds__((SCW + 1) * 32, 4)
+__global__ void __launch_bounds__((SCW + 1) * 32, SSDHEAD_STREAM_CTAS)
 detect_stream_levels_kernel(const FloorArgs fl, const int B, const int P, const int ipi, const __grid_constant__ DetLevels dl,
                             unsigned long long* __restrict__ cand, const int capI, const int icnt_stride)
 {
@@ -1419,7 +1509,9 @@ detect_sweep_body(const FloorArgs fl, const float* __restrict__ conf, const int 
     const int b = blockIdx.x;
     pdl_trigger();
     pdl_wait();                                              // the stream kernel's short lists are complete
-    const ItemLayout la = {SC_T, ipi_a, __ldcg(fl.floor + b) > fl.min_score};
+    const ItemLayout la = {SC_T, ipi_a, __uint_as_float((unsigned)ld_cg_u64(fl.floor + b)) > fl.min_score};
+    __syncthreads();
+    if (threadIdx.x == 0) fl.floor[b] = 0ull;
     if (detect_nms_body<FROM_SCORES, LEVELS, true>(b, fl, la, dl, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, nullptr, nullptr, nullptr, nullptr,
                                                    img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt))
         return;
@@ -1428,8 +1520,8 @@ detect_sweep_body(const FloorArgs fl, const float* __restrict__ conf, const int 
     if (threadIdx.x == 0) atomicAdd(fl.flag_cnt, 1u);
     fence_proxy_async_smem();                                // the sweep wrote the ring's bytes with ordinary stores
     __syncthreads();
-    score_items<C, FROM_SCORES, LEVELS, RCW>(smem_raw, nullptr, b * ipi_b, (b + 1) * ipi_b, ipi_b, false, nullptr, fl.min_score,
-                                             conf, P, dl, cand, capI, fl.icnt, T, fl.hist);
+    score_items<C, FROM_SCORES, LEVELS, RCW, 2, false>(smem_raw, nullptr, b * ipi_b, (b + 1) * ipi_b, ipi_b, 0, nullptr, fl.min_score,
+                                                    conf, P, dl, cand, capI, fl.icnt, T);
     const ItemLayout lb = {RCW * 32, ipi_b, false};
     detect_nms_body<FROM_SCORES, LEVELS, true>(b, fl, lb, dl, loc_or_boxes, pri_cxcywh, cand, scr_a, scr_b, nullptr, nullptr, nullptr, nullptr,
                                                img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
@@ -1460,11 +1552,16 @@ detect_sweep_levels_kernel(const FloorArgs fl, const int ipi_a, const int ipi_b,
                                       img_wh, P, NF, T, capI, top_k, iou_thr, out_boxes, out_prob, out_cls, out_prior, out_cnt);
 }
 
-// SSDHEAD_DETECT_SHORTLIST=0 forces the exhaustive route (developer switch: the two routes give identical outputs)
-static bool shortlist_enabled()
+// Which route serves a call.  SSDHEAD_DETECT_SHORTLIST=0 forces the exhaustive route, =1 the short-list route (the two give
+// identical outputs; read per call so that tests can compare them in one process).  Unset: the short-list route from
+// ~900 k rows per call (batch 104 of SSD300) - measured on B200, batch 256 / 128 / 64 / 32 / 8 / 1: short list 65.9 /
+// 49.8 / 43.1 / 38.7 / 34.1 / 26.7 us, exhaustive 85.0 / 52.9 / 36.8 / 29.3 / 22.5 / 21.4 us (small batches pay the
+// sampling prologue and the sweep's extra pass over the keys without having the rows to amortise them).
+static bool shortlist_enabled(int B, int P)
 {
-    const char* e = getenv("SSDHEAD_DETECT_SHORTLIST");          // read per call: tests compare the two routes in one process
-    return !e || atoi(e) != 0;
+    const char* e = getenv("SSDHEAD_DETECT_SHORTLIST");
+    if (e) return atoi(e) != 0;
+    return (long long)B * P >= 900000;
 }
 
 static int sm_count()
@@ -1496,17 +1593,17 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (ws_bytes < need) return SSDHEAD_E_WORKSPACE;
     const int capI = detect_cap_image(P, C, n_cap);
     // the short-list route gives every row its 20 key slots in the image's list (a max_candidates below P rules it out)
-    const bool fast = shortlist_enabled() && capI == NF * P && (long long)B * T < (1ll << 30);
+    const bool fast = shortlist_enabled(B, P) && capI == NF * P && (long long)B * T < (1ll << 30);
 
     if (fast) {
         const int ipi_a = T;                                                  // 256-row items = the score tiles
         const int ipi_b = dl ? dl->item0[dl->n] : (P + RCW * 32 - 1) / (RCW * 32);
-        const FloorArgs fl = {w.floor, w.hist, w.dir_base, w.work, w.flag_cnt, min_score};
-        const size_t smem_stream = (size_t)2 * SCW * 32 * C * 4;
+        const FloorArgs fl = {w.floor, w.dir_base, w.work, w.flag_cnt, min_score};
+        const size_t smem_stream = (size_t)SST * SCW * 32 * C * 4;
         const size_t smem_sweep = std::max(smem_nms, (size_t)2 * RCW * 32 * C * 4);
         int per_sm = 0;
-        // sample -> floor (an ordinary launch: everything in front of this call is complete when it starts, which is what
-        // lets the stream kernel's producers request conf at once); stream kernel: short lists; sweep kernel
+        // stream kernel (an ordinary launch: everything in front of this call is complete when it starts, which is what lets its
+        // producers request conf at once): floors + short lists; sweep kernel
         if (dl) {
             auto ks = detect_stream_levels_kernel<21>;
             auto kw = detect_sweep_levels_kernel<21>;
@@ -1515,8 +1612,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
             SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, (SCW + 1) * 32, smem_stream));
             if (per_sm < 1) return SSDHEAD_E_UNSUPPORTED;
             const int grid = (int)std::min<long long>((long long)B * ipi_a, (long long)per_sm * sm_count());
-            SSD_CHECK_CUDA(launch_pdl(256, detect_floor_levels_kernel<21>, dim3(B), dim3(SC_T), 0, st, P, min_score, w.floor, w.flag_cnt, *dl));
-            SSD_CHECK_CUDA(launch_pdl(16, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, B, P, ipi_a, *dl, w.cand, capI, T));
+            SSD_CHECK_CUDA(launch_pdl(256, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, B, P, ipi_a, *dl, w.cand, capI, T));
             SSD_CHECK_CUDA(launch_pdl(32, kw, dim3(B), dim3(NT), smem_sweep, st, fl, ipi_a, ipi_b, *dl, (const float4*)pri_cxcywh,
                                       w.cand, w.scr_a, w.scr_b, img_wh, P, NF, T, capI, top_k, iou_thr,
                                       (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
@@ -1528,13 +1624,12 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
             SSD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, (SCW + 1) * 32, smem_stream));
             if (per_sm < 1) return SSDHEAD_E_UNSUPPORTED;
             const int grid = (int)std::min<long long>((long long)B * ipi_a, (long long)per_sm * sm_count());
-            SSD_CHECK_CUDA(launch_pdl(256, detect_floor_kernel<21, FROM_SCORES>, dim3(B), dim3(SC_T), 0, st, conf, P, min_score, w.floor, w.flag_cnt));
-            SSD_CHECK_CUDA(launch_pdl(16, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, conf, B, P, ipi_a, w.cand, capI, T));
+            SSD_CHECK_CUDA(launch_pdl(256, ks, dim3(grid), dim3((SCW + 1) * 32), smem_stream, st, fl, conf, B, P, ipi_a, w.cand, capI, T));
             SSD_CHECK_CUDA(launch_pdl(32, kw, dim3(B), dim3(NT), smem_sweep, st, fl, conf, ipi_a, ipi_b, (const float4*)loc, (const float4*)pri_cxcywh,
                                       w.cand, w.scr_a, w.scr_b, img_wh, P, NF, T, capI, top_k, iou_thr,
                                       (float4*)out_boxes, out_prob, out_cls, out_prior, out_cnt));
         }
-        count_launch(3);
+        count_launch(2);
         return 0;
     }
 
@@ -1624,6 +1719,7 @@ int ssdhead_detect_fallbacks(const void* ws, size_t ws_bytes, int B, int P, int 
 
 #ifdef SSDHEAD_PHASE_TIMES
 int ssdhead_debug_phases(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, g_phase, sizeof(long long) * 16); }
+int ssdhead_debug_stream(long long* out, int n_ctas) { return (int)cudaMemcpyFromSymbol(out, g_stream, sizeof(long long) * 8 * (size_t)n_ctas); }
 #endif
 
 }  // extern "C"

@@ -192,3 +192,43 @@ def test_levels_entry_takes_the_same_routes():
     assert nfb == 0
     _same(a, b)
     _same(a, c)
+
+
+def test_the_stage_isolated_suite_under_the_forced_short_list_route():
+    """tests/test_gpu_detect.py runs its small batches on the exhaustive route (the automatic choice below ~900 k rows);
+    here the same exact-equality tests - ties, heavy suppression through every slice, random shapes, unaligned prior
+    counts, suppression chains - run with the short-list route forced."""
+    import tests.test_gpu_detect as D
+    with _route(True):
+        for args in ((8.0, 0.01, 4), (6.0, 0.01, 2), (6.0, 0.2, 3), (2.0, 0.05, 2)):
+            D.test_detect_from_scores_exact(*args)
+        D.test_detect_fewer_than_topk_is_class_major_unsorted()
+        D.test_detect_no_candidates_and_ties()
+        D.test_detect_small_topk_and_pixel_scale()
+        D.test_detect_ssd512_priors()
+        D.test_detect_end_to_end_close()
+        D.test_detect_heavy_suppression_runs_through_every_slice()
+        D.test_detect_quantised_scores_tie_across_classes_and_priors()
+        D.test_detect_unaligned_prior_count_takes_the_plain_load_path()
+        D.test_detect_randomised_differential()
+        D.test_detect_suppression_chains_and_sparse_overlaps()
+
+
+def test_automatic_route_choice_by_call_size():
+    """Unset switch: small calls take the exhaustive route (which can report an overflowed candidate cap), large calls the
+    short list; both equal the forced routes."""
+    from objectdetection_ssd_b200.head import detect
+    pri = H.priors()
+    head = _head(pri)
+    old = os.environ.pop("SSDHEAD_DETECT_SHORTLIST", None)
+    try:
+        for B in (3, 120):
+            loc, conf = H.detect_inputs(61, B, pri.shape[0], bg_bias=6.0)
+            auto = detect(head, loc, conf, 0.01, 0.45, 200)
+            with _route(B < 100):
+                other = detect(head, loc, conf, 0.01, 0.45, 200)
+            torch.cuda.synchronize()
+            _same(auto, other)
+    finally:
+        if old is not None:
+            os.environ["SSDHEAD_DETECT_SHORTLIST"] = old
