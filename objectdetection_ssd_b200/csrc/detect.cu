@@ -1037,6 +1037,7 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
     int* oi = out_prior ? out_prior + (size_t)b * top_k : nullptr;
 
     int fl_n = 0;                                            // keys in the image's short list
+    bool fl_parked = false;                                  // ... and they sit in s_buf_b (until the first sort uses it as scratch)
     if (FLOOR) {
         // the items' key counts: where every item's segment starts in the list and in the flat numbering of the image's keys
         const unsigned n_j = t < il.n ? (unsigned)ld_cg_s32(reinterpret_cast<const int*>(fl.icnt) + (size_t)b * T + t) : 0u;
@@ -1044,6 +1045,7 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
         const unsigned off_j = block_excl_scan(n_j, ss.wsum, ntot);
         if (t < il.n) { s_coff[t] = off_j; s_cbase[t] = (unsigned)item_first_row<LEVELS>(dl, il.rows, t) * (unsigned)NF; }
         fl_n = (int)ntot;
+        fl_parked = fl_n <= SL;
         __syncthreads();
         // one pass over the keys: the image's coarse histogram (s_col was zeroed above) -> prefix sums
         for (int f0 = 0; f0 < fl_n; f0 += 4 * NT) {
@@ -1060,7 +1062,10 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (f0 + u * NT + t < fl_n) atomicAdd(&s_col[coarse_rank((unsigned)(kk[u] >> 32))], 1u);
+                if (f0 + u * NT + t < fl_n) {
+                    atomicAdd(&s_col[coarse_rank((unsigned)(kk[u] >> 32))], 1u);
+                    if (fl_parked) s_buf_b[f0 + u * NT + t] = kk[u];     // the first slice is picked out of shared memory
+                }
         }
         __syncthreads();
         unsigned total;
@@ -1142,6 +1147,17 @@ detect_nms_body(const int b, const FloorArgs fl, const ItemLayout il,
             // the short list is unordered: one pass over its keys picks the slice's (the sort below orders them)
             if (t == 0) s_gcnt = 0u;
             __syncthreads();
+            if (fl_parked) {
+                for (int f = t; f < fl_n; f += NT) {
+                    const unsigned long long k = s_buf_b[f];
+                    const int r = coarse_rank((unsigned)(k >> 32));
+                    if (r >= rc0 && r < rc1) {
+                        X[atomicAdd(&s_gcnt, 1u)] = k;
+                        if (pre) atomicAdd(&s_cnt[bin0(k)], 1u);
+                    }
+                }
+                fl_parked = false;
+            } else
             // flat key f sits in the item whose range of the flat numbering holds f (binary search over the items' offsets);
             // four keys per thread are requested before any is looked at
             for (int f0 = 0; f0 < fl_n; f0 += 4 * NT) {
