@@ -608,6 +608,15 @@ def time_detect(args, rank, world, dev, sampler, B, steps, warmup, workload="det
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     r = dict(ms_total=ms, launches=launches, kern_ms=None, B=B, steps=steps, P=P, algo=algo_bytes(P, "detect"),
              kernel="detect kernels (whole step)", detections=int(out["cnt"].clamp(min=0).sum()))
+    import ctypes
+    nfb = ctypes.c_int32(-1)
+    _lib.check(lib.ssdhead_detect_fallbacks(ws.data_ptr(), ws.numel(), B, P, C, 0, ctypes.addressof(nfb), st), "ssdhead_detect_fallbacks")
+    env = os.environ.get("SSDHEAD_DETECT_SHORTLIST")
+    shortlist = (int(env) != 0) if env else B * P >= 900000           # the library's own rule (csrc/detect.cu, shortlist_enabled)
+    r["detect_route"] = {"route": "short list (sampled score floor; stream kernel + sweep kernel)" if shortlist
+                         else "exhaustive (score kernel + sweep kernel)",
+                         "images_listed_twice_in_last_step": int(nfb.value),
+                         "note": "identical outputs on both routes; chosen by call size unless SSDHEAD_DETECT_SHORTLIST is set"}
     if e2e:
         # end to end: host buffers in, detections out
         ctx = SSDHeadContext(pri.numpy(), max_batch=B, device=dev.index)
@@ -820,6 +829,8 @@ def run_ours(args):
         line["roofline"] = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                             "traffic": None, "kernel": r["kernel"],
                             "note": "whole step: algorithmic bytes of the step / step time", "peak_source": peak_src}
+    if "detect_route" in r:
+        line["detect_route"] = r["detect_route"]
     if "losses" in r:
         line["loss"] = r["losses"]
     if "sharded_check" in r:

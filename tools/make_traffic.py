@@ -59,10 +59,13 @@ tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (aver
                               algo=256 * (P * C * 4 + P * 4 + P + P * (C + 4) * 4)),
       "mine_b256": entry(loss, "mine_kernel", "one CTA per image: forced-match override, exact top-k mining, sparse gradient rows, loss sums; "
                          "re-reads ~300 conf rows + loc/prior rows per image, its gradient rows stay in L2"),
-      "detect_score_b64": entry(d64, "detect_score", "B=64, bias +6: conf only; the keys it writes stay in L2 for the sweep", algo=64 * P * C * 4),
-      "detect_nms_b64": entry(d64, "detect_nms", "B=64: one CTA per image, latency-bound"),
-      "detect_score_b256": entry(d256, "detect_score", "B=256, bias +6: issue-bound, not HBM-bound", algo=256 * P * C * 4),
-      "detect_nms_b256": entry(d256, "detect_nms", "B=256")}
+      "detect_score_b64": entry(d64, "detect_score", "B=64, bias +6, exhaustive route (the automatic choice at this size): conf only; the keys it "
+                                "writes stay in L2 for the sweep", algo=64 * P * C * 4),
+      "detect_nms_b64": entry(d64, "detect_nms", "B=64, exhaustive route: one CTA per image, latency-bound"),
+      "detect_stream_b256": entry(d256, "detect_stream", "B=256, bias +6, short-list route: floors sampled in the prologue, then conf once through the "
+                                  "item ring; ~1600 keys per image written", algo=256 * P * C * 4),
+      "detect_sweep_b256": entry(d256, "detect_sweep", "B=256, short-list route: one CTA per image, latency-bound")}
+tj = {k: v for k, v in tj.items() if v is not None}
 with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
     json.dump(tj, f, indent=1)
 print(json.dumps({k: (v and {kk: v[kk] for kk in ("dram_bytes_per_launch", "ncu_time_us", "warp_instructions")}) for k, v in tj.items() if isinstance(v, dict)}, indent=1))
