@@ -101,7 +101,9 @@ struct FusedMatch {
     unsigned long long* best_key;
     int* npos_acc;
     unsigned short* obj_u16;     // nullable: natural best gt (local index) of every prior, for batches with many gts per image
-};
+    const float* seed_lb;        // batches with many gts per image (else nullptr): a lower bound of every gt's best IoU
+    int sumG;                    // (match_seed_kernel); a warp skips the gts that can neither make one of its priors positive
+};                               // nor be best matched by one of them
 
 // Everything the match of one row needs from global memory, fetched ONE TILE AHEAD so the two dependent L2 round trips
 // (gt offsets -> gt boxes) and the prior box are in flight while the previous tile is being scored.
@@ -192,6 +194,22 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
         wx2 = fmaxf(wx2, __shfl_xor_sync(FULL, wx2, d));
         wy2 = fmaxf(wy2, __shfl_xor_sync(FULL, wy2, d));
     }
+    // Many gts per image (m.cull): IoU(prior, gt) <= min(area) / max(area), so with [amin, amax] the areas of the warp's
+    // priors no pair of the warp with gt g can exceed ub(g) = 1 if area_g lies inside, area_g / amin below, amax / area_g
+    // above.  A gt whose ub is below BOTH pos_iou (it cannot make a prior of the warp positive - the only use of the
+    // per-prior maximum) and the gt's seed (match_seed_kernel: the IoU of a real prior, so strictly smaller values cannot
+    // win the arg-max; ties keep the rule of the atomicMax) is skipped; the margin covers the rounding of the fp32 IoU.
+    // The seeds are read-only during this kernel: cached loads next to the gt boxes, no extra round trip to L2.
+    float amin = 0.0f, amax = 0.0f;
+    if (m.seed_lb) {
+        amin = valid ? pa : __int_as_float(0x7f800000);
+        amax = valid ? pa : 0.0f;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            amin = fminf(amin, __shfl_xor_sync(FULL, amin, d));
+            amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, d));
+        }
+    }
     for (int bb = pre.b_first; bb <= pre.b_last; ++bb) {     // one image per warp except where a warp straddles two
         const bool first = (bb == pre.b_first);
         const int off0 = first ? pre.off0 : m.gt_off[bb];
@@ -212,9 +230,15 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
             }
             const float myarea = box_area(mybox);
             int chunk_best = -1;
+            bool useful = true;
+            if (m.seed_lb && lane < gc) {
+                const float lb = __ldg(m.seed_lb + off0 + g0 + lane);                           // 0: no overlap in the sample
+                const float ub = myarea < amin ? __fdiv_rn(myarea, amin) : (myarea > amax ? __fdiv_rn(amax, myarea) : 1.0f);
+                useful = !(__fmul_rn(ub, 1.00002f) < fminf(m.pos_iou, lb));
+            }
             // lanes whose gt can touch the warp's priors (the warp owning prior 0 must visit every gt: an all-zero
             // IoU row resolves to prior 0)
-            unsigned todo = __ballot_sync(FULL, lane < gc && (owns_p0 || (mybox.z > wx1 && mybox.x < wx2 && mybox.w > wy1 && mybox.y < wy2)));
+            unsigned todo = __ballot_sync(FULL, lane < gc && (owns_p0 || (useful && mybox.z > wx1 && mybox.x < wx2 && mybox.w > wy1 && mybox.y < wy2)));
             while (todo) {
                 const int g = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -255,6 +279,42 @@ __device__ __forceinline__ void fused_match_rows(const FusedMatch& m, unsigned r
         m.cls_u8[row] = (uint8_t)c;                                               // natural class; forced matches patched later
         if (m.obj_u16) m.obj_u16[row] = (unsigned short)obj_mine;
         if (c != m.bg_class) atomicAdd(&m.npos_acc[b], 1);
+    }
+}
+
+// Batches with many gts per image: a lower bound of every gt's best IoU - its best IoU over every SEED_STRIDE-th prior.
+// One warp per gt.  The fused match then skips, per warp, the gts whose IoU with its priors cannot reach that bound.
+// The sampled priors are staged in shared memory once per CTA (every warp of the grid walks all of them); a warp then
+// takes gts in turn.
+constexpr int SEED_STRIDE = 16;                              // (stress shape: stride 8 / 16 / 32 leaves 8.0 / 8.6 / 10.3 of 23.2 gts per warp to visit)
+constexpr int SEED_CAP = 65536;                              // gts of a batch the cull has seeds for (a fixed tail of the loss workspace:
+                                                             // written before it is read, so it needs no cleaning)
+constexpr int SEED_MAX = 8192;                               // sampled priors held in shared memory (128 KB)
+__global__ void __launch_bounds__(256)
+match_seed_kernel(const float4* __restrict__ gt_xyxy, const float4* __restrict__ pri_xyxy, int sumG, int nsamp, int stride,
+                  float* __restrict__ seed_lb)
+{
+    extern __shared__ __align__(16) float4 s_pri[];
+    const int t = threadIdx.x, lane = t & 31;
+    for (int i = t; i < nsamp; i += 256) s_pri[i] = pri_xyxy[(size_t)i * stride];
+    __syncthreads();
+    for (int g = blockIdx.x * 8 + (t >> 5); g < sumG; g += gridDim.x * 8) {
+        const float4 gb = gt_xyxy[g];
+        const float ga = box_area(gb);
+        float best = 0.0f;
+#pragma unroll 4
+        for (int i = lane; i < nsamp; i += 32) {
+            const float4 pb = s_pri[i];
+            const float dx = __fsub_rn(fminf(gb.z, pb.z), fmaxf(gb.x, pb.x));
+            const float dy = __fsub_rn(fminf(gb.w, pb.w), fmaxf(gb.y, pb.y));
+            if (dx > 0.0f && dy > 0.0f) {                    // the fused match's own expression: the same bits
+                const float inter = __fmul_rn(dx, dy);
+                best = fmaxf(best, __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, box_area(pb)), inter)));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, d));
+        if (lane == 0) seed_lb[g] = best;
     }
 }
 
@@ -1332,7 +1392,8 @@ size_t loss_workspace_bytes(int B, int P, int C)
 {
     if (mine_smem_bytes(P) > 220 * 1024 || P >= 65536) return 0;   // P <= ~31 000 priors
     return 16 + round_up((size_t)B * 2 * sizeof(double), 16) + round_up((size_t)B * P * sizeof(float), 16) +
-           round_up((size_t)B * P * sizeof(unsigned short), 16);      // CE, then the best-gt map of large-G batches
+           round_up((size_t)B * P * sizeof(unsigned short), 16) +     // CE, then the best-gt map of large-G batches,
+           (size_t)SEED_CAP * sizeof(float);                           // then the seeds of the fused match's cull
 }
 
 // rows workspace of the resident-gradient step: one record per image, the same for every batch size - int32 rows,
@@ -1366,6 +1427,16 @@ static int launch_ce_stream(const float* conf, float* ce, float* grad_conf, floa
     const int use_tma = (aligned16(conf) && (!GRADS || (aligned16(grad_conf) && aligned16(grad_loc)))) ? 1 : 0;
     const long long tiles = (rows + CE_ROWS - 1) / CE_ROWS;
     const int grid_ce = (int)std::min<long long>(tiles, (long long)CE_CTAS * num_sms());
+    if (MATCH && fm.seed_lb) {
+        const int stride = std::max(SEED_STRIDE, (fm.P + SEED_MAX - 1) / SEED_MAX);
+        const int nsamp = (fm.P + stride - 1) / stride;
+        const size_t smem_seed = (size_t)nsamp * 16;
+        SSD_CHECK_CUDA(cudaFuncSetAttribute(match_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_seed));
+        const int grid_seed = std::min((fm.sumG + 7) / 8, 2 * num_sms());
+        match_seed_kernel<<<grid_seed, 256, smem_seed, st>>>(fm.gt_xyxy, fm.pri_xyxy, fm.sumG, nsamp, stride, const_cast<float*>(fm.seed_lb));
+        SSD_LAUNCH_CHECK();
+        count_launch();
+    }
     SSD_CHECK_CUDA(launch_pdl(1, kce, dim3(grid_ce), dim3(CE_THREADS), smem_ce, st, conf, ce, grad_conf, grad_loc, rows, use_tma, fm));
     count_launch();
     return 0;
@@ -1434,12 +1505,21 @@ static int launch_mine_fin(MineParams prm, cudaStream_t st)
 }
 
 static float* ws_ce(void* ws, int B) { return (float*)((char*)ws + 16 + round_up((size_t)B * 2 * sizeof(double), 16)); }
+static float* ws_seed(void* ws, int B, int P) { return (float*)((char*)ws_ce(ws, B) + round_up((size_t)B * P * sizeof(float), 16) + round_up((size_t)B * P * sizeof(unsigned short), 16)); }
 static unsigned short* ws_obj(void* ws, int B, int P) { return (unsigned short*)((char*)ws_ce(ws, B) + round_up((size_t)B * P * sizeof(float), 16)); }
 // The walk over an image's gts in the mining kernel costs G x ~25 instructions per positive row, on the latency chain
 // of the step's last kernel; the streaming kernel can record the best gt of every prior instead (2 bytes per row, +1 %
 // of its traffic) and the walk disappears.  Measured at 1-10 gts per image: 112.4 -> 111.5 us per step at B=256 with the
 // map, 671 -> 565 us at 100 gts per image - so the map is used whenever a gt index fits its 16 bits
 // (SSDHEAD_OBJ_MAP_MIN=<average gts per image> restores a threshold for experiments).
+// The seeded cull of the fused match pays from a few dozen gts per image (the stress shape has 100); the ordinary
+// batches (<= 10 gts per image) keep the plain loop.  SSDHEAD_MATCH_CULL_MIN overrides the average gt count it starts at.
+static bool match_cull_enabled(int B, int sumG)
+{
+    static const int min_avg = getenv("SSDHEAD_MATCH_CULL_MIN") ? atoi(getenv("SSDHEAD_MATCH_CULL_MIN")) : 24;
+    return B > 0 && sumG >= (long long)min_avg * B && sumG <= SEED_CAP;
+}
+
 static bool use_obj_map(int B, int sumG)
 {
     static const int min_avg = getenv("SSDHEAD_OBJ_MAP_MIN") ? atoi(getenv("SSDHEAD_OBJ_MAP_MIN")) : 0;
@@ -1502,6 +1582,7 @@ static int ce_match_stream_impl(const float* conf, const float* gt_xyxy, const f
     FusedMatch fm;
     fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
     fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc; fm.obj_u16 = obj_u16;
+    fm.sumG = sumG; fm.seed_lb = match_cull_enabled(B, sumG) ? ws_seed(ws_loss, B, P) : nullptr;
     float* ce_buf = ce ? ce : ws_ce(ws_loss, B);
     const long long rows = (long long)B * P;
     const int rc = grad_loc ? launch_ce_stream<21, true, true>(conf, ce_buf, grad_conf, grad_loc, rows, fm, st)
@@ -1708,6 +1789,7 @@ static int step_levels_common(const ssdhead_levels* levels,
     FusedMatch fm;
     fm.gt_xyxy = (const float4*)gt_xyxy; fm.gt_cls = gt_cls; fm.gt_off = gt_off; fm.pri_xyxy = (const float4*)pri_xyxy;
     fm.P = P; fm.bg_class = C - 1; fm.pos_iou = pos_iou; fm.cls_u8 = cls_u8; fm.best_key = best_key; fm.npos_acc = npos_acc; fm.obj_u16 = use_obj_map(B, sumG) ? ws_obj(ws_loss, B, P) : nullptr;
+    fm.sumG = sumG; fm.seed_lb = nullptr;                    // (per-level layout: not seeded)
 
     MineParams prm = {};
     prm.loc = nullptr; prm.conf = nullptr; prm.cls_u8 = cls_u8;
