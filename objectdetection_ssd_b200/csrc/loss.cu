@@ -1516,7 +1516,8 @@ static unsigned short* ws_obj(void* ws, int B, int P) { return (unsigned short*)
 // batches (<= 10 gts per image) keep the plain loop.  SSDHEAD_MATCH_CULL_MIN overrides the average gt count it starts at.
 static bool match_cull_enabled(int B, int sumG)
 {
-    static const int min_avg = getenv("SSDHEAD_MATCH_CULL_MIN") ? atoi(getenv("SSDHEAD_MATCH_CULL_MIN")) : 24;
+    const char* e = getenv("SSDHEAD_MATCH_CULL_MIN");          // read per call: a test compares the two paths in one process
+    const int min_avg = e ? atoi(e) : 24;
     return B > 0 && sumG >= (long long)min_avg * B && sumG <= SEED_CAP;
 }
 

@@ -341,3 +341,52 @@ def test_many_gt_per_image_slow_paths(counts):
     assert torch.equal(m["cls_u8"], out["cls_u8"]) and torch.equal(m["npos"], out["npos"])
     assert torch.equal(gcf, out["grad_conf"]) and torch.equal(gl, out["grad_loc"])
     assert torch.equal(losses, out["losses"])
+
+
+def test_seeded_cull_of_the_fused_match_changes_nothing():
+    """Batches with many gts per image skip, per warp, the gts whose area ratio with the warp's priors can reach neither
+    pos_iou nor a sampled lower bound of the gt's best IoU (csrc/loss.cu, match_seed_kernel).  With the cull forced on
+    and forced off the step must produce the same bits: class map, best priors, positive counts, losses, gradients -
+    for an ordinary batch, for many gts per image (tiny, huge and degenerate boxes included), and for ties."""
+    import os
+    from objectdetection_ssd_b200 import synth
+    from objectdetection_ssd_b200.head import PackedGT
+    pri = H.priors()
+    P = pri.shape[0]
+    head = _head(pri)
+    cases = []
+    loc, conf, tb, tc = H.train_inputs(95, 6, P)                                   # ordinary: 1..10 gts per image
+    cases.append((loc, conf, tb, tc))
+    gb, gc = synth.make_gt(96, 3, 60, 100)                                         # many gts per image
+    tb = [torch.from_numpy(b).clone() for b in gb]
+    tc = [torch.from_numpy(c) for c in gc]
+    tb[0][0] = torch.tensor([0.50, 0.50, 0.505, 0.505])                            # tiny
+    tb[0][1] = torch.tensor([0.0, 0.0, 1.0, 1.0])                                  # the whole image
+    tb[0][2] = torch.tensor([0.3, 0.3, 0.3001, 0.6])                               # a sliver
+    tb[1][0] = tb[1][1].clone()                                                    # two identical gts (T2 / T3 ties)
+    tb[2][5] = torch.cat([pri[4000, :2] - pri[4000, 2:] / 2, pri[4000, :2] + pri[4000, 2:] / 2])   # exactly a prior
+    l2, c2 = synth.make_head(97, 3, P)
+    cases.append((torch.from_numpy(l2), torch.from_numpy(c2), tb, tc))
+    old = os.environ.get("SSDHEAD_MATCH_CULL_MIN")
+    try:
+        for loc, conf, tb, tc in cases:
+            outs = []
+            for setting in ("1", "1000000"):
+                os.environ["SSDHEAD_MATCH_CULL_MIN"] = setting
+                gt = PackedGT(tb, tc, head.dev)
+                outs.append(head.loss(loc.cuda(), conf.cuda(), gt, with_grads=True))
+                torch.cuda.synchronize()
+            a, b = outs
+            n = sum(int(x.shape[0]) for x in tb)
+            assert torch.equal(a["cls_u8"], b["cls_u8"]) and torch.equal(a["npos"], b["npos"])
+            assert torch.equal(a["best_prior"][:n], b["best_prior"][:n])
+            assert torch.equal(a["losses"], b["losses"]) and torch.equal(a["sums"], b["sums"])
+            assert torch.equal(a["grad_loc"], b["grad_loc"]) and torch.equal(a["grad_conf"], b["grad_conf"])
+        ref = O.multibox_loss(cases[1][0], cases[1][1], cases[1][2], cases[1][3], pri)      # and the oracle agrees
+        assert torch.equal(a["cls_u8"].cpu().long(), ref["cls"])
+        assert torch.equal(a["best_prior"][:n].cpu().long(), ref["best_prior"])
+    finally:
+        if old is None:
+            os.environ.pop("SSDHEAD_MATCH_CULL_MIN", None)
+        else:
+            os.environ["SSDHEAD_MATCH_CULL_MIN"] = old
