@@ -12,10 +12,10 @@
 // formulation produces can never reach the output.  If the list runs out with <= top_k boxes kept the output is
 // the class-major concatenation (Losses.py:71-73), produced by a stable partition of the kept list by class.
 //
-// Two routes with identical outputs.  The SHORT-LIST route (default; detect_floor_kernel + detect_stream_kernel +
-// detect_sweep_kernel, described at SAMPLE_STRIDE below) lists only the candidates above a sampled score floor and falls
-// back, per image and inside the sweep kernel, to the full list when that was not enough.  The EXHAUSTIVE route
-// (SSDHEAD_DETECT_SHORTLIST=0, or a max_candidates cap below P) lists every candidate:
+// Two routes with identical outputs.  The SHORT-LIST route (large calls; detect_stream_kernel + detect_sweep_kernel,
+// described at SAMPLE_STRIDE below) lists only the candidates above a sampled score floor and falls back, per image and
+// inside the sweep kernel, to the full list when that was not enough.  The EXHAUSTIVE route (small calls, a
+// max_candidates cap below P, or SSDHEAD_DETECT_SHORTLIST=0) lists every candidate:
 //   detect_score_kernel  grid (row tiles, B), 256 rows per CTA: the tile's conf rows arrive in shared memory with one
 //                        1-D TMA bulk copy (plain loads when unaligned), one thread per prior does the softmax and
 //                        appends a 64-bit key (prob bits << 32 | ~(class << 24 | prior)) to the image's candidate list
@@ -377,13 +377,15 @@ detect_score_levels_kernel(int P, float min_score, int capI,
 // ------------------------------------------------------------------------------------------------
 // Short-list route.  At min_score = 0.01 an image has tens of thousands of candidates, and the sweep stops after a few
 // hundred of them: listing all of them is what made the score kernel issue-bound.
-//   detect_floor_kernel   looks at every SAMPLE_STRIDE-th row of an image and picks a score FLOOR (an edge of the coarse
-//                         rank bins, >= min_score) above which about SAMPLE_STRIDE x SAMPLE_TARGET candidates are expected.
-//   detect_stream_kernel  persistent, warp-specialised: a producer lane draws 256-row ITEMS from a global counter and moves
-//                         them into a two-stage ring with bulk copies (full/empty mbarriers); 8 consumer warps work on their
-//                         own 32 rows without any CTA-wide barrier - thread-per-row softmax (the exhaustive route's
-//                         arithmetic), class mask against the image's floor, one shared-memory atomic per warp for its
-//                         place in the item's key segment, keys straight to global memory.  No dense passes, no directory.
+//   detect_stream_kernel  persistent, warp-specialised, 8 consumer warps + a producer lane.  Prologue: the consumer warps of
+//                         CTA c look at every SAMPLE_STRIDE-th row of the images c, c + grid, ... and pick each image's score
+//                         FLOOR (an edge of the coarse rank bins, >= min_score) above which about SAMPLE_STRIDE x
+//                         SAMPLE_TARGET candidates are expected - while the producer's first copies are in flight.  Main
+//                         loop: the producer draws 256-row ITEMS from a global counter and moves them into a two-stage ring
+//                         with bulk copies (full/empty mbarriers); a consumer warp works on its own 32 rows without any
+//                         CTA-wide barrier - thread-per-row softmax (the exhaustive route's arithmetic), class mask against
+//                         the image's floor, one shared-memory atomic per lane that holds a candidate for its place in the
+//                         item's key segment, keys straight to global memory.  No dense passes, no directory.
 //   detect_sweep_kernel   one CTA per image: the sweep of the exhaustive route on the short list.  A candidate's fate
 //                         depends only on higher-scored candidates, so if the sweep keeps top_k + 1 boxes inside the short
 //                         list - or the floor never rose above min_score - the output is the exhaustive route's, bit for
