@@ -344,12 +344,13 @@ __device__ __forceinline__ void
 detect_score_grid(const float* __restrict__ conf, int P, float min_score, int capI,
                   unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
                   unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
-                  unsigned int* __restrict__ overflow, const DetLevels* __restrict__ dl)
+                  unsigned int* __restrict__ overflow, const DetLevels* __restrict__ dl, unsigned int* __restrict__ flag_cnt)
 {
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
     pdl_trigger();                       // the sweep kernel may become resident; it waits for this grid to finish
     pdl_wait();                          // the previous call's sweep may still be reading the lists we overwrite
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *flag_cnt = 0u;   // ssdhead_detect_fallbacks: none on this route
     detect_score_body<C, FROM_SCORES, LEVELS>(blockIdx.y, blockIdx.x, gridDim.x, &s_bar, 0u, conf, P, min_score, capI,
                                               cand, cand_cnt, dir, dir_base, overflow, dl);
 }
@@ -359,9 +360,9 @@ __global__ void __launch_bounds__(SC_T)
 detect_score_kernel(const float* __restrict__ conf, int P, float min_score, int capI,
                     unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
                     unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
-                    unsigned int* __restrict__ overflow)
+                    unsigned int* __restrict__ overflow, unsigned int* __restrict__ flag_cnt)
 {
-    detect_score_grid<C, FROM_SCORES, false>(conf, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, nullptr);
+    detect_score_grid<C, FROM_SCORES, false>(conf, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, nullptr, flag_cnt);
 }
 
 template <int C>
@@ -369,9 +370,9 @@ __global__ void __launch_bounds__(SC_T)
 detect_score_levels_kernel(int P, float min_score, int capI,
                            unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_cnt,
                            unsigned short* __restrict__ dir, unsigned int* __restrict__ dir_base,
-                           unsigned int* __restrict__ overflow, const __grid_constant__ DetLevels dl)
+                           unsigned int* __restrict__ overflow, unsigned int* __restrict__ flag_cnt, const __grid_constant__ DetLevels dl)
 {
-    detect_score_grid<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl);
+    detect_score_grid<C, false, true>(nullptr, P, min_score, capI, cand, cand_cnt, dir, dir_base, overflow, &dl, flag_cnt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1377,6 +1378,7 @@ score_items(unsigned char* ring, unsigned int* counter, const int w_begin, const
         if (lane == 0) {
             // Nothing the producer needs per item may cost it a round trip to L2 - it serves the whole CTA: the index of
             // the item after the next (w2) and the floor word of the next item (fw1) are requested one item ahead.
+            if (SAMPLE) pdl_wait();                          // (no-op for the ordinary launch the stream kernel gets by default)
             unsigned w1 = counter ? atomicAdd(counter, 1u) : (unsigned)w_begin;
             unsigned w2 = counter ? atomicAdd(counter, 1u) : w1 + 1u;
             unsigned long long fw1 = 0ull;
@@ -1656,7 +1658,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     if (dl) {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_score_levels_kernel<21>, g1, dim3(SC_T), 0, st,
-                                  P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, *dl));
+                                  P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, w.flag_cnt, *dl));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_levels_kernel, dim3(B), dim3(NT), smem_nms, st,
                                   *dl, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, (const unsigned short*)w.dir,
                                   (const unsigned int*)w.dir_base, w.cand_cnt, w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,
@@ -1664,7 +1666,7 @@ static int run_detect(const float* loc, const float* conf, const float* pri_cxcy
     } else {
         SSD_CHECK_CUDA(cudaFuncSetAttribute(detect_nms_kernel<FROM_SCORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         SSD_CHECK_CUDA(launch_pdl(8, detect_score_kernel<21, FROM_SCORES>, g1, dim3(SC_T), 0, st,
-                                  conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow));
+                                  conf, P, min_score, capI, w.cand, w.cand_cnt, w.dir, w.dir_base, w.overflow, w.flag_cnt));
         SSD_CHECK_CUDA(launch_pdl(8, detect_nms_kernel<FROM_SCORES>, dim3(B), dim3(NT), smem_nms, st,
                                   (const float4*)loc, (const float4*)pri_cxcywh, w.cand, w.scr_a, w.scr_b, (const unsigned short*)w.dir,
                                   (const unsigned int*)w.dir_base, w.cand_cnt, w.overflow, img_wh, P, NF, T, capI, top_k, iou_thr,

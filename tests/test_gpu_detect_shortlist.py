@@ -104,6 +104,14 @@ def test_heavy_suppression_is_flagged_and_served_by_the_exhaustive_kernels():
         nfb = detect_fallbacks(head, 3)
     assert nfb == 0, nfb
     _check_exact(out, _oracle_stage(boxes, probs, 0.05, 0.45, 7), 7)
+    # the count describes the LAST call: a call on the exhaustive route after a call that needed the fallback reports 0
+    with _route(True):
+        detect_from_scores(head, boxes, probs, 0.05, 0.45, 200)
+        assert detect_fallbacks(head, 3) == 3
+    with _route(False):
+        out = detect_from_scores(head, boxes, probs, 0.05, 0.45, 200)
+        assert detect_fallbacks(head, 3) == 0
+    _check_exact(out, _oracle_stage(boxes, probs, 0.05, 0.45, 200), 200)
 
 
 def test_mixed_batch_only_the_undecided_images_take_the_fallback():
