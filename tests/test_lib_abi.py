@@ -45,6 +45,10 @@ def test_metadata_entry_points(lib):
     assert lib.ssdhead_workspace_bytes(_lib.WS_ROWS, 256, 8732, 21, 0) >= 256 * (8732 * 2 + 8)
     assert lib.ssdhead_workspace_bytes(_lib.WS_ROWS, 1, 70000, 21, 0) == 0           # row indices are 16 bits
     assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 1024) < lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 64, 8732, 21, 0)
+    # three key buffers of 20 keys per prior (every row of the short-list route owns its 20 slots: nothing can overflow)
+    assert lib.ssdhead_workspace_bytes(_lib.WS_DETECT, 256, 8732, 21, 0) >= 3 * 256 * 20 * 8732 * 8
+    # CE + best-gt map + the 65 536 seeds of the fused match's cull
+    assert lib.ssdhead_workspace_bytes(_lib.WS_LOSS, 128, 24564, 21, 0) >= 128 * 24564 * 6 + 65536 * 4
 
 
 def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
